@@ -1,0 +1,183 @@
+/*
+ * p2vit_b200 - C ABI of the B200 (sm_100a) kernels behind the P2-ViT quantized operator surface.
+ *
+ * The reference has no FFI: its hot path sits behind Python classes (models/ptq/__init__.py:2-3)
+ * whose forward() methods dispatch ATen ops.  Each entry point below replaces the ATen sequence
+ * of one of those call sites (cited per function, paths relative to the reference root); the
+ * Python classes in p2vit_b200/ptq bind them with ctypes (p2vit_b200/_lib.py).  See INTEGRATION.md
+ * for the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 = ok, non-zero = error (p2v_last_error() returns a static description);
+ *   - activations are int8 codes, token-major [rows, channels], channels contiguous;
+ *     weights are int8 codes [out_features, in_features] (nn.Linear layout), in_features contiguous;
+ *   - RNE = round-half-to-even (torch.round); "sat" = clamp to [-128,127] (bit_type.py:17-27);
+ *   - fp32 epilogue arithmetic is op-for-op IEEE (no FMA contraction, correctly rounded division)
+ *     so integer codes equal the reference's fake-quant results (quantizer/uniform.py:83-86,125).
+ */
+#ifndef P2VIT_B200_H_
+#define P2VIT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2V_ABI_VERSION 1
+
+int p2v_abi_version(void);
+const char* p2v_last_error(void);
+/* number of kernels this library has launched since load / since the last reset (bench: gpu_launches) */
+int64_t p2v_launch_count(void);
+void p2v_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * QAct  (models/ptq/layers.py:242-257, quantizer/uniform.py:48-126)
+ * q = sat(RNE(x / scale[c] + zp)), lo/hi given;  x_hat = (q - zp) * scale[c].
+ * `n_scale` is 1 (layer_wise) or C (channel_wise); `inner` = number of contiguous elements that
+ * share one channel (1 for [..,C] activations, H*W for NCHW inputs - base.py:14-31).
+ * ------------------------------------------------------------------------------------------- */
+int p2v_quantize_f32(const float* x, int8_t* q, int64_t n, int C, int64_t inner,
+                     const float* scale, int n_scale, float zp, int lo, int hi, void* stream);
+int p2v_fake_quant_f32(const float* x, float* y, int8_t* q_or_null, int64_t n, int C, int64_t inner,
+                       const float* scale, int n_scale, float zp, int lo, int hi, void* stream);
+int p2v_dequantize_i8(const int8_t* q, float* y, int64_t n, int C, int64_t inner,
+                      const float* scale, int n_scale, float zp, void* stream);
+
+/* qact_input fused with the patch gather of the k=stride=P convolution
+ * (vit_fquant.py:842-851, layers_quant.py:486-489, layers.py:96-103): fp32 image [B,Cin,H,W]
+ * -> int8 codes [B*(H/P)*(W/P), Cin*P*P] with K ordered (c,py,px) = QConv2d weight.reshape(D,-1). */
+int p2v_quantize_patchify(const float* img, int8_t* out, int B, int Cin, int H, int W, int P,
+                          float scale, float zp, int lo, int hi, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * QLinear / QConv2d(patch-embed) + the QAct(s) that follow it      (layers.py:202-209, 96-103)
+ *   acc[m,n] = sum_k A[m,k] * W[n,k]            int8 x int8 -> int32, tcgen05.mma kind::i8
+ *   y        = fl(acc * acc_scale[n] + bias[n])  (acc*acc_scale is exact for power-of-two scales)
+ * followed by one of the fused epilogues below.  Column vectors have N entries.
+ * ------------------------------------------------------------------------------------------- */
+typedef enum {
+  P2V_EPI_REQUANT = 0,   /* out_i8 = sat(RNE(y / out_scale[n]))            qkv->qact1 (vit_fquant.py:346-371), generic */
+  P2V_EPI_GELU = 1,      /* out_i8 = sat(RNE(gelu_erf(y) / out_scale[n]))  fc1->GELU->qact1 (layers_quant.py:360-375) */
+  P2V_EPI_RESIDUAL = 2,  /* c = sat(RNE(y/mid_scale[n])); z = fl(res[m,n]*res_scale[n]) + fl(c*mid_scale[n]);
+                            out_i8 = sat(RNE(z / out_scale[n]))            proj->qact3->+x->qact2, fc2->qact2->+x->qact4
+                            (vit_fquant.py:397-401,514-534,561-580; layers_quant.py:384-388) */
+  P2V_EPI_EMBED = 3,     /* c = sat(RNE(y/mid_scale[0])); e = sat(RNE(fl(c*mid_scale[0]) / aux_scale));
+                            v = fl(e*aux_scale) + pos[tok+1,n]; out row (b*(T+1)+tok+1) = sat(RNE(v / out_scale[n]))
+                            patch_embed.qact -> qact_embed -> +qact_pos(pos) -> qact1 (vit_fquant.py:851-869) */
+  P2V_EPI_DEQUANT = 4,   /* out_f32 = sat(RNE(y / out_scale[n])) * out_scale[n]; optional out_i8 codes
+                            head->act_out (vit_fquant.py:932-936) */
+  P2V_EPI_F32 = 5        /* out_f32 = y  (eager QLinear.forward result before the next QAct) */
+} p2v_epilogue_t;
+
+typedef struct {
+  int M, N, K;
+  const int8_t* A;          /* [M,K] */
+  const int8_t* W;          /* [N,K] */
+  int epilogue;             /* p2v_epilogue_t */
+  const float* acc_scale;   /* [N]  s_in * s_w[n] */
+  const float* bias;        /* [N] or NULL */
+  const int32_t* zp_corr;   /* [N] or NULL: zp_in * sum_k W[n,k], subtracted from acc (asymmetric inputs) */
+  const float* out_scale;   /* [N] */
+  const float* mid_scale;   /* [N] RESIDUAL: scale of the QAct directly after the GEMM; EMBED: [1] */
+  const float* res_scale;   /* [N] RESIDUAL: scale of the residual stream codes */
+  const int8_t* res;        /* [M,N] RESIDUAL: residual codes */
+  const float* pos;         /* EMBED: [(T+1),N] dequantized qact_pos(pos_embed) */
+  float aux_scale;          /* EMBED: qact_embed scale */
+  int tokens_per_image;     /* EMBED: T (196) */
+  int8_t* out_i8;           /* [M,N] (EMBED: [B*(T+1),N]) */
+  float* out_f32;           /* [M,N] DEQUANT / F32 */
+  int pot_scales;           /* 1: every divisor above is an exact power of two (division == exact multiply) */
+} p2v_gemm_args;
+
+int p2v_gemm_i8(const p2v_gemm_args* args_host, void* stream);
+/* same contract on CUDA cores (dp4a); used by tests to cross-check the tcgen05 kernel */
+int p2v_gemm_i8_simt(const p2v_gemm_args* args_host, void* stream);
+/* EMBED helper: writes the B class-token rows: out[b*(T+1), n] = cls_row[n] */
+int p2v_fill_cls_rows(int8_t* out, const int8_t* cls_row, int B, int T, int N, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * QIntLayerNorm 'int' mode + the QAct that consumes it     (layers.py:270-337; vit_fquant.py:519-524,
+ * 565-570, 905; layers_quant.py:349-356)
+ *   x      = codes[m,c] * in_mult[c]          in_mult = RNE(in_scale/min(in_scale)) in {1,2,4,8}
+ *   mean, std, A, M, N, B as the reference (fp32, op for op); row sums are exact integers
+ *   y_q    = RNE((sign(A)*M*x + B) / 2^N)                       (not clamped by the reference)
+ *   out_i8 = sat(RNE(fl(fl(y_q*out_scale[c]) / post_div[c]) / next_scale))
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int rows, C;
+  const int8_t* x;          /* [rows,C] */
+  int64_t x_row_stride;     /* bytes between rows (C, or (T+1)*C to pick the class token only) */
+  const float* in_mult;     /* [C] */
+  float in_scale_min;       /* s1 */
+  const float* gamma;       /* [C] */
+  const float* beta;        /* [C] */
+  const float* out_scale;   /* [C] LN output grid: next_qact.scale * channel_scale (or next_qact.scale) */
+  const float* post_div;    /* [C] smoothing divisor applied before the next QAct (1 if none) */
+  float next_scale;         /* scale of the QAct after the LN */
+  int pot_scales;           /* 1: out_scale, post_div, next_scale are powers of two */
+  int8_t* out_i8;           /* [rows,C] */
+  float* out_f32;           /* optional [rows,C]: y_q * out_scale (eager QIntLayerNorm.forward result) */
+} p2v_layernorm_args;
+
+int p2v_layernorm_int(const p2v_layernorm_args* args_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * QIntSoftmax (log2, 4 bit)                                         (layers.py:376-428)
+ * A 256-entry table of exp_int for x_int = -d (d = rowmax - code), built on the host with the
+ * reference's fp32 formulas (p2vit_b200/engine.py: build_softmax_lut), drives both the stand-alone
+ * kernel and the fused attention.  exp_int = hi*2^32 + lo exactly; exp_f32 = the same value in fp32.
+ * code = clamp(log_round(RNE(fl(sum)/exp_f32)), 0, 15); probability 2^-code, 0 when log_round >= 16
+ * (code 255 on the wire).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint32_t hi[256];
+  uint32_t lo[256];
+  float exp_f32[256];
+} p2v_softmax_lut;
+
+/* scores: int8 codes [rows, n]; out: u8 codes [rows, n] (0..15, 255 = zero probability) */
+int p2v_int_softmax_log2(const int8_t* scores, uint8_t* out, int64_t rows, int n,
+                         const p2v_softmax_lut* lut_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention core between qact1 and qact2                     (vit_fquant.py:373-389)
+ *   S = q k^T (int32);  c = sat(RNE(S * score_mult))  with score_mult = s_q^2 * head_scale / s_attn
+ *   p = int_softmax_log2(c);  O = sum_j 2^(15-code_j) * v_j (int32, exact)
+ *   out_i8 = sat(RNE(O * out_mult)),  out_mult = 2^-15 * s_v / s_out
+ * qkv: int8 [B, T, 3, H, dh] (the qkv QLinear output, qact1 codes); out: int8 [B, T, H*dh].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, T, H, dh;
+  const int8_t* qkv;
+  int8_t* out;
+  float score_mult;
+  float out_mult;
+  const p2v_softmax_lut* lut_dev;
+  uint8_t* probs_or_null;   /* optional dump of softmax codes [B,H,T,T] (tests) */
+  int8_t* scores_or_null;   /* optional dump of qact_attn1 codes [B,H,T,T] (tests) */
+} p2v_attention_args;
+
+int p2v_attention_i8(const p2v_attention_args* args_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Calibration observers                           (observer/minmax.py:15-32, ptf.py:13-30, base.py:16-29)
+ * per-channel min and max of x viewed as [C, n/C] with the reference's channel rule
+ * (`inner` as in p2v_quantize_f32).  minmax: float [2,C] (row 0 = min, row 1 = max),
+ * initialised by the kernel (not accumulated).
+ * ------------------------------------------------------------------------------------------- */
+int p2v_minmax_per_channel(const float* x, float* minmax, int64_t n, int C, int64_t inner, void* stream);
+/* sum over all elements of (x - fq_k(x))^2 for K candidate scales (minmax.py:165-201 activation case,
+ * omse.py:30-57, ptf.py:123-149): scales [K, n_scale]; out double [K, n_scale_out] where
+ * n_scale_out = C if per_channel_out else 1.  fq_k(x) = (sat_lo_hi(RNE(x/s + zp_k)) - zp_k) * s. */
+int p2v_quant_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales,
+                         const float* zps_or_null, int K, int n_scale, int per_channel_out,
+                         int lo, int hi, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P2VIT_B200_H_ */

@@ -1,0 +1,137 @@
+// extern "C" surface of libp2vit_b200.so (include/p2vit_b200.h): argument validation + launch.
+#include <cstdarg>
+#include <cstdio>
+#include <atomic>
+#include "common.cuh"
+
+namespace p2v {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return 2;
+  }
+  return 0;
+}
+
+int launch_gemm_simt(const p2v_gemm_args& a, cudaStream_t stream);
+int launch_gemm_tc(const p2v_gemm_args& a, cudaStream_t stream);
+int launch_quantize(const float* x, int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale,
+                    float zp, int lo, int hi, cudaStream_t stream);
+int launch_dequantize(const int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale, float zp,
+                      cudaStream_t stream);
+int launch_patchify(const float* img, int8_t* out, int B, int Cin, int H, int W, int P, float scale, float zp, int lo, int hi,
+                    cudaStream_t stream);
+int launch_fill_cls(int8_t* out, const int8_t* cls_row, int B, int T, int N, cudaStream_t stream);
+int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream);
+int launch_softmax(const int8_t* scores, uint8_t* out, int64_t rows, int n, const p2v_softmax_lut* lut, cudaStream_t stream);
+int launch_attention(const p2v_attention_args& a, cudaStream_t stream);
+int launch_minmax(const float* x, float* minmax, int64_t n, int C, int64_t inner, cudaStream_t stream);
+int launch_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales, const float* zps, int K, int n_scale,
+                      int per_channel_out, int lo, int hi, double* out, cudaStream_t stream);
+
+static int validate_gemm(const p2v_gemm_args* a) {
+  P2V_REQUIRE(a != nullptr, "gemm: null args");
+  P2V_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  P2V_REQUIRE(a->K % 16 == 0, "gemm: K=%d must be a multiple of 16 (TMA row pitch)", a->K);
+  P2V_REQUIRE(a->A && a->W && a->acc_scale, "gemm: A, W and acc_scale are required");
+  P2V_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->W) & 15) == 0,
+              "gemm: A and W must be 16-byte aligned");
+  const int e = a->epilogue;
+  P2V_REQUIRE(e >= P2V_EPI_REQUANT && e <= P2V_EPI_F32, "gemm: unknown epilogue %d", e);
+  if (e != P2V_EPI_F32) P2V_REQUIRE(a->out_scale != nullptr, "gemm: out_scale required");
+  if (e == P2V_EPI_F32 || e == P2V_EPI_DEQUANT) P2V_REQUIRE(a->out_f32 != nullptr, "gemm: out_f32 required");
+  else P2V_REQUIRE(a->out_i8 != nullptr, "gemm: out_i8 required");
+  if (e == P2V_EPI_RESIDUAL) P2V_REQUIRE(a->mid_scale && a->res_scale && a->res, "gemm: residual epilogue needs mid_scale, res_scale, res");
+  if (e == P2V_EPI_EMBED) P2V_REQUIRE(a->mid_scale && a->pos && a->tokens_per_image > 0 && a->M % a->tokens_per_image == 0,
+                                      "gemm: embed epilogue needs mid_scale, pos and M %% tokens_per_image == 0");
+  return 0;
+}
+
+}  // namespace p2v
+
+using namespace p2v;
+
+extern "C" {
+
+int p2v_abi_version(void) { return P2V_ABI_VERSION; }
+const char* p2v_last_error(void) { return g_err; }
+int64_t p2v_launch_count(void) { return g_launches.load(); }
+void p2v_reset_launch_count(void) { g_launches.store(0); }
+
+int p2v_quantize_f32(const float* x, int8_t* q, int64_t n, int C, int64_t inner, const float* scale, int n_scale, float zp,
+                     int lo, int hi, void* stream) {
+  P2V_REQUIRE(x && q && scale && n >= 0 && C > 0 && inner > 0 && (n_scale == 1 || n_scale == C), "quantize: bad arguments");
+  P2V_REQUIRE(lo >= -128 && hi <= 127, "quantize: int8 carrier holds [-128,127] only (lo=%d hi=%d)", lo, hi);
+  return launch_quantize(x, q, nullptr, n, C, inner, scale, n_scale, zp, lo, hi, (cudaStream_t)stream);
+}
+int p2v_fake_quant_f32(const float* x, float* y, int8_t* q, int64_t n, int C, int64_t inner, const float* scale, int n_scale,
+                       float zp, int lo, int hi, void* stream) {
+  P2V_REQUIRE(x && y && scale && n >= 0 && C > 0 && inner > 0 && (n_scale == 1 || n_scale == C), "fake_quant: bad arguments");
+  return launch_quantize(x, q, y, n, C, inner, scale, n_scale, zp, lo, hi, (cudaStream_t)stream);
+}
+int p2v_dequantize_i8(const int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale, float zp,
+                      void* stream) {
+  P2V_REQUIRE(q && y && scale && n >= 0 && C > 0 && inner > 0 && (n_scale == 1 || n_scale == C), "dequantize: bad arguments");
+  return launch_dequantize(q, y, n, C, inner, scale, n_scale, zp, (cudaStream_t)stream);
+}
+int p2v_quantize_patchify(const float* img, int8_t* out, int B, int Cin, int H, int W, int P, float scale, float zp, int lo,
+                          int hi, void* stream) {
+  P2V_REQUIRE(img && out && B > 0 && Cin > 0 && P > 0 && H % P == 0 && W % P == 0, "patchify: bad shape");
+  P2V_REQUIRE(P % 4 == 0 && W % 4 == 0, "patchify: P and W must be multiples of 4");
+  P2V_REQUIRE(lo >= -128 && hi <= 127, "patchify: int8 carrier only");
+  return launch_patchify(img, out, B, Cin, H, W, P, scale, zp, lo, hi, (cudaStream_t)stream);
+}
+int p2v_gemm_i8(const p2v_gemm_args* a, void* stream) {
+  if (int r = validate_gemm(a)) return r;
+  return launch_gemm_tc(*a, (cudaStream_t)stream);
+}
+int p2v_gemm_i8_simt(const p2v_gemm_args* a, void* stream) {
+  if (int r = validate_gemm(a)) return r;
+  return launch_gemm_simt(*a, (cudaStream_t)stream);
+}
+int p2v_fill_cls_rows(int8_t* out, const int8_t* cls_row, int B, int T, int N, void* stream) {
+  P2V_REQUIRE(out && cls_row && B > 0 && T > 0 && N > 0, "fill_cls_rows: bad arguments");
+  return launch_fill_cls(out, cls_row, B, T, N, (cudaStream_t)stream);
+}
+int p2v_layernorm_int(const p2v_layernorm_args* a, void* stream) {
+  P2V_REQUIRE(a && a->x && a->in_mult && a->gamma && a->beta && a->out_scale && a->post_div, "layernorm: missing pointers");
+  P2V_REQUIRE(a->rows > 0 && a->C > 0 && a->C % 4 == 0 && a->C <= 4096, "layernorm: C=%d must be a multiple of 4, <= 4096", a->C);
+  P2V_REQUIRE(a->out_i8 || a->out_f32, "layernorm: no output");
+  P2V_REQUIRE(a->x_row_stride % 4 == 0, "layernorm: row stride must be a multiple of 4 bytes");
+  return launch_layernorm(*a, (cudaStream_t)stream);
+}
+int p2v_int_softmax_log2(const int8_t* scores, uint8_t* out, int64_t rows, int n, const p2v_softmax_lut* lut, void* stream) {
+  P2V_REQUIRE(scores && out && lut && rows > 0 && n > 0 && n <= 1024, "int_softmax: bad arguments (n <= 1024)");
+  return launch_softmax(scores, out, rows, n, lut, (cudaStream_t)stream);
+}
+int p2v_attention_i8(const p2v_attention_args* a, void* stream) {
+  P2V_REQUIRE(a && a->qkv && a->out && a->lut_dev, "attention: missing pointers");
+  P2V_REQUIRE(a->B > 0 && a->H > 0 && a->T > 0 && a->T <= 256, "attention: T=%d unsupported (1..256)", a->T);
+  P2V_REQUIRE(a->dh == 64 || a->dh == 32, "attention: head dim %d unsupported (32 or 64)", a->dh);
+  return launch_attention(*a, (cudaStream_t)stream);
+}
+int p2v_minmax_per_channel(const float* x, float* minmax, int64_t n, int C, int64_t inner, void* stream) {
+  P2V_REQUIRE(x && minmax && n > 0 && C > 0 && inner > 0 && n % (int64_t(C) * inner) == 0, "minmax: bad arguments");
+  return launch_minmax(x, minmax, n, C, inner, (cudaStream_t)stream);
+}
+int p2v_quant_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales, const float* zps, int K,
+                         int n_scale, int per_channel_out, int lo, int hi, double* out, void* stream) {
+  P2V_REQUIRE(x && scales && out && n > 0 && C > 0 && inner > 0 && K > 0 && K <= 96, "mse_scores: bad arguments (K <= 96)");
+  P2V_REQUIRE(n_scale == 1 || n_scale == C, "mse_scores: n_scale must be 1 or C");
+  return launch_mse_scores(x, n, C, inner, scales, zps, K, n_scale, per_channel_out, lo, hi, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Shared device helpers for the p2vit_b200 kernels (sm_100a).
+//
+// Bit-exactness rules (DESIGN.md "numerics"): every fp32 operation that the reference performs as a
+// separate ATen op is performed here as one correctly rounded IEEE operation through the __f*_rn
+// intrinsics (never contracted into an FMA by the compiler); torch.round == rintf (half to even).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/p2vit_b200.h"
+
+namespace p2v {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);
+
+#define P2V_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      p2v::set_error(__VA_ARGS__);  \
+      return 1;                     \
+    }                               \
+  } while (0)
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// clamp(RNE(v), -128, 127) as int; NaN -> 0 like cvt.sat
+__device__ __forceinline__ int sat_s8(float v) {
+  int r;
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+
+// q = sat(RNE(x / s)) : POT => s is a power of two and rs = 1/s, so x*rs == x/s exactly
+template <bool POT>
+__device__ __forceinline__ int quant_s8(float x, float s, float rs) {
+  return sat_s8(POT ? fmul(x, rs) : fdiv(x, s));
+}
+
+__device__ __forceinline__ uint32_t pack4_s8(int a, int b, int c, int d) {
+  return (uint32_t(a) & 0xffu) | ((uint32_t(b) & 0xffu) << 8) | ((uint32_t(c) & 0xffu) << 16) | (uint32_t(d) << 24);
+}
+
+// torch's nn.GELU() (erf form): x * 0.5 * (1 + erf(x * sqrt(1/2)))   (ATen cpu/Activation: vectorized
+// x * kAlpha -> erf -> +1 -> * x * 0.5).  erff differs from Sleef's by <= 1 ulp on rare inputs; those
+// only matter at rounding ties (DESIGN.md "tie adjudication").
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float kAlpha = 0.70710678118654752440f;
+  float e = erff(fmul(x, kAlpha));
+  return fmul(fmul(x, 0.5f), fadd(1.0f, e));
+}
+
+// floor(log2(|a|)) for finite non-zero a (normal or subnormal)
+__device__ __forceinline__ int ilog2f(float a) {
+  uint32_t u = __float_as_uint(a) & 0x7fffffffu;
+  int e = int(u >> 23);
+  if (e == 0) return -118 - __clz(u);  // subnormal: value = u * 2^-149 -> floor(log2) = 31 - clz(u) - 149
+  return e - 127;
+}
+
+__device__ __forceinline__ float pow2i(int e) {  // 2^e for -126 <= e <= 127
+  return __uint_as_float(uint32_t(e + 127) << 23);
+}
+
+// QIntSoftmax tail (layers.py:376-381, 422-427): x = RNE(sum/exp); big = floor(log2 x) (+1 if x >= 1.5*2^big);
+// returns min(big,15), or 255 if big >= 16 (probability forced to zero), x >= 1 always.
+__device__ __forceinline__ uint32_t log2_code(float sum_f, float exp_f) {
+  float x = rintf(fdiv(sum_f, exp_f));
+  uint32_t u = __float_as_uint(x);
+  if (u >= 0x7f800000u) return 255u;                   // inf / nan (exp == 0)
+  int big = int((u + 0x00400000u) >> 23) - 127;        // mantissa >= 1.5 carries into the exponent
+  if (big < 0) big = 0;                                // x == 0 cannot happen (exp <= sum); keep defined
+  return big >= 16 ? 255u : uint32_t(big);
+}
+
+// exactly rounded (RNE) fp32 of the 128-bit integer hi*2^32 + lo  (hi, lo < 2^63)
+__device__ __forceinline__ float u96_to_f32(unsigned long long hi, unsigned long long lo) {
+  unsigned __int128 v = ((unsigned __int128)hi << 32) + lo;
+  unsigned long long top = (unsigned long long)(v >> 64);
+  unsigned long long bot = (unsigned long long)v;
+  if (top == 0) return __ull2float_rn(bot);
+  int lz = __clzll(top);                                // top != 0
+  int sh = 64 - lz;                                     // bits of v above bit 63 -> shift right by sh keeps 64 bits
+  unsigned long long kept = (unsigned long long)(v >> sh);
+  unsigned long long lost = bot & ((1ull << sh) - 1ull);
+  if (lost) kept |= 1ull;                               // sticky bit keeps RNE correct
+  return fmul(__ull2float_rn(kept), pow2i(sh));
+}
+
+}  // namespace p2v

@@ -1,0 +1,47 @@
+// CUDA-core (dp4a) int8 GEMM with the same fused epilogues as the tcgen05 kernel.
+// NOT the product path: tests use it to cross-check gemm_tc.cu and to localise a failure to
+// "tensor-core plumbing" vs "epilogue arithmetic" (include/p2vit_b200.h: p2v_gemm_i8_simt).
+#include "epilogue.cuh"
+
+namespace p2v {
+
+constexpr int SIMT_NC = 8;        // columns per thread
+constexpr int SIMT_THREADS = 128;
+
+template <int EPI, bool POT>
+__global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ W, EpiParams p) {
+  // block = 16 rows x 8 column-groups(64 cols); thread = 1 row x 8 cols
+  const int row = blockIdx.y * 16 + threadIdx.x / 8;
+  const int col0 = (blockIdx.x * 8 + threadIdx.x % 8) * SIMT_NC;
+  if (row >= p.M || col0 >= p.N) return;
+  int acc[SIMT_NC];
+#pragma unroll
+  for (int j = 0; j < SIMT_NC; ++j) acc[j] = 0;
+  const int K = p.K;  // multiple of 16
+  const int4* a4 = reinterpret_cast<const int4*>(A + size_t(row) * K);
+  for (int k = 0; k < K / 16; ++k) {
+    const int4 av = __ldg(a4 + k);
+#pragma unroll
+    for (int j = 0; j < SIMT_NC; ++j) {
+      if (col0 + j < p.N) {
+        const int4 wv = __ldg(reinterpret_cast<const int4*>(W + size_t(col0 + j) * K) + k);
+        acc[j] = __dp4a(av.x, wv.x, acc[j]);
+        acc[j] = __dp4a(av.y, wv.y, acc[j]);
+        acc[j] = __dp4a(av.z, wv.z, acc[j]);
+        acc[j] = __dp4a(av.w, wv.w, acc[j]);
+      }
+    }
+  }
+  epilogue_row<EPI, POT, SIMT_NC>(p, row, col0, acc);
+}
+
+int launch_gemm_simt(const p2v_gemm_args& a, cudaStream_t stream) {
+  EpiParams p = make_epi_params(a);
+  dim3 grid((a.N + 63) / 64, (a.M + 15) / 16);
+  P2V_DISPATCH_EPI(a.epilogue, a.pot_scales != 0,
+                   gemm_simt_kernel<EPI, POT><<<grid, SIMT_THREADS, 0, stream>>>(a.A, a.W, p););
+  count_launch();
+  return check_launch("gemm_simt");
+}
+
+}  // namespace p2v

@@ -1,0 +1,404 @@
+// HBM-bound element / row kernels: QAct quantize & fake-quant, patch gather, integer LayerNorm,
+// stand-alone integer log2-softmax, calibration reductions.  Reference call sites are cited in
+// include/p2vit_b200.h next to each entry point.
+#include "common.cuh"
+
+namespace p2v {
+
+static inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// QAct: q = clamp(RNE(x/s + zp), lo, hi); y = (q - zp) * s           (uniform.py:83-86,125)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float quant_code(float x, float s, float zp, float lo, float hi) {
+  float v = rintf(fadd(fdiv(x, s), zp));
+  return fminf(fmaxf(v, lo), hi);
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256) quantize_kernel(const float* __restrict__ x, int8_t* __restrict__ q, float* __restrict__ y,
+                                                       int64_t n, int C, int64_t inner, const float* __restrict__ scale,
+                                                       int n_scale, float zp, float lo, float hi) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  if (VEC4) {
+    // 4 consecutive elements share... not necessarily a channel: inner % 4 == 0 (same channel) or inner == 1 && C % 4 == 0
+    const int64_t n4 = n >> 2;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+      float s[4];
+      if (n_scale == 1) {
+        s[0] = s[1] = s[2] = s[3] = __ldg(scale);
+      } else if (inner == 1) {
+        const int c = int((i << 2) % C);
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(scale + c));
+        s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
+      } else {
+        const int c = int(((i << 2) / inner) % C);
+        s[0] = s[1] = s[2] = s[3] = __ldg(scale + c);
+      }
+      const float c0 = quant_code(v.x, s[0], zp, lo, hi), c1 = quant_code(v.y, s[1], zp, lo, hi);
+      const float c2 = quant_code(v.z, s[2], zp, lo, hi), c3 = quant_code(v.w, s[3], zp, lo, hi);
+      if (q) reinterpret_cast<uint32_t*>(q)[i] = pack4_s8(int(c0), int(c1), int(c2), int(c3));
+      if (y) reinterpret_cast<float4*>(y)[i] = make_float4(fmul(fsub(c0, zp), s[0]), fmul(fsub(c1, zp), s[1]),
+                                                            fmul(fsub(c2, zp), s[2]), fmul(fsub(c3, zp), s[3]));
+    }
+  } else {
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float s = __ldg(scale + (n_scale == 1 ? 0 : int((i / inner) % C)));
+      const float c = quant_code(__ldg(x + i), s, zp, lo, hi);
+      if (q) q[i] = int8_t(int(c));
+      if (y) y[i] = fmul(fsub(c, zp), s);
+    }
+  }
+}
+
+int launch_quantize(const float* x, int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale,
+                    float zp, int lo, int hi, cudaStream_t stream) {
+  if (n == 0) return 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(q) & 3) == 0;
+  const bool vec = aligned && (n % 4 == 0) && (n_scale == 1 || inner % 4 == 0 || (inner == 1 && C % 4 == 0));
+  const int64_t work = vec ? n / 4 : n;
+  const int blocks = int(std::min<int64_t>((work + 255) / 256, int64_t(num_sms()) * 16));
+  if (vec) quantize_kernel<true><<<blocks, 256, 0, stream>>>(x, q, y, n, C, inner, scale, n_scale, zp, float(lo), float(hi));
+  else quantize_kernel<false><<<blocks, 256, 0, stream>>>(x, q, y, n, C, inner, scale, n_scale, zp, float(lo), float(hi));
+  count_launch();
+  return check_launch("quantize");
+}
+
+__global__ void __launch_bounds__(256) dequantize_kernel(const int8_t* __restrict__ q, float* __restrict__ y, int64_t n, int C,
+                                                         int64_t inner, const float* __restrict__ scale, int n_scale, float zp) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float s = __ldg(scale + (n_scale == 1 ? 0 : int((i / inner) % C)));
+    y[i] = fmul(fsub(float(q[i]), zp), s);
+  }
+}
+
+int launch_dequantize(const int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale, float zp,
+                      cudaStream_t stream) {
+  if (n == 0) return 0;
+  const int blocks = int(std::min<int64_t>((n + 255) / 256, int64_t(num_sms()) * 16));
+  dequantize_kernel<<<blocks, 256, 0, stream>>>(q, y, n, C, inner, scale, n_scale, zp);
+  count_launch();
+  return check_launch("dequantize");
+}
+
+// ------------------------------------------------------------------------------------------------
+// qact_input + patch gather: thread = one P-pixel row segment of one patch and channel
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, int8_t* __restrict__ out, int B, int Cin,
+                                                       int H, int W, int P, float s, float zp, float lo, float hi) {
+  const int gw = W / P, gh = H / P;
+  const int64_t total = int64_t(B) * Cin * H * gw;  // segments
+  const int K = Cin * P * P;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t seg = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; seg < total; seg += stride) {
+    const int j = int(seg % gw);
+    int64_t t = seg / gw;
+    const int yy = int(t % H);
+    t /= H;
+    const int c = int(t % Cin);
+    const int b = int(t / Cin);
+    const float4* src = reinterpret_cast<const float4*>(img + ((int64_t(b) * Cin + c) * H + yy) * W + j * P);
+    const int i = yy / P, py = yy % P;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t(b) * gh * gw + int64_t(i) * gw + j) * K + (c * P + py) * P);
+    for (int v = 0; v < P / 4; ++v) {
+      const float4 f = __ldg(src + v);
+      dst[v] = pack4_s8(int(quant_code(f.x, s, zp, lo, hi)), int(quant_code(f.y, s, zp, lo, hi)),
+                        int(quant_code(f.z, s, zp, lo, hi)), int(quant_code(f.w, s, zp, lo, hi)));
+    }
+  }
+}
+
+int launch_patchify(const float* img, int8_t* out, int B, int Cin, int H, int W, int P, float scale, float zp, int lo, int hi,
+                    cudaStream_t stream) {
+  const int64_t total = int64_t(B) * Cin * H * (W / P);
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
+  patchify_kernel<<<blocks, 256, 0, stream>>>(img, out, B, Cin, H, W, P, scale, zp, float(lo), float(hi));
+  count_launch();
+  return check_launch("patchify");
+}
+
+__global__ void fill_cls_kernel(int8_t* __restrict__ out, const int8_t* __restrict__ cls_row, int B, int T, int N) {
+  const int b = blockIdx.x;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) out[size_t(b) * (T + 1) * N + n] = cls_row[n];
+}
+
+int launch_fill_cls(int8_t* out, const int8_t* cls_row, int B, int T, int N, cudaStream_t stream) {
+  fill_cls_kernel<<<B, 128, 0, stream>>>(out, cls_row, B, T, N);
+  count_launch();
+  return check_launch("fill_cls");
+}
+
+// ------------------------------------------------------------------------------------------------
+// QIntLayerNorm (int mode) + following QAct.  One warp per row; lane owns words lane, lane+32, ...
+// ------------------------------------------------------------------------------------------------
+template <bool POT>
+__device__ __forceinline__ float div_by(float x, float s) { return POT ? fmul(x, fdiv(1.f, s)) : fdiv(x, s); }
+
+template <int WPL, bool POT>
+__global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwords = a.C >> 2;
+  const float Cf = float(a.C);
+  const float s1 = a.in_scale_min;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.rows; row += gridDim.x * warps_per_block) {
+    const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
+    int xv[WPL][4];
+    int S1 = 0, S2 = 0;
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) {
+      const int w = lane + 32 * i;
+      if (w < nwords) {
+        const uint32_t u = __ldg(xr + w);
+        const float4 m = __ldg(reinterpret_cast<const float4*>(a.in_mult) + w);
+        xv[i][0] = int(int8_t(u & 0xff)) * int(m.x);
+        xv[i][1] = int(int8_t((u >> 8) & 0xff)) * int(m.y);
+        xv[i][2] = int(int8_t((u >> 16) & 0xff)) * int(m.z);
+        xv[i][3] = int(int8_t(u >> 24)) * int(m.w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { S1 += xv[i][e]; S2 += xv[i][e] * xv[i][e]; }
+      }
+    }
+    S1 = __reduce_add_sync(0xffffffffu, S1);
+    S2 = __reduce_add_sync(0xffffffffu, S2);
+    // layers.py:315-318  (row sums are exact integers; every fp32 op below is one ATen op of the reference)
+    const float S1f = float(S1), S2f = float(S2);
+    const float mean = fmul(fdiv(S1f, Cf), s1);
+    const float stdv = fmul(fdiv(s1, Cf), __fsqrt_rn(fsub(fmul(Cf, S2f), fmul(S1f, S1f))));
+    const float t = fdiv(s1, stdv);
+    const float mos = fdiv(mean, stdv);
+#pragma unroll
+    for (int i = 0; i < WPL; ++i) {
+      const int w = lane + 32 * i;
+      if (w < nwords) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma) + w);
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.beta) + w);
+        const float4 o4 = __ldg(reinterpret_cast<const float4*>(a.out_scale) + w);
+        const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.post_div) + w);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float os[4] = {o4.x, o4.y, o4.z, o4.w}, pd[4] = {p4.x, p4.y, p4.z, p4.w};
+        int q[4];
+        float yf[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float A = div_by<POT>(fmul(t, g[e]), os[e]);                       // layers.py:320-324
+          const float aA = fabsf(A);
+          int N;                                                                    // get_MN, layers.py:270-274
+          if (aA == 0.f) N = 31;
+          else if (!(aA < __int_as_float(0x7f800000))) N = 0;
+          else N = min(max(7 - ilog2f(aA), 0), 31);
+          const float twoN = pow2i(N);
+          const float M = fminf(fmaxf(floorf(fmul(aA, twoN)), 0.f), 255.f);
+          const float sgn = A > 0.f ? 1.f : (A < 0.f ? -1.f : 0.f);
+          const float Bv = rintf(fmul(div_by<POT>(fsub(be[e], fmul(mos, g[e])), os[e]), twoN));   // :327-334
+          const float yq = rintf(fmul(fadd(fmul(fmul(sgn, M), float(xv[i][e])), Bv), pow2i(-N)));  // :336
+          const float deq = fmul(yq, os[e]);                                                       // :337
+          yf[e] = deq;
+          q[e] = sat_s8(div_by<POT>(div_by<POT>(deq, pd[e]), a.next_scale));
+        }
+        if (a.out_i8) reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(row) * a.C)[w] = pack4_s8(q[0], q[1], q[2], q[3]);
+        if (a.out_f32) reinterpret_cast<float4*>(a.out_f32 + int64_t(row) * a.C)[w] = make_float4(yf[0], yf[1], yf[2], yf[3]);
+      }
+    }
+  }
+}
+
+int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
+  const int wpl = (a.C / 4 + 31) / 32;
+  const int blocks = std::min((a.rows + 7) / 8, num_sms() * 8);
+#define P2V_LN(W)                                                                   \
+  if (a.pot_scales) layernorm_kernel<W, true><<<blocks, 256, 0, stream>>>(a);       \
+  else layernorm_kernel<W, false><<<blocks, 256, 0, stream>>>(a);
+  if (wpl <= 1) { P2V_LN(1) } else if (wpl <= 2) { P2V_LN(2) } else if (wpl <= 3) { P2V_LN(3) } else if (wpl <= 4) { P2V_LN(4) }
+  else if (wpl <= 6) { P2V_LN(6) } else if (wpl <= 8) { P2V_LN(8) } else if (wpl <= 12) { P2V_LN(12) }
+  else if (wpl <= 16) { P2V_LN(16) } else { P2V_LN(32) }
+#undef P2V_LN
+  count_launch();
+  return check_launch("layernorm_int");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stand-alone QIntSoftmax on int8 score codes (one warp per row)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_kernel(const int8_t* __restrict__ scores, uint8_t* __restrict__ out, int64_t rows,
+                                                      int n, const p2v_softmax_lut* __restrict__ lut) {
+  __shared__ uint32_t s_hi[256], s_lo[256];
+  __shared__ float s_e[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_hi[i] = lut->hi[i]; s_lo[i] = lut->lo[i]; s_e[i] = lut->exp_f32[i]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t row = int64_t(blockIdx.x) * wpb + (threadIdx.x >> 5); row < rows; row += int64_t(gridDim.x) * wpb) {
+    const int8_t* r = scores + row * n;
+    int mx = -128;
+    for (int j = lane; j < n; j += 32) mx = max(mx, int(r[j]));
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    unsigned long long hi = 0, lo = 0;
+    for (int j = lane; j < n; j += 32) { const int d = mx - int(r[j]); hi += s_hi[d]; lo += s_lo[d]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { hi += __shfl_xor_sync(0xffffffffu, hi, o); lo += __shfl_xor_sync(0xffffffffu, lo, o); }
+    const float tot = u96_to_f32(hi, lo);
+    for (int j = lane; j < n; j += 32) out[row * n + j] = uint8_t(log2_code(tot, s_e[mx - int(r[j])]));
+  }
+}
+
+int launch_softmax(const int8_t* scores, uint8_t* out, int64_t rows, int n, const p2v_softmax_lut* lut, cudaStream_t stream) {
+  const int blocks = int(std::min<int64_t>((rows + 7) / 8, int64_t(num_sms()) * 8));
+  softmax_kernel<<<blocks, 256, 0, stream>>>(scores, out, rows, n, lut);
+  count_launch();
+  return check_launch("int_softmax_log2");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Calibration reductions
+// ------------------------------------------------------------------------------------------------
+// x viewed as [outer, C, inner]; block b handles a slab of `outer` (inner == 1: rows) and writes partial
+// min/max per channel; the second kernel folds the partials.
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const float* __restrict__ x, float* __restrict__ part, int64_t outer,
+                                                             int C, int64_t inner, int64_t outer_per_block) {
+  const int64_t o0 = int64_t(blockIdx.x) * outer_per_block;
+  const int64_t o1 = min(outer, o0 + outer_per_block);
+  float* pmin = part + size_t(blockIdx.x) * 2 * C;
+  float* pmax = pmin + C;
+  if (inner == 1) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float mn = __int_as_float(0x7f800000), mx = -mn;
+      for (int64_t o = o0; o < o1; ++o) { const float v = __ldg(x + o * C + c); mn = fminf(mn, v); mx = fmaxf(mx, v); }
+      pmin[c] = mn; pmax[c] = mx;
+    }
+  } else {
+    __shared__ float smn[256], smx[256];
+    for (int c = 0; c < C; ++c) {
+      float mn = __int_as_float(0x7f800000), mx = -mn;
+      for (int64_t o = o0; o < o1; ++o) {
+        const float* p = x + (o * C + c) * inner;
+        for (int64_t i = threadIdx.x; i < inner; i += blockDim.x) { const float v = __ldg(p + i); mn = fminf(mn, v); mx = fmaxf(mx, v); }
+      }
+      smn[threadIdx.x] = mn; smx[threadIdx.x] = mx;
+      __syncthreads();
+      for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { smn[threadIdx.x] = fminf(smn[threadIdx.x], smn[threadIdx.x + s]); smx[threadIdx.x] = fmaxf(smx[threadIdx.x], smx[threadIdx.x + s]); }
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) { pmin[c] = smn[0]; pmax[c] = smx[0]; }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void minmax_final_kernel(const float* __restrict__ part, float* __restrict__ out, int nblocks, int C) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float mn = __int_as_float(0x7f800000), mx = -mn;
+    for (int b = 0; b < nblocks; ++b) { mn = fminf(mn, part[size_t(b) * 2 * C + c]); mx = fmaxf(mx, part[size_t(b) * 2 * C + C + c]); }
+    out[c] = mn; out[C + c] = mx;
+  }
+}
+
+static float* g_scratch = nullptr;
+static size_t g_scratch_bytes = 0;
+static float* scratch(size_t bytes) {
+  if (bytes > g_scratch_bytes) {
+    if (g_scratch) cudaFree(g_scratch);
+    g_scratch = nullptr;
+    if (cudaMalloc(&g_scratch, bytes) != cudaSuccess) { g_scratch_bytes = 0; return nullptr; }
+    g_scratch_bytes = bytes;
+  }
+  return g_scratch;
+}
+
+int launch_minmax(const float* x, float* minmax, int64_t n, int C, int64_t inner, cudaStream_t stream) {
+  const int64_t outer = n / (int64_t(C) * inner);
+  int nblocks = int(std::min<int64_t>(outer, int64_t(num_sms()) * 4));
+  if (nblocks < 1) nblocks = 1;
+  const int64_t opb = (outer + nblocks - 1) / nblocks;
+  nblocks = int((outer + opb - 1) / opb);
+  float* part = scratch(size_t(nblocks) * 2 * C * sizeof(float));
+  P2V_REQUIRE(part != nullptr, "minmax: scratch allocation failed");
+  minmax_partial_kernel<<<nblocks, 256, 0, stream>>>(x, part, outer, C, inner, opb);
+  minmax_final_kernel<<<(C + 255) / 256, 256, 0, stream>>>(part, minmax, nblocks, C);
+  count_launch(2);
+  return check_launch("minmax_per_channel");
+}
+
+// sum (x - fq_k(x))^2 for K candidate scales.  Thread t of a block owns channel positions t, t+256, ...
+// of a slab of rows (inner == 1), so per-channel sums need no cross-thread reduction.
+constexpr int MSE_KG = 8;
+__global__ void __launch_bounds__(256) mse_scores_kernel(const float* __restrict__ x, int64_t outer, int C, int64_t inner,
+                                                         const float* __restrict__ scales, const float* __restrict__ zps, int K,
+                                                         int n_scale, int per_channel_out, float lo, float hi,
+                                                         double* __restrict__ out, int64_t outer_per_block) {
+  const int k0 = blockIdx.y * MSE_KG;
+  const int kn = min(MSE_KG, K - k0);
+  const int64_t o0 = int64_t(blockIdx.x) * outer_per_block;
+  const int64_t o1 = min(outer, o0 + outer_per_block);
+  const int n_out = per_channel_out ? C : 1;
+  double tot[MSE_KG];
+#pragma unroll
+  for (int k = 0; k < MSE_KG; ++k) tot[k] = 0.0;
+  const int64_t per_row = int64_t(C) * inner;
+  for (int64_t e = threadIdx.x; e < per_row; e += blockDim.x) {
+    const int c = int(e / inner);
+    float acc[MSE_KG];
+#pragma unroll
+    for (int k = 0; k < MSE_KG; ++k) acc[k] = 0.f;
+    for (int64_t o = o0; o < o1; ++o) {
+      const float v = __ldg(x + o * per_row + e);
+#pragma unroll
+      for (int k = 0; k < MSE_KG; ++k) {
+        if (k < kn) {
+          const float s = __ldg(scales + size_t(k0 + k) * n_scale + (n_scale == 1 ? 0 : c));
+          const float zp = zps ? __ldg(zps + size_t(k0 + k) * n_scale + (n_scale == 1 ? 0 : c)) : 0.f;
+          const float qv = fminf(fmaxf(rintf(fadd(fdiv(v, s), zp)), lo), hi);
+          const float d = fsub(v, fmul(fsub(qv, zp), s));
+          acc[k] = fadd(acc[k], fmul(d, d));
+        }
+      }
+    }
+    if (per_channel_out) {
+#pragma unroll
+      for (int k = 0; k < MSE_KG; ++k) if (k < kn) atomicAdd(out + size_t(k0 + k) * n_out + c, double(acc[k]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < MSE_KG; ++k) tot[k] += double(acc[k]);
+    }
+  }
+  if (!per_channel_out) {
+    __shared__ double sh[256];
+    for (int k = 0; k < kn; ++k) {
+      sh[threadIdx.x] = tot[k];
+      __syncthreads();
+      for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
+      if (threadIdx.x == 0) atomicAdd(out + (k0 + k), sh[0]);
+      __syncthreads();
+    }
+  }
+}
+
+int launch_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales, const float* zps, int K, int n_scale,
+                      int per_channel_out, int lo, int hi, double* out, cudaStream_t stream) {
+  const int64_t outer = n / (int64_t(C) * inner);
+  const int n_out = per_channel_out ? C : 1;
+  cudaMemsetAsync(out, 0, size_t(K) * n_out * sizeof(double), stream);
+  int nblocks = int(std::min<int64_t>(outer, int64_t(num_sms()) * 2));
+  if (nblocks < 1) nblocks = 1;
+  const int64_t opb = (outer + nblocks - 1) / nblocks;
+  nblocks = int((outer + opb - 1) / opb);
+  dim3 grid(nblocks, (K + MSE_KG - 1) / MSE_KG);
+  mse_scores_kernel<<<grid, 256, 0, stream>>>(x, outer, C, inner, scales, zps, K, n_scale, per_channel_out, float(lo), float(hi), out, opb);
+  count_launch();
+  return check_launch("quant_mse_scores");
+}
+
+}  // namespace p2v

@@ -1,0 +1,265 @@
+"""Integer inference engine for the quantized ViT/DeiT forward (reference dataflow: models/vit_fquant.py:334-407,
+489-596,830-939; models/layers_quant.py:348-393,462-497 - restated as integer codes in SURVEY.md 8a').
+
+What the reference does per forward in fp32 (re-smooth and re-quantize every weight, 6 elementwise ATen ops per
+QAct, ~35 per LayerNorm, ~40 per softmax) is split here into
+  * a *plan* (once per bit_config): int8 weight codes with the PoT smoothing folded in, per-column epilogue
+    vectors, softmax tables, LayerNorm shift vectors - all resident in HBM;
+  * a *program* (once per batch size): the kernel argument blocks over a fixed int8 workspace;
+  * the launch sequence, optionally captured into a CUDA graph (7 launches per block, 5 outside):
+        patchify(qact_input) -> GEMM[embed epilogue] -> cls rows
+        per block: LN1 -> GEMM[qkv, requant] -> attention -> GEMM[proj, residual] -> LN2 -> GEMM[fc1, GELU] -> GEMM[fc2, residual]
+        LN(cls rows) -> GEMM[head, dequant]
+Only int8 tensors cross HBM between kernels: r/r2 [B*197, D], qkv [B*197, 3D], attention out, MLP hidden.
+"""
+import torch
+
+from . import intmath, ops
+from .ptq import QIntLayerNorm
+
+
+def _vec(t, n, dev):
+    t = torch.as_tensor(t).detach().reshape(-1).to(device=dev, dtype=torch.float32)
+    return (t.expand(n) if t.numel() == 1 else t).contiguous()
+
+
+def _sym_scale(qact, who):
+    q = qact.quantizer
+    if q.scale is None:
+        raise RuntimeError("%s is not calibrated (run the calibrate -> model_quant flow or load_quant_state first)" % who)
+    if bool((q.zero_point != 0).any()):
+        raise NotImplementedError("%s has a non-zero zero point (asymmetric observer, e.g. omse): the integer engine "
+                                  "handles symmetric activations only; use model.forward_eager" % who)
+    if q.bit_type.name != "int8":
+        raise NotImplementedError("%s: activation bit type %s (engine carries int8 codes)" % (who, q.bit_type.name))
+    return q.scale.detach().reshape(-1).float()
+
+
+class _Gemm:
+    """device-resident pieces of one fused GEMM"""
+
+    def __init__(self, lin, weight, bit, in_scale, dev):
+        lin._set_bits(bit)
+        self.W, ws = lin.weight_codes(weight)
+        self.N, self.K = self.W.shape
+        self.acc_scale = (in_scale.reshape(-1).to(dev) * ws.to(dev)).contiguous()
+        self.bias = None if lin.bias is None else lin.bias.detach().float().contiguous()
+
+
+class VitPlan:
+    def __init__(self, model, bits):
+        m = model
+        dev = m.cls_token.device
+        D, L = m.embed_dim, m.depth
+        if len(bits) != 4 * L + 2:
+            raise ValueError("bit_config needs %d entries (1 + 4*depth + 1), got %d" % (4 * L + 2, len(bits)))
+        if any(b not in (4, 8) for b in bits):
+            raise ValueError("bit_config entries must be 4 or 8 (registered weight bit types int4/int8)")
+        if not m.input_quant:
+            raise NotImplementedError("input_quant=False (ViT-L: fp32 pixels into the patch embedding, SURVEY Q15) is not "
+                                      "on the int8 path yet")
+        if not all(isinstance(x, QIntLayerNorm) and x.mode == "int" for x in [m.norm] + [b.norm1 for b in m.blocks]):
+            raise NotImplementedError("the integer engine needs QIntLayerNorm in 'int' mode (Config(ptf=True))")
+        if not m.cfg.INT_SOFTMAX:
+            raise NotImplementedError("the integer engine needs the log-int-softmax (Config(lis=True))")
+        self.D, self.L, self.H = D, L, m.num_heads
+        self.P = m.patch_size
+        self.T = m.patch_embed.num_patches
+        # ---- stem
+        self.s_in = float(_sym_scale(m.qact_input, "qact_input"))
+        pe = m.patch_embed
+        self.g_embed = _Gemm(pe.proj, pe.proj.weight, bits[0], _sym_scale(m.qact_input, "qact_input"), dev)
+        self.s_pe = _vec(_sym_scale(pe.qact, "patch_embed.qact"), 1, dev)
+        s_e = _sym_scale(m.qact_embed, "qact_embed").to(dev)
+        self.s_e = float(s_e)
+        s_p = _sym_scale(m.qact_pos, "qact_pos").to(dev)
+        s0 = _vec(_sym_scale(m.qact1, "qact1"), D, dev)
+        pos = m.pos_embed.detach().float()
+        self.pos_hat = ((pos / s_p).round().clamp(-128, 127) * s_p).reshape(self.T + 1, D).contiguous()
+        cls = m.cls_token.detach().float().reshape(1, D)
+        cls_hat = (cls / s_e).round().clamp(-128, 127) * s_e
+        self.cls_row = ((cls_hat + self.pos_hat[0:1]) / s0).round().clamp(-128, 127).to(torch.int8).reshape(D).contiguous()
+        self.s_r0 = s0
+        # ---- blocks
+        self.blocks = []
+        last = s0
+        for i, blk in enumerate(m.blocks):
+            b4 = bits[4 * i + 1: 4 * i + 5]
+            a, mlp = blk.attn, blk.mlp
+            if a.channel_scale is None or mlp.channel_scale is None:
+                raise RuntimeError("block %d is not calibrated" % i)
+            p = {}
+            cs_a = a.best_scale[[4, 8].index(b4[0])].detach().float().to(dev)
+            cs_m = mlp.best_scale[[4, 8].index(b4[2])].detach().float().to(dev)
+            a0 = _sym_scale(a.qact0, "attn.qact0").to(dev)
+            a1 = _sym_scale(a.qact1, "attn.qact1").to(dev)
+            as_ = _sym_scale(a.qact_attn1, "attn.qact_attn1").to(dev)
+            a2 = _sym_scale(a.qact2, "attn.qact2").to(dev)
+            m0 = _sym_scale(mlp.qact0, "mlp.qact0").to(dev)
+            m1 = _sym_scale(mlp.qact1, "mlp.qact1").to(dev)
+            for s, nm in ((a0, "attn.qact0"), (a1, "attn.qact1"), (as_, "attn.qact_attn1"), (a2, "attn.qact2"), (m0, "mlp.qact0"), (m1, "mlp.qact1")):
+                if s.numel() != 1:
+                    raise NotImplementedError("%s must be layer-wise" % nm)
+            p["ln1"] = self._ln(blk.norm1, last, a0 * cs_a, cs_a, float(a0), dev)
+            p["qkv"] = _Gemm(a.qkv, a.qkv.weight * cs_a.reshape(1, -1), b4[0], a0, dev)
+            p["qkv_out"] = _vec(a1, 3 * D, dev)
+            p["qkv_pot"] = intmath.is_pot(a1)
+            dh = D // m.num_heads
+            p["score_mult"] = float(a1.double() * a1.double() * a.scale / as_.double())
+            p["out_mult"] = float(a1.double() / a2.double() / 32768.0)
+            p["lut"] = intmath.lut_to_device(intmath.build_softmax_lut(as_), dev)
+            p["proj"] = _Gemm(a.proj, a.proj.weight, b4[1], a2, dev)
+            p["proj_mid"] = _vec(_sym_scale(a.qact3, "attn.qact3"), D, dev)
+            p["res1_scale"] = last
+            s_b2 = _vec(_sym_scale(blk.qact2, "block.qact2"), D, dev)
+            p["proj_out"] = s_b2
+            p["ln2"] = self._ln(blk.norm2, s_b2, m0 * cs_a, cs_m, float(m0), dev)   # out grid uses attn's scale (Q7)
+            p["fc1"] = _Gemm(mlp.fc1, mlp.fc1.weight * cs_m.reshape(1, -1), b4[2], m0, dev)
+            p["fc1_out"] = _vec(m1, p["fc1"].N, dev)
+            p["fc1_pot"] = intmath.is_pot(m1)
+            p["fc2"] = _Gemm(mlp.fc2, mlp.fc2.weight, b4[3], m1, dev)
+            p["fc2_mid"] = _vec(_sym_scale(mlp.qact2, "mlp.qact2"), D, dev)
+            s_b4 = _vec(_sym_scale(blk.qact4, "block.qact4"), D, dev)
+            p["fc2_out"] = s_b4
+            p["dh"] = dh
+            self.blocks.append(p)
+            last = s_b4
+        # ---- tail
+        q2 = _sym_scale(m.qact2, "qact2").to(dev)
+        ones = torch.ones(D, device=dev)
+        self.ln_f = self._ln(m.norm, last, q2, ones, float(q2), dev)
+        self.head = _Gemm(m.head, m.head.weight, bits[-1], q2, dev)
+        ao = _sym_scale(m.act_out, "act_out")
+        self.head_out = _vec(ao, self.head.N, dev)
+        self.head_pot = intmath.is_pot(ao)
+
+    @staticmethod
+    def _ln(norm, in_scale, out_scale, post_div, next_scale, dev):
+        C = norm.weight.numel()
+        in_scale = _vec(in_scale, C, dev)
+        s1 = in_scale.min()
+        return dict(in_mult=(in_scale / s1).round().contiguous(), s1=float(s1),
+                    gamma=norm.weight.detach().float().contiguous(), beta=norm.bias.detach().float().contiguous(),
+                    out_scale=_vec(out_scale, C, dev), post_div=_vec(post_div, C, dev), next_scale=next_scale,
+                    pot=intmath.is_pot(out_scale) and intmath.is_pot(post_div) and intmath.is_pot(torch.tensor(next_scale)))
+
+
+class VitEngine:
+    def __init__(self, model, use_graph=True, simt_gemm=False):
+        self.model = model
+        self.use_graph = use_graph
+        self.simt_gemm = simt_gemm      # tests only: route GEMMs through the dp4a cross-check kernel
+        self.plans, self.programs, self.graphs = {}, {}, {}
+
+    # ---- workspace + argument blocks for one (bit_config, batch)
+    def _program(self, bits, B):
+        key = (bits, B)
+        if key in self.programs:
+            return self.programs[key]
+        if bits not in self.plans:
+            self.plans[bits] = VitPlan(self.model, list(bits))
+        pl = self.plans[bits]
+        dev = self.model.cls_token.device
+        D, T, H = pl.D, pl.T, pl.H
+        R = B * (T + 1)
+        i8 = lambda *s: torch.empty(s, dtype=torch.int8, device=dev)
+        ws = dict(img=torch.empty((B, 3, T_side(pl), T_side(pl)), dtype=torch.float32, device=dev),
+                  cols=i8(B * T, pl.g_embed.K), ra=i8(R, D), rb=i8(R, D), ln=i8(R, D), qkv=i8(R, 3 * D), ao=i8(R, D),
+                  hid=i8(R, pl.blocks[0]["fc1"].N), cls=i8(B, D),
+                  logits=torch.empty((B, pl.head.N), dtype=torch.float32, device=dev), logit_codes=i8(B, pl.head.N))
+        steps = []
+        g = pl.g_embed
+        steps.append(("patchify", lambda: ops.quantize_patchify(ws["img"], pl.P, pl.s_in, out=ws["cols"])))
+        steps.append(("embed", self._gemm(ops.gemm_args(ws["cols"], g.W, ops.EPI_EMBED, g.acc_scale, bias=g.bias, out_scale=pl.s_r0,
+                                                        mid_scale=pl.s_pe, pos=pl.pos_hat, aux_scale=pl.s_e, tokens_per_image=T,
+                                                        out_i8=ws["ra"]))))
+        steps.append(("cls", lambda: ops.fill_cls_rows(ws["ra"], pl.cls_row, B, T, D)))
+        for i, p in enumerate(pl.blocks):
+            pre = "blocks.%d." % i
+            steps.append((pre + "norm1", self._ln(p["ln1"], ws["ra"], R, D, D, ws["ln"])))
+            g = p["qkv"]
+            steps.append((pre + "attn.qact1", self._gemm(ops.gemm_args(ws["ln"], g.W, ops.EPI_REQUANT, g.acc_scale, bias=g.bias,
+                                                                       out_scale=p["qkv_out"], out_i8=ws["qkv"], pot=p["qkv_pot"]))))
+            at = ops.attention_args(ws["qkv"], ws["ao"], B, T + 1, H, p["dh"], p["score_mult"], p["out_mult"], p["lut"])
+            steps.append((pre + "attn.qact2", (lambda at=at: ops.attention(at))))
+            g = p["proj"]
+            steps.append((pre + "qact2", self._gemm(ops.gemm_args(ws["ao"], g.W, ops.EPI_RESIDUAL, g.acc_scale, bias=g.bias,
+                                                                  out_scale=p["proj_out"], mid_scale=p["proj_mid"],
+                                                                  res_scale=p["res1_scale"], res=ws["ra"], out_i8=ws["rb"]))))
+            steps.append((pre + "norm2", self._ln(p["ln2"], ws["rb"], R, D, D, ws["ln"])))
+            g = p["fc1"]
+            steps.append((pre + "mlp.qact1", self._gemm(ops.gemm_args(ws["ln"], g.W, ops.EPI_GELU, g.acc_scale, bias=g.bias,
+                                                                      out_scale=p["fc1_out"], out_i8=ws["hid"], pot=p["fc1_pot"]))))
+            g = p["fc2"]
+            steps.append((pre + "qact4", self._gemm(ops.gemm_args(ws["hid"], g.W, ops.EPI_RESIDUAL, g.acc_scale, bias=g.bias,
+                                                                  out_scale=p["fc2_out"], mid_scale=p["fc2_mid"],
+                                                                  res_scale=p["proj_out"], res=ws["rb"], out_i8=ws["ra"]))))
+        steps.append(("qact2", self._ln(pl.ln_f, ws["ra"], B, D, (T + 1) * D, ws["cls"])))
+        g = pl.head
+        steps.append(("act_out", self._gemm(ops.gemm_args(ws["cls"], g.W, ops.EPI_DEQUANT, g.acc_scale, bias=g.bias, out_scale=pl.head_out,
+                                                          out_f32=ws["logits"], out_i8=ws["logit_codes"], pot=pl.head_pot))))
+        # which workspace tensor holds each step's result (for per-op parity taps)
+        outs = {"patchify": "cols", "embed": "ra", "cls": "ra", "qact2": "cls", "act_out": "logits"}
+        for i in range(pl.L):
+            pre = "blocks.%d." % i
+            outs.update({pre + "norm1": "ln", pre + "attn.qact1": "qkv", pre + "attn.qact2": "ao", pre + "qact2": "rb",
+                         pre + "norm2": "ln", pre + "mlp.qact1": "hid", pre + "qact4": "ra"})
+        prog = dict(ws=ws, steps=steps, outs=outs, plan=pl)
+        self.programs[key] = prog
+        return prog
+
+    def _gemm(self, args):
+        simt = self.simt_gemm
+        return lambda: ops.gemm(args, simt=simt)
+
+    @staticmethod
+    def _ln(p, x, rows, C, stride, out):
+        a = ops.layernorm_args(x, rows, C, stride, p["in_mult"], p["s1"], p["gamma"], p["beta"], p["out_scale"], p["post_div"],
+                               p["next_scale"], p["pot"], out_i8=out)
+        return lambda: ops.layernorm(a)
+
+    def launches_per_forward(self, bit_config):
+        return 5 + 7 * self.model.depth
+
+    def static_input(self, B, bit_config):
+        """the fp32 image buffer the program reads; copy a batch into it (e.g. straight from pinned host memory) and call
+        run_static() to skip the device-to-device copy of __call__."""
+        return self._program(tuple(bit_config), B)["ws"]["img"]
+
+    def run_static(self, B, bit_config, taps=None):
+        bits = tuple(bit_config)
+        prog = self._program(bits, B)
+        if taps is not None:
+            for name, fn in prog["steps"]:
+                fn()
+                taps[name] = prog["ws"][prog["outs"][name]].clone()
+            return prog["ws"]["logits"]
+        if not self.use_graph:
+            for _, fn in prog["steps"]:
+                fn()
+            return prog["ws"]["logits"]
+        key = (bits, B)
+        if key not in self.graphs:
+            for _, fn in prog["steps"]:   # eager warm-up: sets kernel attributes, loads modules
+                fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _, fn in prog["steps"]:
+                    fn()
+            self.graphs[key] = g
+        self.graphs[key].replay()
+        return prog["ws"]["logits"]
+
+    def __call__(self, x, bit_config, taps=None):
+        if not x.is_cuda:
+            raise RuntimeError("p2vit_b200: the quantized forward runs on the GPU only (input is on %s)" % x.device)
+        B = x.shape[0]
+        img = self.static_input(B, bit_config)
+        if x.data_ptr() != img.data_ptr():
+            img.copy_(x)
+        return self.run_static(B, bit_config, taps).clone()
+
+
+def T_side(pl):
+    return int(round(pl.T ** 0.5)) * pl.P

@@ -1,0 +1,163 @@
+"""Tensor-level wrappers over the C ABI (include/p2vit_b200.h).  Every function enqueues on
+torch's current CUDA stream and allocates outputs with torch; inputs must be CUDA tensors."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_DEQUANT, EPI_EMBED, EPI_F32, EPI_GELU, EPI_REQUANT, EPI_RESIDUAL,  # noqa: F401
+                   AttentionArgs, GemmArgs, LayerNormArgs, check, ptr, stream)
+
+
+def _scale_vec(scale, device):
+    s = scale if isinstance(scale, torch.Tensor) else torch.tensor([float(scale)])
+    return s.detach().reshape(-1).to(device=device, dtype=torch.float32).contiguous()
+
+
+def _channel_geometry(x):
+    """(C, inner) of the reference's activation channel rule (quantizer/base.py:14-31)."""
+    if x.dim() == 4:
+        return x.shape[1], x.shape[2] * x.shape[3]
+    return x.shape[-1], 1
+
+
+def quantize(x, scale, zero_point=0.0, lo=-128, hi=127):
+    """QAct codes: clamp(RNE(x/scale + zp), lo, hi) as int8."""
+    x = x.contiguous()
+    s = _scale_vec(scale, x.device)
+    Cn, inner = _channel_geometry(x)
+    q = torch.empty(x.shape, dtype=torch.int8, device=x.device)
+    check(_lib.load().p2v_quantize_f32(ptr(x), ptr(q), x.numel(), Cn, inner, ptr(s), s.numel(), float(zero_point), lo, hi, stream()),
+          "quantize_f32")
+    return q
+
+
+def fake_quant(x, scale, zero_point=0.0, lo=-128, hi=127, return_codes=False):
+    """BaseQuantizer.forward: dequantize(quant(x)) in one pass (quantizer/base.py:42-45)."""
+    x = x.contiguous()
+    s = _scale_vec(scale, x.device)
+    Cn, inner = _channel_geometry(x)
+    y = torch.empty_like(x)
+    q = torch.empty(x.shape, dtype=torch.int8, device=x.device) if return_codes else None
+    check(_lib.load().p2v_fake_quant_f32(ptr(x), ptr(y), ptr(q), x.numel(), Cn, inner, ptr(s), s.numel(), float(zero_point), lo, hi,
+                                         stream()), "fake_quant_f32")
+    return (y, q) if return_codes else y
+
+
+def dequantize(q, scale, zero_point=0.0):
+    q = q.contiguous()
+    s = _scale_vec(scale, q.device)
+    Cn, inner = _channel_geometry(q)
+    y = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    check(_lib.load().p2v_dequantize_i8(ptr(q), ptr(y), q.numel(), Cn, inner, ptr(s), s.numel(), float(zero_point), stream()),
+          "dequantize_i8")
+    return y
+
+
+def quantize_patchify(img, patch, scale, zero_point=0.0, lo=-128, hi=127, out=None):
+    img = img.contiguous()
+    B, Cin, H, W = img.shape
+    rows, K = B * (H // patch) * (W // patch), Cin * patch * patch
+    if out is None:
+        out = torch.empty((rows, K), dtype=torch.int8, device=img.device)
+    check(_lib.load().p2v_quantize_patchify(ptr(img), ptr(out), B, Cin, H, W, patch, float(scale), float(zero_point), lo, hi, stream()),
+          "quantize_patchify")
+    return out
+
+
+def gemm_args(A, W, epilogue, acc_scale, bias=None, out_scale=None, mid_scale=None, res_scale=None, res=None, pos=None,
+              aux_scale=0.0, tokens_per_image=0, out_i8=None, out_f32=None, pot=False, zp_corr=None):
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K
+    a = GemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.A, a.W = ptr(A), ptr(W)
+    a.epilogue = epilogue
+    a.acc_scale, a.bias, a.zp_corr = ptr(acc_scale), ptr(bias), ptr(zp_corr)
+    a.out_scale, a.mid_scale, a.res_scale = ptr(out_scale), ptr(mid_scale), ptr(res_scale)
+    a.res, a.pos = ptr(res), ptr(pos)
+    a.aux_scale, a.tokens_per_image = float(aux_scale), int(tokens_per_image)
+    a.out_i8, a.out_f32 = ptr(out_i8), ptr(out_f32)
+    a.pot_scales = 1 if pot else 0
+    return a
+
+
+def gemm(args, simt=False):
+    lib = _lib.load()
+    fn = lib.p2v_gemm_i8_simt if simt else lib.p2v_gemm_i8
+    check(fn(C.byref(args), stream()), "gemm_i8_simt" if simt else "gemm_i8")
+
+
+def fill_cls_rows(out, cls_row, B, T, N):
+    check(_lib.load().p2v_fill_cls_rows(ptr(out), ptr(cls_row), B, T, N, stream()), "fill_cls_rows")
+
+
+def layernorm_args(x, rows, Cn, row_stride, in_mult, in_scale_min, gamma, beta, out_scale, post_div, next_scale, pot,
+                   out_i8=None, out_f32=None):
+    a = LayerNormArgs()
+    a.rows, a.C = rows, Cn
+    a.x, a.x_row_stride = ptr(x), row_stride
+    a.in_mult, a.in_scale_min = ptr(in_mult), float(in_scale_min)
+    a.gamma, a.beta = ptr(gamma), ptr(beta)
+    a.out_scale, a.post_div = ptr(out_scale), ptr(post_div)
+    a.next_scale, a.pot_scales = float(next_scale), 1 if pot else 0
+    a.out_i8, a.out_f32 = ptr(out_i8), ptr(out_f32)
+    return a
+
+
+def layernorm(args):
+    check(_lib.load().p2v_layernorm_int(C.byref(args), stream()), "layernorm_int")
+
+
+def int_softmax_log2(scores_i8, lut_dev):
+    scores_i8 = scores_i8.contiguous()
+    n = scores_i8.shape[-1]
+    rows = scores_i8.numel() // n
+    out = torch.empty(scores_i8.shape, dtype=torch.uint8, device=scores_i8.device)
+    check(_lib.load().p2v_int_softmax_log2(ptr(scores_i8), ptr(out), rows, n, ptr(lut_dev), stream()), "int_softmax_log2")
+    return out
+
+
+def attention_args(qkv, out, B, T, H, dh, score_mult, out_mult, lut_dev, probs=None, scores=None):
+    a = AttentionArgs()
+    a.B, a.T, a.H, a.dh = B, T, H, dh
+    a.qkv, a.out = ptr(qkv), ptr(out)
+    a.score_mult, a.out_mult = float(score_mult), float(out_mult)
+    a.lut_dev = ptr(lut_dev)
+    a.probs_or_null, a.scores_or_null = ptr(probs), ptr(scores)
+    return a
+
+
+def attention(args):
+    check(_lib.load().p2v_attention_i8(C.byref(args), stream()), "attention_i8")
+
+
+def minmax_per_channel(x):
+    """[2,C] tensor: row 0 per-channel min, row 1 per-channel max (observer/base.py:16-29 layout rule)."""
+    x = x.detach().contiguous().float()
+    Cn, inner = _channel_geometry(x)
+    out = torch.empty((2, Cn), dtype=torch.float32, device=x.device)
+    check(_lib.load().p2v_minmax_per_channel(ptr(x), ptr(out), x.numel(), Cn, inner, stream()), "minmax_per_channel")
+    return out
+
+
+def quant_mse_scores(x, scales, lo, hi, zero_points=None, per_channel_out=False):
+    """sum((x - fq_k(x))^2) for K candidate scales [K, 1 or C] -> float64 [K, 1 or C]."""
+    x = x.detach().contiguous().float()
+    Cn, inner = _channel_geometry(x)
+    scales = scales.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    K, n_scale = scales.shape
+    zps = None if zero_points is None else zero_points.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    out = torch.empty((K, Cn if per_channel_out else 1), dtype=torch.float64, device=x.device)
+    check(_lib.load().p2v_quant_mse_scores(ptr(x), x.numel(), Cn, inner, ptr(scales), ptr(zps), K, n_scale, 1 if per_channel_out else 0,
+                                           lo, hi, ptr(out), stream()), "quant_mse_scores")
+    return out
+
+
+def launch_count(reset=False):
+    lib = _lib.load()
+    n = lib.p2v_launch_count()
+    if reset:
+        lib.p2v_reset_launch_count()
+    return n

@@ -1,0 +1,155 @@
+"""GPU: the quantized model (integer engine and module-by-module path) against the golden vectors of the
+unmodified reference (tests/golden, calibrated state loaded) and against the CPU oracle on fresh inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.port import VitOracle
+from p2vit_b200 import Config, build_model, synth
+from p2vit_b200.engine import VitEngine
+
+pytestmark = pytest.mark.gpu
+
+
+def _state(g):
+    return {k[6:]: g[k] for k in g.files if k.startswith("state/")}
+
+
+def _model(name, g):
+    m = build_model(name, Config(), seed=int(g["meta.seed"]), device="cuda")
+    m.load_quant_state(_state(g))
+    m.model_quant()
+    return m
+
+
+def _tap_codes(golden_tap, scale):
+    return np.round(golden_tap / scale.reshape(1, 1, -1)).astype(np.int64)
+
+
+def test_micro_engine_per_op_codes_match_reference(golden):
+    g = golden("vit_micro_minmax")
+    m = _model("vit_micro", g)
+    st = _state(g)
+    x = synth.synth_images(int(g["meta.eval"]), seed=1).cuda()
+    bits = [8] * (4 * m.depth + 2)
+    eng = VitEngine(m, use_graph=False)
+    taps = {}
+    logits = eng(x, bits, taps=taps).cpu().numpy()
+    B, T1, D = x.shape[0], 197, m.embed_dim
+    report = []
+    # residual stream after the stem
+    got = taps["cls"].cpu().numpy().reshape(B, T1, D).astype(np.int64)
+    report.append(("qact1", (got != _tap_codes(g["tap8/qact1"], st["qact1.scale"])).sum()))
+    for i in range(m.depth):
+        p = "blocks.%d." % i
+        for step, tap, sc in ((p + "norm1", p + "attn.qact0", st[p + "attn.qact0.scale"]),
+                              (p + "attn.qact1", p + "attn.qact1", st[p + "attn.qact1.scale"]),
+                              (p + "attn.qact2", p + "attn.qact2", st[p + "attn.qact2.scale"]),
+                              (p + "qact2", p + "qact2", st[p + "qact2.scale"]),
+                              (p + "norm2", p + "mlp.qact0", st[p + "mlp.qact0.scale"]),
+                              (p + "mlp.qact1", p + "mlp.qact1", st[p + "mlp.qact1.scale"]),
+                              (p + "qact4", p + "qact4", st[p + "qact4.scale"])):
+            ref = _tap_codes(g["tap8/" + tap], sc)
+            got = taps[step].cpu().numpy().reshape(ref.shape).astype(np.int64)
+            report.append((step, int((got != ref).sum())))
+    bad = [(k, v) for k, v in report if v]
+    assert not bad, "code mismatches vs reference taps: %s" % bad
+    assert np.array_equal(logits, g["logits8"])
+
+
+@pytest.mark.parametrize("name", ["vit_micro", "deit_tiny"])
+@pytest.mark.parametrize("wbits", [8, 4])
+def test_engine_logits_match_reference_golden(golden, name, wbits):
+    g = golden(name + "_minmax")
+    m = _model(name, g)
+    x = synth.synth_images(int(g["meta.eval"]), seed=1).cuda()
+    bits = [wbits] * (4 * m.depth + 2)
+    logits, flops, gd = m(x, bits)
+    ref = g["logits%d" % wbits]
+    got = logits.cpu().numpy()
+    assert np.array_equal(got.argmax(1), ref.argmax(1)), "top-1 differs"
+    assert np.array_equal(got, ref), "logit codes differ in %d of %d entries" % ((got != ref).sum(), ref.size)
+    assert len(flops) == 4 * m.depth + 2
+
+
+def test_graph_replay_and_simt_cross_check(golden):
+    g = golden("vit_micro_minmax")
+    m = _model("vit_micro", g)
+    bits = [8] * (4 * m.depth + 2)
+    x = synth.synth_images(3, seed=5).cuda()
+    a = VitEngine(m, use_graph=True)(x, bits)
+    a2 = m(x, bits)[0]           # graph replay through the model's own engine (second call replays)
+    a3 = m(x, bits)[0]
+    b = VitEngine(m, use_graph=False, simt_gemm=True)(x, bits)
+    assert torch.equal(a, a2) and torch.equal(a, a3) and torch.equal(a, b)
+
+
+def test_batch_split_invariance(golden):
+    """sharding the batch (the data-parallel partition) cannot change any logit."""
+    g = golden("vit_micro_minmax")
+    m = _model("vit_micro", g)
+    bits = [8] * (4 * m.depth + 2)
+    x = synth.synth_images(7, seed=11).cuda()
+    full = m(x, bits)[0]
+    parts = torch.cat([m(x[:3].contiguous(), bits)[0], m(x[3:].contiguous(), bits)[0]])
+    assert torch.equal(full, parts)
+
+
+def test_engine_vs_oracle_fresh_inputs(golden):
+    """new images, W8A8 and mixed bit_config, against the exact-sum oracle."""
+    g = golden("vit_micro_minmax")
+    m = _model("vit_micro", g)
+    c = synth.VIT_CONFIGS["vit_micro"]
+    o = VitOracle(synth.synth_vit_state_dict(**c, seed=0), **c, exact_sums=True)
+    o.load_state(_state(g))
+    x = synth.synth_images(4, seed=123)
+    for bits in ([8] * 10, [8, 4, 4, 8, 8, 8, 8, 4, 4, 8]):
+        ref = o.forward_quant(x, bits)
+        got = m(x.cuda(), bits)[0].cpu()
+        assert torch.equal(got, ref), "bits=%s: %d mismatches" % (bits, int((got != ref).sum()))
+
+
+def test_eager_modules_match_engine(golden):
+    g = golden("vit_micro_minmax")
+    m = _model("vit_micro", g)
+    bits = [8] * (4 * m.depth + 2)
+    x = synth.synth_images(2, seed=1).cuda()
+    eager = m.forward_eager(x, bits)[0]
+    assert np.array_equal(eager.cpu().numpy(), g["logits8"])
+    assert torch.equal(eager, m(x, bits)[0])
+
+
+def test_quantized_forward_requires_bit_config_and_cuda(golden):
+    g = golden("vit_micro_minmax")
+    m = _model("vit_micro", g)
+    with pytest.raises(ValueError):
+        m(synth.synth_images(1).cuda())
+    with pytest.raises(RuntimeError):
+        m(synth.synth_images(1), [8] * 10)
+    with pytest.raises(ValueError):
+        m(synth.synth_images(1).cuda(), [8] * 9)
+
+
+def test_calibration_matches_reference_state(golden):
+    """the B200 calibration (block-reduce observers, batched weight search) freezes the same PoT exponents as the
+    reference; raw fp32 scales (PTF base) agree to fp32 rounding of the GPU's own FP forward."""
+    from p2vit_b200 import calibrate_model
+
+    g = golden("vit_micro_minmax")
+    m = build_model("vit_micro", Config(), seed=0, device="cuda")
+    calibrate_model(m, synth.synth_images(int(g["meta.calib"]), seed=0).cuda())
+    st, ref = m.export_quant_state(), _state(g)
+    assert set(st) == set(ref)
+    exp_bad, ptf_bad = [], []
+    for k, v in ref.items():
+        a = st[k].numpy().astype(np.float64)
+        v = v.astype(np.float64)
+        if "zero_point" in k:
+            assert np.array_equal(a, v), k
+        elif k.endswith(".scale") and v.size > 1:   # PTF: fp32 base scale x {1,2,4,8}
+            if not (np.array_equal(np.round(np.log2(a / a.min())), np.round(np.log2(v / v.min()))) and abs(a.min() / v.min() - 1) < 1e-5):
+                ptf_bad.append(k)
+        elif not np.array_equal(a, v):
+            exp_bad.append(k)
+    assert not exp_bad, "PoT scales differ: %s" % exp_bad[:10]
+    assert not ptf_bad, "PTF scales differ: %s" % ptf_bad[:10]

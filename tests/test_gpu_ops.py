@@ -1,0 +1,292 @@
+"""GPU: every kernel behind the C ABI against the CPU oracle (oracle/port.py) / exact integer arithmetic on the
+same seeded inputs.  Integer codes must match bit for bit; the only tolerated differences are erf ulp ties in
+the GELU epilogue (rate bound stated in the test)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from p2vit_b200 import intmath, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand_codes(*shape, lo=-128, hi=128, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(lo, hi, shape, generator=g, dtype=torch.int32).to(torch.int8)
+
+
+# ------------------------------------------------------------------------------------------------ QAct
+@pytest.mark.parametrize("shape,scale_kind", [((3, 197, 192), "pot"), ((3, 197, 192), "ptf"), ((2, 3, 224, 224), "pot"),
+                                              ((5, 1000), "raw"), ((2, 6, 197, 197), "pot"), ((1, 7, 10), "raw")])
+def test_quantize_and_fake_quant(shape, scale_kind):
+    torch.manual_seed(1)
+    x = torch.randn(shape) * 3
+    C = shape[1] if len(shape) == 4 else shape[-1]
+    if scale_kind == "pot":
+        s = torch.tensor([2.0 ** -5])
+    elif scale_kind == "raw":
+        s = torch.tensor([0.0123])
+    else:
+        s = 0.0171 * torch.tensor([1.0, 2.0, 4.0, 8.0])[torch.randint(0, 4, (C,))]
+    zp = torch.zeros(1, dtype=torch.int64)
+    sh = port.act_shape(x)
+    ref_q = port.quantize(x, s, zp, -128, 127, sh)
+    ref_y = port.fake_quant(x, s, zp, -128, 127, sh)
+    q = ops.quantize(x.to(DEV), s).cpu()
+    y, q2 = ops.fake_quant(x.to(DEV), s, return_codes=True)
+    assert torch.equal(q.float(), ref_q)
+    assert torch.equal(q2.cpu().float(), ref_q)
+    assert torch.equal(y.cpu(), ref_y)
+    assert torch.equal(ops.dequantize(q.to(DEV), s).cpu(), ref_y)
+
+
+def test_fake_quant_unsigned_and_zero_point():
+    torch.manual_seed(2)
+    x = torch.rand(4, 50, 64) * 4 - 1
+    s, zp = torch.tensor([0.021]), torch.tensor([37])
+    ref = port.fake_quant(x, s, zp, 0, 255, (1, 1, -1))
+    assert torch.equal(ops.fake_quant(x.to(DEV), s, 37.0, 0, 255).cpu(), ref)
+
+
+def test_patchify_matches_conv_layout():
+    torch.manual_seed(3)
+    B, P = 3, 16
+    img = torch.randn(B, 3, 224, 224)
+    s = 2.0 ** -5
+    cols = ops.quantize_patchify(img.to(DEV), P, s).cpu()
+    q = (img / s).round().clamp(-128, 127)
+    ref = q.reshape(B, 3, 14, P, 14, P).permute(0, 2, 4, 1, 3, 5).reshape(B * 196, 3 * P * P)
+    assert torch.equal(cols.float(), ref)
+    # same K order as the conv weight: conv(x, w) == cols @ w.reshape(D,-1).T
+    w = torch.randint(-8, 8, (5, 3, P, P)).float()
+    conv = torch.nn.functional.conv2d(q, w, stride=P).flatten(2).transpose(1, 2).reshape(B * 196, 5)
+    assert torch.equal(conv, ref @ w.reshape(5, -1).T)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def _acc_exact(A, W):
+    return (A.to(DEV).double() @ W.to(DEV).double().T).round().to(torch.int64)
+
+
+def _gemm_inputs(M, N, K, seed):
+    A = _rand_codes(M, K, seed=seed)
+    W = _rand_codes(N, K, seed=seed + 1)
+    g = torch.Generator().manual_seed(seed + 2)
+    bias = torch.randn(N, generator=g) * 0.5
+    return A, W, bias
+
+
+SHAPES = [(394, 384, 384), (197 * 3, 1152, 384), (130, 1536, 384), (256, 384, 1536), (64, 1000, 192), (5, 1000, 384),
+          (1000, 192, 192), (129, 144, 64)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("simt", [False, True], ids=["tcgen05", "simt"])
+def test_gemm_f32_epilogue_exact(M, N, K, simt):
+    A, W, bias = _gemm_inputs(M, N, K, 10)
+    acc_scale = torch.full((N,), 2.0 ** -12)
+    out = torch.empty(M, N, device=DEV)
+    args = ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_F32, acc_scale.to(DEV), bias=bias.to(DEV), out_f32=out)
+    ops.gemm(args, simt=simt)
+    ref = _acc_exact(A, W).float() * acc_scale.to(DEV) + bias.to(DEV)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref), "mismatches: %d" % int((out != ref).sum())
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES[:5])
+@pytest.mark.parametrize("pot", [True, False])
+def test_gemm_requant_and_dequant(M, N, K, pot):
+    A, W, bias = _gemm_inputs(M, N, K, 20)
+    acc_scale = (torch.full((N,), 2.0 ** -13) if pot else torch.rand(N) * 1e-4 + 1e-4).to(DEV)
+    out_scale = (torch.full((N,), 2.0 ** -4) if pot else torch.rand(N) * 0.05 + 0.03).to(DEV)
+    y = _acc_exact(A, W).float() * acc_scale + bias.to(DEV)
+    ref = (y / out_scale).round().clamp(-128, 127)
+    for simt in (False, True):
+        o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
+        ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_REQUANT, acc_scale, bias=bias.to(DEV), out_scale=out_scale, out_i8=o8,
+                               pot=pot), simt=simt)
+        assert torch.equal(o8.float(), ref), "requant simt=%s mismatches %d" % (simt, int((o8.float() != ref).sum()))
+        of = torch.empty(M, N, device=DEV)
+        ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_DEQUANT, acc_scale, bias=bias.to(DEV), out_scale=out_scale, out_f32=of,
+                               out_i8=o8, pot=pot), simt=simt)
+        assert torch.equal(of, ref * out_scale)
+
+
+@pytest.mark.parametrize("M,N,K", [(394, 1536, 384), (200, 768, 192)])
+def test_gemm_gelu(M, N, K):
+    A, W, bias = _gemm_inputs(M, N, K, 30)
+    acc_scale = torch.full((N,), 2.0 ** -13, device=DEV)
+    out_scale = torch.full((N,), 2.0 ** -6, device=DEV)
+    y = _acc_exact(A, W).float() * acc_scale + bias.to(DEV)
+    ref_gpu = (torch.nn.functional.gelu(y) / out_scale).round().clamp(-128, 127)
+    ref_cpu = (torch.nn.functional.gelu(y.cpu()) / out_scale.cpu()).round().clamp(-128, 127)
+    outs = []
+    for simt in (False, True):
+        o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
+        ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_GELU, acc_scale, bias=bias.to(DEV), out_scale=out_scale, out_i8=o8, pot=True),
+                 simt=simt)
+        outs.append(o8.float())
+    assert torch.equal(outs[0], outs[1])
+    # erf implementations (CUDA erff / torch-CUDA / Sleef on the CPU) may differ by an ulp: only rounding ties can flip
+    for ref in (ref_gpu, ref_cpu.to(DEV)):
+        d = (outs[0] - ref).abs()
+        assert d.max() <= 1 and (d != 0).float().mean() < 2e-5, (float(d.max()), float((d != 0).float().mean()))
+
+
+@pytest.mark.parametrize("M,N,K", [(394, 384, 384), (300, 384, 1536), (197, 192, 768)])
+def test_gemm_residual_ptf(M, N, K):
+    A, W, bias = _gemm_inputs(M, N, K, 40)
+    torch.manual_seed(41)
+    fac = torch.tensor([1.0, 2.0, 4.0, 8.0])
+    acc_scale = torch.full((N,), 2.0 ** -14).to(DEV)
+    mid = (0.00931 * fac[torch.randint(0, 4, (N,))]).to(DEV)
+    rs = (0.0123 * fac[torch.randint(0, 4, (N,))]).to(DEV)
+    outs = (0.0171 * fac[torch.randint(0, 4, (N,))]).to(DEV)
+    res = _rand_codes(M, N, seed=42).to(DEV)
+    y = _acc_exact(A, W).float() * acc_scale + bias.to(DEV)
+    c = (y / mid).round().clamp(-128, 127)
+    z = res.float() * rs + c * mid
+    ref = (z / outs).round().clamp(-128, 127)
+    for simt in (False, True):
+        o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
+        ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_RESIDUAL, acc_scale, bias=bias.to(DEV), out_scale=outs, mid_scale=mid,
+                               res_scale=rs, res=res, out_i8=o8), simt=simt)
+        assert torch.equal(o8.float(), ref), "simt=%s mismatches %d" % (simt, int((o8.float() != ref).sum()))
+
+
+def test_gemm_embed_epilogue():
+    B, T, N, K = 3, 196, 192, 768
+    A, W, bias = _gemm_inputs(B * T, N, K, 50)
+    torch.manual_seed(51)
+    acc_scale = torch.full((N,), 2.0 ** -16).to(DEV)
+    s_pe, s_e = torch.tensor([2.0 ** -5]).to(DEV), 2.0 ** -4
+    pos = (torch.randn(T + 1, N) * 0.2).mul(2 ** 10).round().div(2 ** 10).to(DEV)
+    s0 = (0.011 * torch.tensor([1.0, 2.0, 4.0, 8.0])[torch.randint(0, 4, (N,))]).to(DEV)
+    y = _acc_exact(A, W).float() * acc_scale + bias.to(DEV)
+    c = (y / s_pe).round().clamp(-128, 127)
+    e = ((c * s_pe) / s_e).round().clamp(-128, 127)
+    v = (e * s_e).reshape(B, T, N) + pos[1:].unsqueeze(0)
+    ref = (v / s0).round().clamp(-128, 127)
+    for simt in (False, True):
+        out = torch.zeros(B * (T + 1), N, dtype=torch.int8, device=DEV)
+        ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_EMBED, acc_scale, bias=bias.to(DEV), out_scale=s0, mid_scale=s_pe, pos=pos,
+                               aux_scale=s_e, tokens_per_image=T, out_i8=out), simt=simt)
+        cls = _rand_codes(N, seed=52).to(DEV)
+        ops.fill_cls_rows(out, cls, B, T, N)
+        o = out.reshape(B, T + 1, N)
+        assert torch.equal(o[:, 1:].float(), ref)
+        assert torch.equal(o[:, 0], cls.unsqueeze(0).expand(B, -1))
+
+
+def test_gemm_rejects_bad_arguments():
+    A, W, _ = _gemm_inputs(16, 16, 24, 60)
+    with pytest.raises(RuntimeError, match="multiple of 16"):
+        ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_F32, torch.ones(16, device=DEV), out_f32=torch.empty(16, 16, device=DEV)))
+    A, W, _ = _gemm_inputs(16, 16, 32, 61)
+    with pytest.raises(RuntimeError, match="out_scale"):
+        ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_REQUANT, torch.ones(16, device=DEV), out_i8=torch.empty(16, 16, dtype=torch.int8, device=DEV)))
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("C", [128, 192, 384, 768, 1024, 1536])
+@pytest.mark.parametrize("pot", [True, False])
+def test_layernorm_int_vs_oracle(C, pot):
+    torch.manual_seed(C)
+    rows = 197 * 2 + 3
+    fac = torch.tensor([1.0, 2.0, 4.0, 8.0])
+    in_scale = 0.0137 * fac[torch.randint(0, 4, (C,))]
+    in_scale[0] = 0.0137
+    codes = _rand_codes(rows, C, seed=C)
+    x = (codes.float() * in_scale).reshape(1, rows, C)
+    cs = 2.0 ** torch.randint(-3, 3, (C,)).float()
+    nxt = torch.tensor([2.0 ** -6]) if pot else torch.tensor([0.0173])
+    gamma, beta = 1 + 0.2 * torch.randn(C), 0.2 * torch.randn(C)
+    out_scale = nxt * cs
+    ref_f = port.int_layernorm(x, in_scale, out_scale, gamma, beta, exact_sums=True).reshape(rows, C)
+    ref_q = ((ref_f / cs) / nxt).round().clamp(-128, 127)
+    o8 = torch.empty(rows, C, dtype=torch.int8, device=DEV)
+    of = torch.empty(rows, C, device=DEV)
+    a = ops.layernorm_args(codes.to(DEV), rows, C, C, (in_scale / in_scale.min()).round().to(DEV), float(in_scale.min()), gamma.to(DEV),
+                           beta.to(DEV), out_scale.to(DEV), cs.to(DEV), float(nxt), pot, out_i8=o8, out_f32=of)
+    ops.layernorm(a)
+    assert torch.equal(of.cpu(), ref_f), "f32 mismatches %d" % int((of.cpu() != ref_f).sum())
+    assert torch.equal(o8.cpu().float(), ref_q)
+
+
+def test_layernorm_cls_rows_only():
+    torch.manual_seed(7)
+    B, T1, C = 5, 197, 192
+    codes = _rand_codes(B * T1, C, seed=7)
+    in_scale = torch.full((C,), 0.02)
+    gamma, beta, os_ = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C), torch.full((C,), 2.0 ** -5)
+    x = (codes.float() * in_scale).reshape(B, T1, C)
+    ref = port.int_layernorm(x, in_scale, os_, gamma, beta, exact_sums=True)[:, 0]
+    ref_q = (ref / os_).round().clamp(-128, 127)
+    o8 = torch.empty(B, C, dtype=torch.int8, device=DEV)
+    a = ops.layernorm_args(codes.to(DEV), B, C, T1 * C, torch.ones(C, device=DEV), 0.02, gamma.to(DEV), beta.to(DEV), os_.to(DEV),
+                           torch.ones(C, device=DEV), 2.0 ** -5, True, out_i8=o8)
+    ops.layernorm(a)
+    assert torch.equal(o8.cpu().float(), ref_q)
+
+
+# ------------------------------------------------------------------------------------------------ softmax / attention
+@pytest.mark.parametrize("log2s", [-2, -3, -5, -8])
+@pytest.mark.parametrize("n", [197, 49, 64])
+def test_int_softmax_vs_oracle(log2s, n):
+    s = torch.tensor([2.0 ** log2s])
+    codes = _rand_codes(2, 3, 40, n, seed=n + log2s + 100)
+    codes[0, 0, 0, :] = 5          # all-equal row
+    codes[0, 0, 1, :] = -128
+    codes[0, 0, 1, 3] = 127        # one dominant entry
+    ref = port.int_softmax_log2(codes.float() * s, s, 4, exact_sums=True)
+    lut = intmath.lut_to_device(intmath.build_softmax_lut(s), DEV)
+    c = ops.int_softmax_log2(codes.to(DEV), lut).cpu()
+    out = torch.pow(2.0, -c.float())
+    out[c == 255] = 0
+    assert torch.equal(out, ref), "mismatches %d" % int((out != ref).sum())
+
+
+@pytest.mark.parametrize("B,T,H,dh", [(2, 197, 3, 64), (3, 49, 2, 32), (1, 197, 6, 64)])
+def test_attention_vs_oracle(B, T, H, dh):
+    D = H * dh
+    qkv = _rand_codes(B, T, 3 * D, lo=-40, hi=41, seed=T + H)
+    s1, s_as, s2 = 2.0 ** -4, 2.0 ** -3, 2.0 ** -5
+    head_scale = dh ** -0.5 if dh == 64 else 2.0 ** -2
+    x = qkv.float() * s1
+    q, k, v = x.reshape(B, T, 3, H, dh).permute(2, 0, 3, 1, 4)
+    sc = port.fake_quant((q @ k.transpose(-2, -1)) * head_scale, torch.tensor([s_as]), torch.zeros(1), -128, 127, (1, -1, 1, 1))
+    p = port.int_softmax_log2(sc, torch.tensor([s_as]), 4, exact_sums=True)
+    o = (p @ v).transpose(1, 2).reshape(B, T, D)
+    ref = (o / s2).round().clamp(-128, 127)
+    out = torch.empty(B * T, D, dtype=torch.int8, device=DEV)
+    probs = torch.empty(B, H, T, T, dtype=torch.uint8, device=DEV)
+    scores = torch.empty(B, H, T, T, dtype=torch.int8, device=DEV)
+    lut = intmath.lut_to_device(intmath.build_softmax_lut(s_as), DEV)
+    a = ops.attention_args(qkv.to(DEV).contiguous(), out, B, T, H, dh, s1 * s1 * head_scale / s_as, s1 / s2 / 32768.0, lut, probs, scores)
+    ops.attention(a)
+    assert torch.equal(scores.cpu().float(), sc / s_as)
+    pc = probs.cpu()
+    pr = torch.pow(2.0, -pc.float())
+    pr[pc == 255] = 0
+    assert torch.equal(pr, p)
+    assert torch.equal(out.cpu().float().reshape(B, T, D), ref)
+
+
+# ------------------------------------------------------------------------------------------------ observers' kernels
+def test_minmax_and_mse_scores():
+    torch.manual_seed(9)
+    x = torch.randn(4, 197, 192) * 2
+    mm = ops.minmax_per_channel(x.to(DEV)).cpu()
+    assert torch.equal(mm[0], x.reshape(-1, 192).min(0).values) and torch.equal(mm[1], x.reshape(-1, 192).max(0).values)
+    img = torch.randn(2, 3, 64, 64)
+    mm = ops.minmax_per_channel(img.to(DEV)).cpu()
+    assert torch.equal(mm[1], img.permute(1, 0, 2, 3).reshape(3, -1).max(1).values)
+    scales = torch.tensor([[2.0 ** -6], [2.0 ** -5], [2.0 ** -4], [2.0 ** -3]])
+    sc = ops.quant_mse_scores(x.to(DEV), scales, -128, 127).cpu().reshape(-1)
+    ref = torch.stack([((x - port.fake_quant(x, s, torch.zeros(1), -128, 127, (1, 1, -1))).double() ** 2).sum() for s in scales])
+    assert torch.allclose(sc, ref, rtol=1e-6)
+    scp = ops.quant_mse_scores(x.to(DEV), scales, -128, 127, per_channel_out=True).cpu()
+    refp = torch.stack([((x - port.fake_quant(x, s, torch.zeros(1), -128, 127, (1, 1, -1))).double() ** 2).sum((0, 1)) for s in scales])
+    assert torch.allclose(scp, refp, rtol=1e-6)
