@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/s of the fully quantized (W8A8, power-of-two) DeiT-Small forward at 224^2 on
+N B200s (BASELINE.json configs[1]); one "step" = one batch of synthetic images through the hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--model deit_small] [--batch 256]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+  python bench.py --impl reference ...      the reference's CPU algorithm (oracle port) on the host cores
+
+Prints ONE JSON line on rank 0 (contract: task prompt, section 4): `value` = images/s with inputs resident in HBM
+(CUDA events, max over ranks), `e2e` = the same through the public model call with pinned HOST images and a
+device->host read of the logits inside the timed region, `roofline` for the dominant kernel family,
+`cpu_baseline` = the oracle port timed on a bounded sample on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from p2vit_b200 import synth  # noqa: E402
+
+# MACs per image = L*(12*N*D^2 + 2*N^2*D) + 196*768*D + 1000*D
+GMAC = {"deit_tiny": 1.2537, "deit_small": 4.5989, "deit_base": 17.5638, "vit_base": 17.5638, "vit_micro": None}
+
+
+def macs_per_image(name):
+    c = synth.VIT_CONFIGS[name]
+    D, L, N = c["embed_dim"], c["depth"], 197
+    return L * (12 * N * D * D + 2 * N * N * D) + 196 * 768 * D + 1000 * D
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_run(name, batch, steps, warmup, threads=None):
+    """the reference's algorithm (oracle/port.py, fp32 fake-quant, torch CPU ops) on the host cores."""
+    from oracle.port import VitOracle
+
+    torch.set_num_threads(threads or os.cpu_count())
+    c = synth.VIT_CONFIGS[name]
+    o = VitOracle(synth.synth_vit_state_dict(**c, seed=0), **c)
+    state = load_state(name)
+    if state is None:
+        t0 = time.time()
+        o.calibrate(synth.synth_images(4, seed=0))
+        calib_s = time.time() - t0
+    else:
+        o.load_state(state)
+        calib_s = None
+    x = synth.synth_images(batch, seed=1)
+    bits = [8] * (4 * c["depth"] + 2)
+    for _ in range(warmup):
+        o.forward_quant(x, bits)
+    t0 = time.time()
+    for _ in range(steps):
+        out = o.forward_quant(x, bits)
+    dt = time.time() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads(), calib_s, out
+
+
+def load_state(name):
+    p = os.path.join(ROOT, "tests", "golden", "%s_minmax.npz" % name)
+    if not os.path.isfile(p):
+        return None
+    g = np.load(p)
+    return {k[6:]: g[k] for k in g.files if k.startswith("state/")}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--model", default="deit_small")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--calib", type=int, default=32, help="calibration images (whole job)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--golden-state", action="store_true", help="load the reference-calibrated state instead of calibrating on the GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    workload = "%s W8A8 PoT minmax, 224x224, batch %d/GPU" % (args.model, args.batch)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = 8
+        ips, spstep, cores, calib_s, _ = cpu_reference_run(args.model, cb, max(1, min(args.steps, 3)), 1)
+        line = {"impl": "reference", "metric": "images/sec (224^2, int8 PoT)", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+                "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32 (fake-quant int8)", "data": "synthetic",
+                "config": {"workload": workload, "sample": "batch %d per step on the host CPU" % cb},
+                "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                 "sample": "oracle/port.py quantized forward, batch %d" % cb},
+                "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from p2vit_b200 import Config, build_model, calibrate_model, ops
+    from p2vit_b200.engine import VitEngine
+    from p2vit_b200.runner import shard_range
+
+    model = build_model(args.model, Config(True, True, "minmax"), seed=0, device=dev)
+    t0 = time.time()
+    state = load_state(args.model) if args.golden_state else None
+    if state is not None:
+        model.load_quant_state(state)
+        model.model_quant()
+        calib_src = "reference-calibrated state (tests/golden)"
+    else:
+        s, e = shard_range(args.calib, rank, world)
+        calibrate_model(model, synth.synth_images(e - s, seed=0, start=s).to(dev))
+        calib_src = "calibrated on the GPU(s) from %d synthetic images" % args.calib
+    calib_s = time.time() - t0
+    bits = [8] * (4 * model.depth + 2)
+    B = args.batch
+    eng = VitEngine(model, use_graph=True)
+    model._engine = eng
+    host = synth.synth_images(min(B, 64), seed=1, start=rank * B)
+    host = host.repeat((B + host.shape[0] - 1) // host.shape[0], 1, 1, 1)[:B].contiguous().pin_memory()
+    img = eng.static_input(B, bits)
+    img.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: inputs resident in HBM, CUDA-graph replay of the whole forward
+    for _ in range(args.warmup):
+        eng.run_static(B, bits)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        eng.run_static(B, bits)
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_value = float(ms)
+
+    # ---------------- e2e: pinned host images -> H2D -> model(x, bits) -> logits D2H, every step
+    out_host = torch.empty((B, 1000), dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = [torch.empty_like(img) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_steps(n):
+        main_s = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            staging[0].copy_(host, non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n):
+            cur, nxt = i & 1, (i + 1) & 1
+            if i + 1 < n:   # prefetch the next batch while this one computes
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(consumed[nxt])
+                    staging[nxt].copy_(host, non_blocking=True)
+                    ready[nxt].record(copy_stream)
+            main_s.wait_event(ready[cur])
+            logits = model(staging[cur], bits)[0]       # public API call: D2D into the program's input + graph replay
+            consumed[cur].record(main_s)
+            out_host.copy_(logits, non_blocking=True)
+        main_s.synchronize()
+
+    e2e_steps(args.warmup)
+    barrier()
+    ev0.record()
+    e2e_steps(args.steps)
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms)
+    sampler.stop_flag = True
+
+    # ---------------- per-kernel-family device time (eager launches, CUDA events on the launching stream)
+    prog = eng._program(tuple(bits), B)
+    fam_ms, fam_n = {}, {}
+
+    def family(step):
+        if step in ("patchify", "cls"):
+            return step
+        if "norm" in step or step == "qact2" and "blocks" not in step:
+            return "layernorm"
+        if step.endswith("attn.qact2"):
+            return "attention"
+        return "gemm"
+
+    reps = 3
+    for _ in range(reps):
+        for step, fn in prog["steps"]:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            f = family(step)
+            fam_ms[f] = fam_ms.get(f, 0.0) + a.elapsed_time(b)
+            fam_n[f] = fam_n.get(f, 0) + 1
+    fam_ms = {k: v / reps for k, v in fam_ms.items()}
+    fam_n = {k: v // reps for k, v in fam_n.items()}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_gbs, bf16_tf, bf16_tf_sus, peak_src = peaks()
+    total_imgs = B * world * args.steps
+    value = total_imgs / (ms_value * 1e-3)
+    e2e = total_imgs / (ms_e2e * 1e-3)
+    macs = macs_per_image(args.model)
+    c = synth.VIT_CONFIGS[args.model]
+    D, L, T1 = c["embed_dim"], c["depth"], 197
+    top = max(fam_ms, key=fam_ms.get)
+    share = {k: round(v / sum(fam_ms.values()), 4) for k, v in fam_ms.items()}
+    if top == "gemm":
+        lin_macs = L * 12 * T1 * D * D + 196 * 768 * D + 1000 * D
+        ach = 2.0 * lin_macs * B / (fam_ms["gemm"] * 1e-3) / 1e12
+        peak = 2.0 * bf16_tf_sus
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (all %d launches of a step)" % fam_n["gemm"], "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "note": "int8 ops; peak = 2 x %s sustained bf16 cuBLAS (%.0f TF) since MEASURED_PEAKS has no int8 figure (nominal int8 dense 4500)" % (peak_src, bf16_tf_sus)}
+    else:
+        if top == "attention":
+            by = L * B * (T1 * 3 * D + T1 * D)          # qkv codes in, attention codes out
+        elif top == "layernorm":
+            by = (2 * L) * B * T1 * D * 2
+        else:
+            by = B * 3 * 224 * 224 * 5
+        ach = by / (fam_ms[top] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "%s (all %d launches of a step)" % (top, fam_n[top]), "achieved": ach, "peak": hbm_gbs, "unit": "GB/s",
+                "frac": ach / hbm_gbs, "traffic": None, "note": "algorithmic int8 bytes in+out; peak = %s copy bandwidth" % peak_src}
+    roof["device_ms_per_step_by_family"] = {k: round(v, 4) for k, v in fam_ms.items()}
+    roof["share_of_step"] = share
+    roof["tensor_fraction_of_whole_forward"] = 2.0 * macs * value / world / (2.0 * bf16_tf_sus * 1e12)
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        ips, spstep, cores, _, ref_logits = cpu_reference_run(args.model, 8, 2, 1)
+        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": "oracle/port.py (reference algorithm, torch CPU fp32 fake-quant) forward, batch 8 x 2 steps"}
+
+    line = {"metric": "images/sec (224^2, int8 PoT)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 (int32 accumulate, fp32 requant epilogue)", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": B * world, "bit_config": "[8]*%d" % len(bits), "calibration": calib_src,
+                       "calibration_seconds": round(calib_s, 2), "l2": "inputs larger than L2 (fp32 images %.0f MB + int8 workspace per step)" % (B * 3 * 224 * 224 * 4 / 1e6),
+                       "parallelism": "dp%d (batch sharded, no collective in the forward)" % world, "cuda_graph": True},
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 * world, "d2h_bytes_per_step": B * 1000 * 4 * world,
+                    "ms_per_step": ms_e2e / args.steps, "path": "pinned host fp32 images -> H2D (copy stream, double buffered) -> model(x, bit_config) -> logits D2H"},
+            "gpu_launches": eng.launches_per_forward(bits) * args.steps,
+            "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,15 @@ __device__ __forceinline__ int ilog2f(float a) {
   return e - 127;
 }
 
+// floor(fl32(log2(a))) - what `torch.floor(torch.log2(a))` evaluates to (layers.py:272): the fp32 log2 of a value a few
+// ulps below 2^k rounds UP to exactly k, so the floor is k, not k-1 (measured: torch's CPU log2 is correctly rounded at
+// these points).  Only mantissas within 16 ulps of the next power of two can be affected; they take the fp64 path.
+__device__ __forceinline__ int floor_log2_as_fp32(float a) {
+  int e = ilog2f(a);
+  if ((__float_as_uint(a) & 0x007fffffu) >= 0x007ffff0u) e = int(floorf(__double2float_rn(log2(double(a)))));
+  return e;
+}
+
 __device__ __forceinline__ float pow2i(int e) {  // 2^e for -126 <= e <= 127
   return __uint_as_float(uint32_t(e + 127) << 23);
 }

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
           int N;                                                                    // get_MN, layers.py:270-274
           if (aA == 0.f) N = 31;
           else if (!(aA < __int_as_float(0x7f800000))) N = 0;
-          else N = min(max(7 - ilog2f(aA), 0), 31);
+          else N = min(max(7 - floor_log2_as_fp32(aA), 0), 31);
           const float twoN = pow2i(N);
           const float M = fminf(fmaxf(floorf(fmul(aA, twoN)), 0.f), 255.f);
           const float sgn = A > 0.f ? 1.f : (A < 0.f ? -1.f : 0.f);

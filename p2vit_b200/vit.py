@@ -424,6 +424,7 @@ class VisionTransformer(nn.Module):
                     if k in st:
                         m.quantizer.dic_scale[bit] = t(st[k], torch.float32)
                         m.quantizer.dic_zero_point[bit] = t(st["%s.zero_point.%s" % (name, bit)], torch.int64)
+        for name, m in self.named_modules():   # second pass: the children's quantizers are filled now
             if isinstance(m, (Attention, Mlp)) and (name + ".channel_scale") in st:
                 cs = t(st[name + ".channel_scale"], torch.float32)
                 lin, qa = (m.qkv, m.qact0) if isinstance(m, Attention) else (m.fc1, m.qact0)

@@ -290,3 +290,41 @@ def test_minmax_and_mse_scores():
     scp = ops.quant_mse_scores(x.to(DEV), scales, -128, 127, per_channel_out=True).cpu()
     refp = torch.stack([((x - port.fake_quant(x, s, torch.zeros(1), -128, 127, (1, 1, -1))).double() ** 2).sum((0, 1)) for s in scales])
     assert torch.allclose(scp, refp, rtol=1e-6)
+
+
+def test_layernorm_floor_log2_follows_fp32_rounding():
+    """|A| a few ulps below 2^k: torch.log2 rounds up to k in fp32, so the reference's floor(log2|A|) is k (not k-1) and
+    (M, N) change (layers.py:270-274).  gamma is searched so that this happens in every channel of the row."""
+    torch.manual_seed(11)
+    C = 128
+    codes = _rand_codes(3, C, seed=77)
+    in_scale = torch.full((C,), 0.0211)
+    os_ = torch.full((C,), 2.0 ** -6)
+    x = (codes.float() * in_scale).reshape(1, 3, C)
+    xq = codes.float()
+    s1 = in_scale.min()
+    std = (s1 / C) * torch.sqrt(C * (xq ** 2).sum(-1) - xq.sum(-1) ** 2)
+    t = (s1 / std)[0]                                  # row 0
+    gamma = torch.ones(C)
+    hits = 0
+    for c in range(C):
+        k = (c % 6) - 3
+        target = np.nextafter(np.float32(2.0 ** k), np.float32(0))
+        g0 = np.float32(float(target) * float(os_[c]) / float(t))
+        for step in range(-64, 65):
+            g = np.float32(g0)
+            for _ in range(abs(step)):
+                g = np.nextafter(g, np.float32(np.inf if step > 0 else 0))
+            A = (t * torch.tensor(g)) / os_[c]
+            if float(A) == float(target):
+                gamma[c] = float(g)
+                hits += 1
+                break
+    assert hits > C // 2
+    beta = 0.1 * torch.randn(C)
+    ref = port.int_layernorm(x, in_scale, os_, gamma, beta, exact_sums=True).reshape(3, C)
+    of = torch.empty(3, C, device=DEV)
+    a = ops.layernorm_args(codes.to(DEV), 3, C, C, torch.ones(C, device=DEV), float(s1), gamma.to(DEV), beta.to(DEV), os_.to(DEV),
+                           torch.ones(C, device=DEV), 1.0, True, out_f32=of)
+    ops.layernorm(a)
+    assert torch.equal(of.cpu(), ref), "mismatches %d" % int((of.cpu() != ref).sum())

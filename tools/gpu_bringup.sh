@@ -9,3 +9,4 @@ run gemm_tc python -m pytest tests/test_gpu_ops.py -q -m gpu -k "gemm_f32 and tc
 run gemm_epi python -m pytest tests/test_gpu_ops.py -q -m gpu -k "gemm and not gemm_f32" -p no:cacheprovider
 run attention python -m pytest tests/test_gpu_ops.py -q -m gpu -k "attention" -p no:cacheprovider
 run model python -m pytest tests/test_gpu_model.py -q -m gpu -p no:cacheprovider
+run diag python tools/diag_parity.py deit_tiny 8 8
