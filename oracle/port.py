@@ -22,11 +22,12 @@ Reference map (file:line relative to /root/reference):
                         models/vit_fquant.py:177-407,489-596,830-939,
                         models/layers_quant.py:225-393,462-497, test_quant.py:262-312
 
-`exact_sums=True` replaces the two order-dependent fp32 row reductions of the reference
-(sum of squares in LayerNorm, layers.py:316-318; sum of exp_int in softmax, :416) by
-exactly-rounded sums (fp64/int accumulation, one final rounding to fp32).  That is the
-definition the CUDA kernels implement (order independent, batch-split invariant); see
-DESIGN.md "tie adjudication".
+`exact_sums=True` is the canonical, backend-independent variant the CUDA kernels implement: the two
+order-dependent fp32 row reductions of the reference (sum of squares in LayerNorm, layers.py:316-318;
+sum of exp_int in softmax, :416) become exactly-rounded sums (fp64/int accumulation, one final rounding
+to fp32), and LayerNorm's sqrt is the IEEE correctly-rounded one (torch's CPU sqrt is MKL VML, off by one
+ulp on ~0.1% of inputs; torch-CUDA's is IEEE).  Order independent, batch-split invariant; see DESIGN.md
+"tie adjudication".
 """
 import math
 
@@ -251,7 +252,11 @@ def int_layernorm(x, in_scale, out_scale, weight, bias, exact_sums=False, in_sca
         sum_x = x_q.sum(dim=-1)
         sum_sq = (x_q ** 2).sum(dim=-1)
         mean = x_q.mean(dim=-1) * s1
-    std = (s1 / C) * torch.sqrt(C * sum_sq - sum_x ** 2)
+    var = C * sum_sq - sum_x ** 2
+    # torch's CPU sqrt goes through MKL VML (<= 1 ulp, not correctly rounded: ~0.1% of inputs differ from IEEE sqrt, which is
+    # what torch-CUDA and the kernels compute); the canonical (exact) variant uses the correctly rounded one
+    root = torch.from_numpy(np.sqrt(var.numpy())) if exact_sums else torch.sqrt(var)
+    std = (s1 / C) * root
     g = weight.reshape(1, 1, -1)
     A = (s1 / std).unsqueeze(-1) * g / out_scale
     N = torch.clamp(7 - torch.floor(torch.log2(A.abs())), 0, 31)

@@ -1,0 +1,141 @@
+"""CPU: host-side logic of the product - softmax table builder vs the oracle, data-parallel sharding, the drop-in
+surface (names, signatures, defaults), seeded synthetic data, and the world_size-2 statistics all-reduce (gloo)."""
+import inspect
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import port
+from p2vit_b200 import Config, intmath, synth
+from p2vit_b200.runner import accuracy, shard_range
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lut_softmax(codes, lut):
+    """numpy emulation of csrc softmax_kernel / attention: exact table sums + log2 rounding"""
+    c = codes.astype(np.int64)
+    d = c.max(-1, keepdims=True) - c
+    e_int = (lut["hi"].astype(object) << 32) + lut["lo"].astype(object)
+    tot = e_int[d].sum(-1, keepdims=True)
+    tot_f = np.vectorize(lambda v: port._int_to_f32_rne(int(v)), otypes=[np.float32])(tot)
+    x = np.rint((tot_f / lut["exp_f32"][d]).astype(np.float32))
+    u = x.view(np.uint32).astype(np.int64)
+    big = ((u + 0x00400000) >> 23) - 127
+    p = np.where(big >= 16, 0.0, 2.0 ** (-np.minimum(big, 15).astype(np.float64))).astype(np.float32)
+    return p
+
+
+@pytest.mark.parametrize("log2s", [-2, -3, -4, -6, -9])
+def test_softmax_table_reproduces_oracle(log2s):
+    s = torch.tensor([2.0 ** log2s])
+    g = torch.Generator().manual_seed(log2s + 50)
+    codes = torch.randint(-128, 128, (3, 2, 30, 197), generator=g)
+    ref = port.int_softmax_log2(codes.float() * s, s, 4, exact_sums=True).numpy()
+    got = _lut_softmax(codes.numpy(), intmath.build_softmax_lut(s))
+    assert np.array_equal(got, ref)
+
+
+def test_softmax_table_rejects_unrepresentable_scale():
+    with pytest.raises(NotImplementedError):
+        intmath.build_softmax_lut(torch.tensor(2.0 ** -40))
+
+
+def test_is_pot():
+    assert intmath.is_pot(torch.tensor([0.5, 2.0 ** -9, 4.0])) and not intmath.is_pot(torch.tensor([0.5, 0.3]))
+
+
+def test_shard_range_partitions_exactly():
+    for n in (1, 7, 32, 256, 1000):
+        for w in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synthetic_data_is_deterministic_and_shardable():
+    a = synth.synth_images(4, seed=3)
+    b = torch.cat([synth.synth_images(2, seed=3), synth.synth_images(2, seed=3, start=2)])
+    assert torch.equal(a, b)
+    sd1 = synth.synth_vit_state_dict(**synth.VIT_CONFIGS["vit_micro"], seed=0)
+    sd2 = synth.synth_vit_state_dict(**synth.VIT_CONFIGS["vit_micro"], seed=0)
+    assert all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+    assert float(sd1["blocks.0.attn.qkv.weight"].abs().sum()) != float(synth.synth_vit_state_dict(**synth.VIT_CONFIGS["vit_micro"], seed=1)["blocks.0.attn.qkv.weight"].abs().sum())
+
+
+def test_config_defaults_match_reference():
+    c = Config()
+    assert (c.BIT_TYPE_W.name, c.BIT_TYPE_A.name, c.BIT_TYPE_S.name) == ("int4", "int8", "uint4")
+    assert (c.OBSERVER_W, c.OBSERVER_A, c.OBSERVER_A_LN, c.OBSERVER_S) == ("minmax", "minmax", "ptf", "minmax")
+    assert (c.CALIBRATION_MODE_W, c.CALIBRATION_MODE_A, c.CALIBRATION_MODE_A_LN) == ("channel_wise", "layer_wise", "channel_wise")
+    assert c.INT_SOFTMAX and c.INT_NORM and c.QUANTIZER_S == "log2"
+    c = Config(ptf=False, lis=False, quant_method="ema")
+    assert not c.INT_NORM and not c.INT_SOFTMAX and c.OBSERVER_A_LN == "ema" and c.BIT_TYPE_S.name == "uint8"
+    assert Config("False", "0").INT_NORM is False
+
+
+def test_drop_in_surface():
+    import p2vit_b200 as P
+    from p2vit_b200.ptq import BIT_TYPE_DICT
+    from p2vit_b200.ptq.observer import str2observer
+    from p2vit_b200.ptq.quantizer import str2quantizer
+
+    assert sorted(BIT_TYPE_DICT) == ["int4", "int8", "uint3", "uint4", "uint8"]
+    assert (BIT_TYPE_DICT["int4"].lower_bound, BIT_TYPE_DICT["int4"].upper_bound, BIT_TYPE_DICT["uint4"].upper_bound) == (-8, 7, 15)
+    assert sorted(str2observer) == ["ema", "minmax", "omse", "percentile", "ptf"] and sorted(str2quantizer) == ["log2", "uniform"]
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(P.QLinear.forward) == ["self", "x", "global_distance", "bit_config", "weight_smoothed", "attn", "attn_para"]
+    assert sig(P.QAct.forward) == ["self", "x", "asymmetric", "attn", "attn_para"]
+    assert sig(P.QIntLayerNorm.forward) == ["self", "x", "in_quantizer", "out_quantizer", "out_quantizer_scale", "in_scale_expand"]
+    assert sig(P.QIntSoftmax.forward) == ["self", "x", "scale"] and sig(P.QConv2d.forward) == ["self", "x", "bit_config"]
+    assert sig(P.QLinear.__init__)[1:] == ["in_features", "out_features", "bias", "quant", "calibrate", "last_calibrate", "bit_type",
+                                           "calibration_mode", "observer_str", "quantizer_str"]
+    m = P.deit_tiny_patch16_224(cfg=Config())
+    ref_keys = set(synth.synth_vit_state_dict(**synth.VIT_CONFIGS["deit_tiny"]))
+    assert set(m.state_dict()) == ref_keys
+    for meth in ("model_quant", "model_dequant", "model_open_calibrate", "model_open_last_calibrate", "model_close_calibrate"):
+        assert hasattr(m, meth)
+    assert sig(m.forward) == ["x", "bit_config", "plot", "hessian_statistic"]
+    assert len(m.flops_list()) == 50
+    with pytest.raises(RuntimeError):
+        P.deit_tiny_patch16_224(pretrained=True, cfg=Config())
+
+
+def test_accuracy_counts():
+    out = torch.tensor([[0.1, 0.9, 0.0], [0.8, 0.1, 0.1], [0.2, 0.3, 0.5]])
+    c1, c2 = accuracy(out, torch.tensor([1, 2, 2]), (1, 2))
+    assert float(c1) == 2 and float(c2) == 2
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from p2vit_b200.ptq.observer.utils import allreduce_
+from p2vit_b200.runner import shard_range
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+full = torch.arange(40, dtype=torch.float32).reshape(10, 4) * (1 if True else 0)
+a, b = shard_range(10, r, w)
+mine = full[a:b]
+mx = allreduce_(mine.max(0).values.clone(), "max"); mn = allreduce_(mine.min(0).values.clone(), "min")
+sc = allreduce_((mine ** 2).sum(0).double(), "sum")
+assert torch.equal(mx, full.max(0).values) and torch.equal(mn, full.min(0).values) and torch.equal(sc, (full ** 2).sum(0).double())
+print("rank", r, "ok")
+dist.destroy_process_group()
+'''
+
+
+def test_statistics_allreduce_world2_gloo(tmp_path):
+    """calibration statistics are MAX/MIN/SUM all-reduced so every rank freezes identical scales (NCCL on GPUs, gloo here)"""
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29641", str(script)], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
