@@ -1,6 +1,13 @@
 // Fused GEMM epilogues: one thread owns NC consecutive output columns of one row (int32 accumulators in
 // registers, read from TMEM by the tcgen05 kernel or produced by dp4a in the SIMT cross-check kernel).
 // Reference call sites per mode are listed in include/p2vit_b200.h (p2v_epilogue_t).
+//
+// Per-column parameters are staged once per output tile into shared memory as a small struct-of-arrays
+// (ColParams) together with derived values (reciprocals, folded scales), so the per-element work is pure
+// register math + broadcast LDS.128.  Divisions by non-power-of-two scales use quant_div(): an exact
+// shortcut (multiply by the correctly rounded reciprocal, round) that falls back to the IEEE division only
+// when the quotient is within 1e-3 of a rounding tie - the result is always identical to
+// rint(__fdiv_rn(y, s)) (see DESIGN.md "exact fast requantisation").
 #pragma once
 #include "common.cuh"
 
@@ -32,48 +39,143 @@ inline EpiParams make_epi_params(const p2v_gemm_args& a) {
   return p;
 }
 
-// y = fl(acc * acc_scale + bias): acc*acc_scale is one rounding (exact for PoT), + bias a second one
-__device__ __forceinline__ float acc_to_y(int acc, float s, float b) { return fadd(fmul(float(acc), s), b); }
+// sat(RNE(fl(y / s))) with rs = RN(1/s).  |y*rs - fl(y/s)| <= |q| * 3 * 2^-24, so away from a tie the rounded
+// integers agree; within the guard band the IEEE quotient decides.  Saturation makes large |q| irrelevant.
+__device__ __forceinline__ float quant_div(float y, float s, float rs) {
+  const float qa = fmul(y, rs);
+  float k = rintf(qa);
+  const float d = fabsf(fsub(qa, k));
+  if (d > 0.499f && fabsf(qa) < 300.f) k = rintf(fdiv(y, s));
+  return fminf(fmaxf(k, -128.f), 127.f);
+}
 
-// Processes columns [col0, col0+NC) of row `row`; NC is a multiple of 4; col0 % 4 == 0; N % 4 == 0 is NOT
-// required (tail columns are masked element-wise on store).
-template <int EPI, bool POT, int NC>
-__device__ __forceinline__ void epilogue_row(const EpiParams& p, int row, int col0, const int (&acc)[NC]) {
+// column-parameter tile in shared memory: CP_ROWS arrays of BN floats
+constexpr int CP_ROWS = 8;
+enum { CP_S = 0, CP_B = 1, CP_O = 2, CP_RO = 3, CP_M = 4, CP_RM = 5, CP_RS = 6, CP_Z = 7 };
+
+// thread `t` of a group stages column n = n0 + t (t < BN)
+template <int EPI, bool POT, int BN>
+__device__ __forceinline__ void stage_col_params(const EpiParams& p, float* cp, int n0, int t) {
+  if (t >= BN) return;
+  const int n = n0 + t;
+  const bool ok = n < p.N;
+  const float s = ok ? __ldg(p.acc_scale + n) : 0.f;
+  const float b = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+  const float o = (ok && EPI != P2V_EPI_F32) ? __ldg(p.out_scale + n) : 1.f;
+  const float ro = fdiv(1.f, o);
+  if (POT && (EPI == P2V_EPI_REQUANT || EPI == P2V_EPI_DEQUANT)) {
+    // y/o == fma(acc, s*ro, b*ro) exactly: ro is a power of two, scaling commutes with rounding
+    cp[CP_S * BN + t] = fmul(s, ro);
+    cp[CP_B * BN + t] = fmul(b, ro);
+  } else {
+    cp[CP_S * BN + t] = s;
+    cp[CP_B * BN + t] = b;
+  }
+  cp[CP_O * BN + t] = o;
+  cp[CP_RO * BN + t] = ro;
+  if (EPI == P2V_EPI_RESIDUAL) {
+    const float m = ok ? __ldg(p.mid_scale + n) : 1.f;
+    cp[CP_M * BN + t] = m;
+    cp[CP_RM * BN + t] = fdiv(1.f, m);
+    cp[CP_RS * BN + t] = ok ? __ldg(p.res_scale + n) : 0.f;
+  }
+  cp[CP_Z * BN + t] = (ok && p.zp_corr) ? __int_as_float(__ldg(p.zp_corr + n)) : __int_as_float(0);
+}
+
+// Processes columns [col0, col0+NC) of row `row`, col0 = n0 + c0 with c0 the offset inside the staged tile.
+// NC is a multiple of 4.  Tail columns (>= N) are masked on store.
+template <int EPI, bool POT, int BN, int NC>
+__device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp, int row, int n0, int c0, const int (&acc)[NC]) {
   if (row >= p.M) return;
   const int N = p.N;
+  const int col0 = n0 + c0;
   int q[NC];
   float f[NC];
+  const bool has_zp = p.zp_corr != nullptr;
+  uint32_t resw[NC / 4];
+  if (EPI == P2V_EPI_RESIDUAL) {
+    const int8_t* rp = p.res + size_t(row) * N + col0;
+    if ((N & 15) == 0 && (NC & 15) == 0 && col0 + NC <= N) {
 #pragma unroll
-  for (int j = 0; j < NC; ++j) {
-    const int n = col0 + j;
-    if (n >= N) { q[j] = 0; f[j] = 0.f; continue; }
-    int a = acc[j];
-    if (p.zp_corr) a -= __ldg(p.zp_corr + n);
-    const float y = acc_to_y(a, __ldg(p.acc_scale + n), p.bias ? __ldg(p.bias + n) : 0.f);
-    if (EPI == P2V_EPI_F32) { f[j] = y; continue; }
-    const float so = __ldg(p.out_scale + n);
-    const float rso = POT ? fdiv(1.f, so) : 0.f;
-    if (EPI == P2V_EPI_REQUANT) {
-      q[j] = quant_s8<POT>(y, so, rso);
-    } else if (EPI == P2V_EPI_GELU) {
-      q[j] = quant_s8<POT>(gelu_erf(y), so, rso);
-    } else if (EPI == P2V_EPI_DEQUANT) {
-      q[j] = quant_s8<POT>(y, so, rso);
-      f[j] = fmul(float(q[j]), so);
-    } else if (EPI == P2V_EPI_RESIDUAL) {
-      const float sm = __ldg(p.mid_scale + n);
-      const int c = sat_s8(fdiv(y, sm));
-      const float t = fmul(float(c), sm);
-      const int r = int(__ldg(p.res + size_t(row) * N + n));
-      const float z = fadd(fmul(float(r), __ldg(p.res_scale + n)), t);
-      q[j] = sat_s8(fdiv(z, so));
-    } else if (EPI == P2V_EPI_EMBED) {
-      const float sm = __ldg(p.mid_scale);
-      const int c = sat_s8(fdiv(y, sm));
-      const int e = sat_s8(fdiv(fmul(float(c), sm), p.aux_scale));
-      const int tok = row % p.tokens_per_image;
-      const float v = fadd(fmul(float(e), p.aux_scale), __ldg(p.pos + size_t(tok + 1) * N + n));
-      q[j] = sat_s8(fdiv(v, so));
+      for (int j = 0; j < NC / 16; ++j) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+        resw[4 * j] = v.x; resw[4 * j + 1] = v.y; resw[4 * j + 2] = v.z; resw[4 * j + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col0 + 4 * j + e < N) w |= (uint32_t(uint8_t(rp[4 * j + e])) << (8 * e));
+        resw[j] = w;
+      }
+    }
+  }
+  float e_sm = 0.f, e_rsm = 0.f, e_raux = 0.f;
+  int tok = 0;
+  if (EPI == P2V_EPI_EMBED) {
+    e_sm = __ldg(p.mid_scale);
+    e_rsm = fdiv(1.f, e_sm);
+    e_raux = fdiv(1.f, p.aux_scale);
+    tok = row % p.tokens_per_image;
+  }
+#pragma unroll
+  for (int j4 = 0; j4 < NC; j4 += 4) {
+    const float4 S4 = *reinterpret_cast<const float4*>(cp + CP_S * BN + c0 + j4);
+    const float4 B4 = *reinterpret_cast<const float4*>(cp + CP_B * BN + c0 + j4);
+    const float4 O4 = *reinterpret_cast<const float4*>(cp + CP_O * BN + c0 + j4);
+    const float4 R4 = *reinterpret_cast<const float4*>(cp + CP_RO * BN + c0 + j4);
+    const float Sv[4] = {S4.x, S4.y, S4.z, S4.w}, Bv[4] = {B4.x, B4.y, B4.z, B4.w};
+    const float Ov[4] = {O4.x, O4.y, O4.z, O4.w}, Rv[4] = {R4.x, R4.y, R4.z, R4.w};
+    float Mv[4], RMv[4], RSv[4];
+    if (EPI == P2V_EPI_RESIDUAL) {
+      const float4 M4 = *reinterpret_cast<const float4*>(cp + CP_M * BN + c0 + j4);
+      const float4 RM4 = *reinterpret_cast<const float4*>(cp + CP_RM * BN + c0 + j4);
+      const float4 RS4 = *reinterpret_cast<const float4*>(cp + CP_RS * BN + c0 + j4);
+      Mv[0] = M4.x; Mv[1] = M4.y; Mv[2] = M4.z; Mv[3] = M4.w;
+      RMv[0] = RM4.x; RMv[1] = RM4.y; RMv[2] = RM4.z; RMv[3] = RM4.w;
+      RSv[0] = RS4.x; RSv[1] = RS4.y; RSv[2] = RS4.z; RSv[3] = RS4.w;
+    }
+    int4 Z4 = make_int4(0, 0, 0, 0);
+    if (has_zp) Z4 = *reinterpret_cast<const int4*>(cp + CP_Z * BN + c0 + j4);
+    const int Zv[4] = {Z4.x, Z4.y, Z4.z, Z4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = j4 + e;
+      const float af = float(acc[j] - Zv[e]);
+      if (POT && (EPI == P2V_EPI_REQUANT || EPI == P2V_EPI_DEQUANT)) {
+        const float yq = __fmaf_rn(af, Sv[e], Bv[e]);        // == fl(fl(acc*s) + b) / o  (s, o powers of two)
+        q[j] = sat_s8(yq);
+        if (EPI == P2V_EPI_DEQUANT) f[j] = fmul(float(q[j]), Ov[e]);
+        continue;
+      }
+      const float y = fadd(fmul(af, Sv[e]), Bv[e]);
+      if (EPI == P2V_EPI_F32) {
+        f[j] = y;
+      } else if (EPI == P2V_EPI_REQUANT) {
+        q[j] = int(quant_div(y, Ov[e], Rv[e]));
+      } else if (EPI == P2V_EPI_DEQUANT) {
+        const float k = quant_div(y, Ov[e], Rv[e]);
+        q[j] = int(k);
+        f[j] = fmul(k, Ov[e]);
+      } else if (EPI == P2V_EPI_GELU) {
+        const float g = gelu_erf(y);
+        q[j] = POT ? sat_s8(fmul(g, Rv[e])) : int(quant_div(g, Ov[e], Rv[e]));
+      } else if (EPI == P2V_EPI_RESIDUAL) {
+        const float c = quant_div(y, Mv[e], RMv[e]);
+        const float t = fmul(c, Mv[e]);
+        const float r = float(int(int8_t((resw[j >> 2] >> (8 * (j & 3))) & 0xffu)));
+        const float z = fadd(fmul(r, RSv[e]), t);
+        q[j] = int(quant_div(z, Ov[e], Rv[e]));
+      } else if (EPI == P2V_EPI_EMBED) {
+        const float c = quant_div(y, e_sm, e_rsm);
+        const float ecode = quant_div(fmul(c, e_sm), p.aux_scale, e_raux);
+        const int n = col0 + j;
+        const float pv = n < N ? __ldg(p.pos + size_t(tok + 1) * N + n) : 0.f;
+        const float v = fadd(fmul(ecode, p.aux_scale), pv);
+        q[j] = int(quant_div(v, Ov[e], Rv[e]));
+      }
     }
   }
   size_t orow = size_t(row);

@@ -10,9 +10,14 @@ constexpr int SIMT_THREADS = 128;
 
 template <int EPI, bool POT>
 __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ W, EpiParams p) {
-  // block = 16 rows x 8 column-groups(64 cols); thread = 1 row x 8 cols
+  // block = 16 rows x 8 column-groups (64 cols); thread = 1 row x 8 cols
+  __shared__ __align__(16) float cp[CP_ROWS * 64];
+  const int n0 = blockIdx.x * 64;
+  stage_col_params<EPI, POT, 64>(p, cp, n0, int(threadIdx.x));
+  __syncthreads();
   const int row = blockIdx.y * 16 + threadIdx.x / 8;
-  const int col0 = (blockIdx.x * 8 + threadIdx.x % 8) * SIMT_NC;
+  const int c0 = (threadIdx.x % 8) * SIMT_NC;
+  const int col0 = n0 + c0;
   if (row >= p.M || col0 >= p.N) return;
   int acc[SIMT_NC];
 #pragma unroll
@@ -32,7 +37,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const int8_t* _
       }
     }
   }
-  epilogue_row<EPI, POT, SIMT_NC>(p, row, col0, acc);
+  epilogue_row<EPI, POT, 64, SIMT_NC>(p, cp, row, n0, c0, acc);
 }
 
 int launch_gemm_simt(const p2v_gemm_args& a, cudaStream_t stream) {

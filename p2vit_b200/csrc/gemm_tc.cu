@@ -4,13 +4,16 @@
 //   (A, W K-major, one elected thread) -> int32 accumulators in TMEM (2 stages) -> tcgen05.ld -> epilogue
 //   in registers (epilogue.cuh) -> int8 / fp32 stores.
 //
-// Persistent, warp-specialised CTA of 10 warps (1 CTA per SM):
-//   warp 0      TMA producer          (lane 0)
-//   warp 1      TMEM allocator + MMA issuer (lane 0)
-//   warps 2-5   epilogue group 0  (accumulator stage 0: this CTA's even tiles)
-//   warps 6-9   epilogue group 1  (accumulator stage 1: odd tiles)
+// Persistent, warp-specialised CTA of 18 warps (1 CTA per SM):
+//   warp 0        TMA producer                (lane 0)
+//   warp 1        TMEM allocator + MMA issuer (lane 0)
+//   warps 2-17    four epilogue groups of 4 warps; group g owns TMEM accumulator stage g and this CTA's tiles
+//                 g, g+4, g+8, ...  The epilogue is the ALU-bound part of these GEMMs (K is only 384..1536, every
+//                 output element needs a requantisation), so 16 of the 18 warps work on it and the MMA of the next
+//                 three tiles runs underneath.
 // A warp may only read the TMEM lane quarter (warp_id % 4), so each group of 4 consecutive warps covers
-// the 128 accumulator rows.  Tiles are enumerated n-fastest so the CTAs running at the same time share
+// the 128 accumulator rows.  Per-column epilogue parameters are staged per tile in shared memory (double buffered
+// per group, one named barrier per tile).  Tiles are enumerated n-fastest so the CTAs running at the same time share
 // the A row-block through L2 and the (small) weight matrix stays L2 resident.
 #include <cuda.h>
 #include <unordered_map>
@@ -22,7 +25,8 @@ namespace p2v {
 constexpr int BM = 128;
 constexpr int BK = 128;           // one 128-byte swizzle row of int8
 constexpr int UMMA_K = 32;        // K per tcgen05.mma for 8-bit operands
-constexpr int TC_THREADS = 320;
+constexpr int TC_GROUPS = 4;       // epilogue groups == TMEM accumulator stages
+constexpr int TC_THREADS = 64 + TC_GROUPS * 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
@@ -84,6 +88,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void group_barrier(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor):
 // start address>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
 // 8-row groups | version=1 [46,48) | layout type [61,64) = 2 (SWIZZLE_128B)
@@ -107,21 +122,24 @@ template <int BN, int STAGES, int EPI, bool POT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p, int tiles_m, int tiles_n) {
   constexpr uint32_t A_BYTES = BM * BK, B_BYTES = BN * BK, STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages (power of two: BN in {64,128,256})
+  constexpr uint32_t TMEM_COLS = TC_GROUPS * BN;  // one accumulator stage per epilogue group (power of two)
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+  constexpr int NCH = (EPI == P2V_EPI_REQUANT || EPI == P2V_EPI_DEQUANT || EPI == P2V_EPI_F32) ? 32 : 16;  // columns per TMEM load
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 2 * TC_GROUPS];
+  __shared__ __align__(16) float col_params[TC_GROUPS][2][CP_ROWS * BN];
   __shared__ uint32_t tmem_slot;
 
   const uint32_t tiles = uint32_t(tiles_m) * uint32_t(tiles_n);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t stage0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
-  const uint32_t bar_tfull = smem_u32(&bars[2 * STAGES]), bar_tempty = smem_u32(&bars[2 * STAGES + 2]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * STAGES]), bar_tempty = smem_u32(&bars[2 * STAGES + TC_GROUPS]);
   const int nkb = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(bar_tfull + 8 * g, 1); mbar_init(bar_tempty + 8 * g, 4); }
+    for (int g = 0; g < TC_GROUPS; ++g) { mbar_init(bar_tfull + 8 * g, 1); mbar_init(bar_tempty + 8 * g, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -157,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = make_i8_idesc(BM, BN, true, true);
       uint32_t it = 0, local = 0;
       for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
-        const uint32_t g = local & 1u, use = local >> 1;
+        const uint32_t g = local % TC_GROUPS, use = local / TC_GROUPS;
         mbar_wait(bar_tempty + 8 * g, (use & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + g * BN;
@@ -177,23 +195,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================= epilogue groups =================
-    const uint32_t g = uint32_t(warp - 2) >> 2;          // 0: warps 2-5, 1: warps 6-9
+    const uint32_t g = uint32_t(warp - 2) >> 2;          // group == accumulator stage
     const uint32_t quarter = uint32_t(warp) & 3u;        // TMEM lane quarter this warp may access
-    uint32_t local = 0;
-    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
-      if ((local & 1u) != g) continue;
-      const uint32_t use = local >> 1;
+    const int tg = int(threadIdx.x) - 64 - int(g) * 128;  // thread index inside the group
+    uint32_t use = 0;
+    for (uint32_t t = blockIdx.x + g * gridDim.x; t < tiles; t += TC_GROUPS * gridDim.x, ++use) {
       const int m0 = int(t / tiles_n) * BM, n0 = int(t % tiles_n) * BN;
+      float* cp = col_params[g][use & 1u];
+      stage_col_params<EPI, POT, BN>(p, cp, n0, tg);     // overlaps the MMA of this tile
+      group_barrier(1 + g);
       mbar_wait(bar_tfull + 8 * g, use & 1u);
       tc_fence_after();
       const int row = m0 + int(quarter) * 32 + lane;
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + g * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (n0 + c * 32 >= p.N) break;
-        int acc[32];
-        tmem_ld32(taddr + c * 32, acc);
-        epilogue_row<EPI, POT, 32>(p, row, n0 + c * 32, acc);
+      for (int c = 0; c < BN / NCH; ++c) {
+        if (n0 + c * NCH >= p.N) break;
+        int acc[NCH];
+        __syncwarp();
+        if (NCH == 32) tmem_ld32(taddr + c * NCH, reinterpret_cast<int(&)[32]>(acc[0]));
+        else tmem_ld16(taddr + c * NCH, reinterpret_cast<int(&)[16]>(acc[0]));
+        epilogue_row<EPI, POT, BN, NCH>(p, cp, row, n0, c * NCH, acc);
       }
       tc_fence_before();
       __syncwarp();
@@ -267,8 +289,8 @@ static int launch_tc_bn(const p2v_gemm_args& a, cudaStream_t stream) {
 }
 
 int launch_gemm_tc(const p2v_gemm_args& a, cudaStream_t stream) {
-  // BN = 128: 32 KB / stage, 6 stages, 256 TMEM columns.  (BN = 256 variant: see DESIGN.md tuning notes.)
-  return launch_tc_bn<128, 6>(a, stream);
+  // BN = 128: 32 KB / smem stage, 5 stages, 4 x 128 TMEM columns
+  return launch_tc_bn<128, 5>(a, stream);
 }
 
 }  // namespace p2v

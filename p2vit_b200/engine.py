@@ -103,7 +103,7 @@ class VitPlan:
             p["ln1"] = self._ln(blk.norm1, last, a0 * cs_a, cs_a, float(a0), dev)
             p["qkv"] = _Gemm(a.qkv, a.qkv.weight * cs_a.reshape(1, -1), b4[0], a0, dev)
             p["qkv_out"] = _vec(a1, 3 * D, dev)
-            p["qkv_pot"] = intmath.is_pot(a1)
+            p["qkv_pot"] = intmath.is_pot(a1) and intmath.is_pot(p["qkv"].acc_scale)
             dh = D // m.num_heads
             p["score_mult"] = float(a1.double() * a1.double() * a.scale / as_.double())
             p["out_mult"] = float(a1.double() / a2.double() / 32768.0)
@@ -131,7 +131,7 @@ class VitPlan:
         self.head = _Gemm(m.head, m.head.weight, bits[-1], q2, dev)
         ao = _sym_scale(m.act_out, "act_out")
         self.head_out = _vec(ao, self.head.N, dev)
-        self.head_pot = intmath.is_pot(ao)
+        self.head_pot = intmath.is_pot(ao) and intmath.is_pot(self.head.acc_scale)
 
     @staticmethod
     def _ln(norm, in_scale, out_scale, post_div, next_scale, dev):
