@@ -161,7 +161,11 @@ typedef struct {
   int8_t* scores_or_null;   /* optional dump of qact_attn1 codes [B,H,T,T] (tests) */
 } p2v_attention_args;
 
+/* Head dim 64, T <= 224 and no debug dumps: tcgen05 kernel (csrc/attention_tc.cu: TMA-fed S = q k^T and O = P v on
+ * the tensor cores, accumulators in TMEM, softmax per TMEM row); otherwise the dp4a kernel (csrc/attention.cu). */
 int p2v_attention_i8(const p2v_attention_args* args_host, void* stream);
+/* same contract, always on CUDA cores (dp4a); used by tests to cross-check the tcgen05 kernel */
+int p2v_attention_i8_simt(const p2v_attention_args* args_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Calibration observers                           (observer/minmax.py:15-32, ptf.py:13-30, base.py:16-29)

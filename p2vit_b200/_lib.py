@@ -67,6 +67,7 @@ SYMBOLS = {
     "p2v_layernorm_int": (_I, [C.POINTER(LayerNormArgs), _P]),
     "p2v_int_softmax_log2": (_I, [_P, _P, _I64, _I, _P, _P]),
     "p2v_attention_i8": (_I, [C.POINTER(AttentionArgs), _P]),
+    "p2v_attention_i8_simt": (_I, [C.POINTER(AttentionArgs), _P]),
     "p2v_minmax_per_channel": (_I, [_P, _P, _I64, _I, _I64, _P]),
     "p2v_quant_mse_scores": (_I, [_P, _I64, _I, _I64, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
 }

@@ -38,6 +38,8 @@ int launch_fill_cls(int8_t* out, const int8_t* cls_row, int B, int T, int N, cud
 int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream);
 int launch_softmax(const int8_t* scores, uint8_t* out, int64_t rows, int n, const p2v_softmax_lut* lut, cudaStream_t stream);
 int launch_attention(const p2v_attention_args& a, cudaStream_t stream);
+int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream);
+bool attention_tc_supported(const p2v_attention_args& a);
 int launch_minmax(const float* x, float* minmax, int64_t n, int C, int64_t inner, cudaStream_t stream);
 int launch_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales, const float* zps, int K, int n_scale,
                       int per_channel_out, int lo, int hi, double* out, cudaStream_t stream);
@@ -117,10 +119,19 @@ int p2v_int_softmax_log2(const int8_t* scores, uint8_t* out, int64_t rows, int n
   P2V_REQUIRE(scores && out && lut && rows > 0 && n > 0 && n <= 1024, "int_softmax: bad arguments (n <= 1024)");
   return launch_softmax(scores, out, rows, n, lut, (cudaStream_t)stream);
 }
-int p2v_attention_i8(const p2v_attention_args* a, void* stream) {
+static int validate_attention(const p2v_attention_args* a) {
   P2V_REQUIRE(a && a->qkv && a->out && a->lut_dev, "attention: missing pointers");
   P2V_REQUIRE(a->B > 0 && a->H > 0 && a->T > 0 && a->T <= 256, "attention: T=%d unsupported (1..256)", a->T);
   P2V_REQUIRE(a->dh == 64 || a->dh == 32, "attention: head dim %d unsupported (32 or 64)", a->dh);
+  return 0;
+}
+int p2v_attention_i8(const p2v_attention_args* a, void* stream) {
+  if (int r = validate_attention(a)) return r;
+  if (attention_tc_supported(*a)) return launch_attention_tc(*a, (cudaStream_t)stream);
+  return launch_attention(*a, (cudaStream_t)stream);
+}
+int p2v_attention_i8_simt(const p2v_attention_args* a, void* stream) {
+  if (int r = validate_attention(a)) return r;
   return launch_attention(*a, (cudaStream_t)stream);
 }
 int p2v_minmax_per_channel(const float* x, float* minmax, int64_t n, int C, int64_t inner, void* stream) {

@@ -15,9 +15,7 @@
 // the 128 accumulator rows.  Per-column epilogue parameters are staged per tile in shared memory (double buffered
 // per group, one named barrier per tile).  Tiles are enumerated n-fastest so the CTAs running at the same time share
 // the A row-block through L2 and the (small) weight matrix stays L2 resident.
-#include <cuda.h>
-#include <unordered_map>
-#include <mutex>
+#include "tc_common.cuh"
 #include "epilogue.cuh"
 
 namespace p2v {
@@ -28,95 +26,7 @@ constexpr int UMMA_K = 32;        // K per tcgen05.mma for 8-bit operands
 constexpr int TC_GROUPS = 4;       // epilogue groups == TMEM accumulator stages
 constexpr int TC_THREADS = 64 + TC_GROUPS * 128;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, P1;\n"
-      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// try_wait suspends in hardware for a bounded time per call; the iteration cap turns a protocol bug into a
-// trap (reported as a launch error by the next API call) instead of a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, int8 operands, int32 accumulate
-__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void group_barrier(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor):
-// start address>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
-// 8-row groups | version=1 [46,48) | layout type [61,64) = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= uint64_t((smem_addr >> 4) & 0x3FFFu);
-  d |= uint64_t(1) << 16;
-  d |= uint64_t(1024 >> 4) << 32;
-  d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
-  return d;
-}
-
-// cute/arch/mma_sm100_desc.hpp: InstrDescriptor.  c_format=S32(2) [4,6); a/b format [7,10)/[10,13): 1 = signed 8 bit,
-// 0 = unsigned; a/b major bits 15/16 = 0 (K-major); N>>3 [17,23); M>>4 [24,29)
-__host__ __device__ constexpr uint32_t make_i8_idesc(int M, int N, bool a_signed, bool b_signed) {
-  return (2u << 4) | (uint32_t(a_signed) << 7) | (uint32_t(b_signed) << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
-}
+__device__ __forceinline__ void group_barrier(uint32_t id) { named_barrier(id, 128); }
 
 template <int BN, int STAGES, int EPI, bool POT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -140,11 +50,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int g = 0; g < TC_GROUPS; ++g) { mbar_init(bar_tfull + 8 * g, 1); mbar_init(bar_tempty + 8 * g, 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_mbar_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc<TMEM_COLS>(smem_u32(&tmem_slot));
   }
   tc_fence_before();
   __syncthreads();
@@ -154,8 +63,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+      tma_prefetch_map(&tmA);
+      tma_prefetch_map(&tmB);
       uint32_t it = 0;
       for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         const int m0 = int(t / tiles_n) * BM, n0 = int(t % tiles_n) * BN;
@@ -226,16 +135,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host
-typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static encode_tiled_fn get_encode() {
+encode_tiled_fn get_tensor_map_encoder() {
   static encode_tiled_fn fn = nullptr;
   static bool tried = false;
   if (!tried) {
@@ -250,7 +155,7 @@ static encode_tiled_fn get_encode() {
 
 // 2-D int8 row-major [rows, cols] tensor, box = [box_rows, 128 bytes], 128-byte swizzle, zero fill out of bounds
 int make_tmap_i8(CUtensorMap* m, const void* ptr, int rows, int cols, int box_rows) {
-  encode_tiled_fn enc = get_encode();
+  encode_tiled_fn enc = get_tensor_map_encoder();
   P2V_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   cuuint64_t strides[1] = {cuuint64_t(cols)};

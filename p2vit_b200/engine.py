@@ -148,7 +148,7 @@ class VitEngine:
     def __init__(self, model, use_graph=True, simt_gemm=False):
         self.model = model
         self.use_graph = use_graph
-        self.simt_gemm = simt_gemm      # tests only: route GEMMs through the dp4a cross-check kernel
+        self.simt_gemm = simt_gemm      # tests only: route GEMMs and attention through the dp4a cross-check kernels
         self.plans, self.programs, self.graphs = {}, {}, {}
 
     # ---- workspace + argument blocks for one (bit_config, batch)
@@ -181,7 +181,7 @@ class VitEngine:
             steps.append((pre + "attn.qact1", self._gemm(ops.gemm_args(ws["ln"], g.W, ops.EPI_REQUANT, g.acc_scale, bias=g.bias,
                                                                        out_scale=p["qkv_out"], out_i8=ws["qkv"], pot=p["qkv_pot"]))))
             at = ops.attention_args(ws["qkv"], ws["ao"], B, T + 1, H, p["dh"], p["score_mult"], p["out_mult"], p["lut"])
-            steps.append((pre + "attn.qact2", (lambda at=at: ops.attention(at))))
+            steps.append((pre + "attn.qact2", (lambda at=at, simt=self.simt_gemm: ops.attention(at, simt=simt))))
             g = p["proj"]
             steps.append((pre + "qact2", self._gemm(ops.gemm_args(ws["ao"], g.W, ops.EPI_RESIDUAL, g.acc_scale, bias=g.bias,
                                                                   out_scale=p["proj_out"], mid_scale=p["proj_mid"],

@@ -129,8 +129,10 @@ def attention_args(qkv, out, B, T, H, dh, score_mult, out_mult, lut_dev, probs=N
     return a
 
 
-def attention(args):
-    check(_lib.load().p2v_attention_i8(C.byref(args), stream()), "attention_i8")
+def attention(args, simt=False):
+    lib = _lib.load()
+    fn = lib.p2v_attention_i8_simt if simt else lib.p2v_attention_i8
+    check(fn(C.byref(args), stream()), "attention_i8_simt" if simt else "attention_i8")
 
 
 def minmax_per_channel(x):

@@ -274,6 +274,46 @@ def test_attention_vs_oracle(B, T, H, dh):
     assert torch.equal(out.cpu().float().reshape(B, T, D), ref)
 
 
+def _attention_case(B, T, H, seed, s_as=2.0 ** -3, spread=41):
+    D = H * 64
+    qkv = _rand_codes(B, T, 3 * D, lo=-spread + 1, hi=spread, seed=seed)
+    s1, s2 = 2.0 ** -4, 2.0 ** -5
+    lut = intmath.lut_to_device(intmath.build_softmax_lut(s_as), DEV)
+    return qkv.to(DEV).contiguous(), (s1 * s1 * 0.125 / s_as, s1 / s2 / 32768.0, lut), (s1, s_as, s2)
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 197, 3), (1, 197, 6), (3, 128, 2), (2, 50, 1), (2, 224, 2), (1, 129, 1), (5, 64, 3), (1, 17, 1)])
+def test_attention_tcgen05_vs_oracle(B, T, H):
+    """tensor-core attention (no debug dumps -> tcgen05 path) against the CPU oracle, all supported tilings"""
+    dh, D = 64, H * 64
+    qkv, (m1, m2, lut), (s1, s_as, s2) = _attention_case(B, T, H, seed=100 + T + H)
+    x = qkv.cpu().float() * s1
+    q, k, v = x.reshape(B, T, 3, H, dh).permute(2, 0, 3, 1, 4)
+    sc = port.fake_quant((q @ k.transpose(-2, -1)) * 0.125, torch.tensor([s_as]), torch.zeros(1), -128, 127, (1, -1, 1, 1))
+    p = port.int_softmax_log2(sc, torch.tensor([s_as]), 4, exact_sums=True)
+    ref = ((p @ v).transpose(1, 2).reshape(B, T, D) / s2).round().clamp(-128, 127)
+    out = torch.full((B * T, D), 77, dtype=torch.int8, device=DEV)
+    ops.attention(ops.attention_args(qkv, out, B, T, H, dh, m1, m2, lut))
+    bad = int((out.cpu().float().reshape(B, T, D) != ref).sum())
+    assert bad == 0, "%d of %d output codes differ" % (bad, ref.numel())
+
+
+@pytest.mark.parametrize("s_as,spread", [(2.0 ** -3, 41), (2.0 ** -6, 128), (2.0 ** -1, 20), (2.0 ** -8, 128)])
+def test_attention_tcgen05_vs_simt_many_heads(s_as, spread):
+    """full DeiT-S layer worth of heads (persistent loop, both CTAs of an SM, many softmax scales / peaked rows):
+    the tcgen05 kernel must reproduce the dp4a kernel bit for bit"""
+    B, T, H = 64, 197, 6
+    qkv, (m1, m2, lut), _ = _attention_case(B, T, H, seed=7, s_as=s_as, spread=spread)
+    a = torch.empty((B * T, H * 64), dtype=torch.int8, device=DEV)
+    b = torch.empty_like(a)
+    ops.attention(ops.attention_args(qkv, a, B, T, H, 64, m1, m2, lut))
+    ops.attention(ops.attention_args(qkv, b, B, T, H, 64, m1, m2, lut), simt=True)
+    torch.cuda.synchronize()
+    bad = int((a != b).sum())
+    assert bad == 0, "%d of %d output codes differ between tcgen05 and dp4a attention" % (bad, a.numel())
+    assert int((a != 0).sum()) > a.numel() // 4   # not a degenerate case
+
+
 # ------------------------------------------------------------------------------------------------ observers' kernels
 def test_minmax_and_mse_scores():
     torch.manual_seed(9)
