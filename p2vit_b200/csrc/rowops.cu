@@ -215,7 +215,132 @@ __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
   }
 }
 
+// Fast path for power-of-two output scales (every minmax-calibrated model): LPR lanes share a row (8, 16 or 32, so a
+// lane owns >= 12 channels and the per-row scalar work - three IEEE divisions and a square root - is amortised), the
+// per-channel constants live in registers for the whole persistent loop, and every division by a scale is folded into
+// them: with ros = 1/out_scale, f = out_scale/(post_div*next_scale) exact powers of two,
+//   A  = fl(fl(t*g)*ros)            == fl(t*g'),            g' = g*ros
+//   Bv = RNE(fl(fl(b - fl(m*g))*ros)*2^N) == RNE(fl(b' - fl(m*g'))*2^N),  b' = b*ros
+//   q  = sat(RNE(((yq*os)/pd)/next))  == sat(RNE(yq*f))
+// (scaling by a power of two commutes with rounding), so the codes equal the generic kernel's bit for bit.
+template <int LPR, int WPLN>
+__global__ void __launch_bounds__(128) layernorm_pot_kernel(p2v_layernorm_args a) {
+  constexpr int GPW = 32 / LPR;                       // rows per warp iteration
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row_stride = gridDim.x * (blockDim.x >> 5) * GPW;
+  float g[WPLN][4], bt[WPLN][4], f[WPLN][4];
+  int sh[WPLN][4];
+  const float rnext = fdiv(1.f, a.next_scale);
+#pragma unroll
+  for (int i = 0; i < WPLN; ++i) {
+    const int w = sub + LPR * i;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma) + w), b4 = __ldg(reinterpret_cast<const float4*>(a.beta) + w);
+    const float4 o4 = __ldg(reinterpret_cast<const float4*>(a.out_scale) + w), p4 = __ldg(reinterpret_cast<const float4*>(a.post_div) + w);
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.in_mult) + w);
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, oo[4] = {o4.x, o4.y, o4.z, o4.w};
+    const float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ros = fdiv(1.f, oo[e]);
+      g[i][e] = fmul(gg[e], ros);
+      bt[i][e] = fmul(bb[e], ros);
+      f[i][e] = fmul(fmul(oo[e], fdiv(1.f, pp[e])), rnext);
+      sh[i][e] = int(mm[e]);
+    }
+  }
+  const float Cf = float(a.C), s1 = a.in_scale_min, s1c = fdiv(s1, Cf);
+  for (int row = warp_global * GPW + grp; row < a.rows; row += row_stride) {
+    const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
+    int xv[WPLN][4];
+    int S1 = 0, S2 = 0;
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) {
+      const uint32_t u = __ldg(xr + sub + LPR * i);
+      xv[i][0] = int(int8_t(u & 0xff)) * sh[i][0];
+      xv[i][1] = int(int8_t((u >> 8) & 0xff)) * sh[i][1];
+      xv[i][2] = int(int8_t((u >> 16) & 0xff)) * sh[i][2];
+      xv[i][3] = int(int8_t(u >> 24)) * sh[i][3];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { S1 += xv[i][e]; S2 += xv[i][e] * xv[i][e]; }
+    }
+    S1 = __reduce_add_sync(gmask, S1);
+    S2 = __reduce_add_sync(gmask, S2);
+    const float S1f = float(S1), S2f = float(S2);
+    const float mean = fmul(fdiv(S1f, Cf), s1);
+    const float stdv = fmul(s1c, __fsqrt_rn(fsub(fmul(Cf, S2f), fmul(S1f, S1f))));
+    const float t = fdiv(s1, stdv);
+    const float mos = fdiv(mean, stdv);
+    uint32_t* orow = reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(row) * a.C);
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) {
+      int q[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float A = fmul(t, g[i][e]);
+        const uint32_t ab = __float_as_uint(A) & 0x7fffffffu;
+        int ex = int(ab >> 23) - 127;                  // 0 / subnormal -> N = 31, inf / nan -> N = 0 through the clamp
+        if ((ab & 0x007fffffu) >= 0x007ffff0u && ab < 0x7f800000u) ex = floor_log2_as_fp32(__uint_as_float(ab));
+        const int N = min(max(7 - ex, 0), 31);
+        const float twoN = __uint_as_float(uint32_t(N + 127) << 23), rtwoN = __uint_as_float(uint32_t(127 - N) << 23);
+        const float M = fminf(floorf(fmul(__uint_as_float(ab), twoN)), 255.f);
+        const float sM = __uint_as_float(__float_as_uint(M) | (__float_as_uint(A) & 0x80000000u));
+        const float Bv = rintf(fmul(fsub(bt[i][e], fmul(mos, g[i][e])), twoN));
+        const float yq = rintf(fmul(fadd(fmul(sM, float(xv[i][e])), Bv), rtwoN));
+        q[e] = sat_s8(fmul(yq, f[i][e]));
+      }
+      orow[sub + LPR * i] = pack4_s8(q[0], q[1], q[2], q[3]);
+    }
+  }
+}
+
+template <int LPR, int WPLN>
+static void launch_ln_pot(const p2v_layernorm_args& a, cudaStream_t stream) {
+  constexpr int GPW = 32 / LPR;
+  const int rows_per_block = 4 * GPW;
+  // persistent: several rows per lane group so the register-resident channel constants are amortised
+  const int blocks = std::max(1, std::min((a.rows + rows_per_block - 1) / rows_per_block, num_sms() * 3));
+  layernorm_pot_kernel<LPR, WPLN><<<blocks, 128, 0, stream>>>(a);
+}
+
 int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
+  const int nwords = a.C / 4;
+  if (a.pot_scales && a.out_i8 && !a.out_f32) {
+    bool done = true;
+    if (nwords % 8 == 0 && nwords / 8 <= 6 && nwords / 8 >= 3 && a.rows >= 4) {
+      switch (nwords / 8) {
+        case 3: launch_ln_pot<8, 3>(a, stream); break;
+        case 4: launch_ln_pot<8, 4>(a, stream); break;
+        case 5: launch_ln_pot<8, 5>(a, stream); break;
+        default: launch_ln_pot<8, 6>(a, stream); break;
+      }
+    } else if (nwords % 16 == 0 && nwords / 16 <= 6 && nwords / 16 >= 3 && a.rows >= 2) {
+      switch (nwords / 16) {
+        case 3: launch_ln_pot<16, 3>(a, stream); break;
+        case 4: launch_ln_pot<16, 4>(a, stream); break;
+        case 5: launch_ln_pot<16, 5>(a, stream); break;
+        default: launch_ln_pot<16, 6>(a, stream); break;
+      }
+    } else if (nwords % 32 == 0 && nwords / 32 <= 8) {
+      switch (nwords / 32) {
+        case 1: launch_ln_pot<32, 1>(a, stream); break;
+        case 2: launch_ln_pot<32, 2>(a, stream); break;
+        case 3: launch_ln_pot<32, 3>(a, stream); break;
+        case 4: launch_ln_pot<32, 4>(a, stream); break;
+        case 5: launch_ln_pot<32, 5>(a, stream); break;
+        case 6: launch_ln_pot<32, 6>(a, stream); break;
+        case 7: launch_ln_pot<32, 7>(a, stream); break;
+        default: launch_ln_pot<32, 8>(a, stream); break;
+      }
+    } else {
+      done = false;
+    }
+    if (done) {
+      count_launch();
+      return check_launch("layernorm_int");
+    }
+  }
   const int wpl = (a.C / 4 + 31) / 32;
   const int blocks = std::min((a.rows + 7) / 8, num_sms() * 8);
 #define P2V_LN(W)                                                                   \

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+run() { name=$1; shift; echo "=== $name" ; timeout ${TMO:-600} "$@" > gpurun_out/$name.log 2>&1; echo "exit $?"; tail -n ${TAILN:-15} gpurun_out/$name.log; }
+run ln python -m pytest tests/test_gpu_ops.py -q -m gpu -p no:cacheprovider -k layernorm -x
+run model python -m pytest tests/test_gpu_model.py -q -m gpu -p no:cacheprovider -x
+TAILN=3 run bench python bench.py --steps 20 --warmup 3 --golden-state --no-cpu-baseline
