@@ -246,7 +246,10 @@ def main():
             return "layernorm"
         if step.endswith("attn.qact2"):
             return "attention"
-        return "gemm"
+        for suffix, kind in ((".attn.qact1", "gemm_qkv"), (".qact2", "gemm_proj"), (".mlp.qact1", "gemm_fc1"), (".qact4", "gemm_fc2")):
+            if step.startswith("blocks.") and step.endswith(suffix):
+                return kind
+        return "gemm_other"
 
     reps = 3
     for _ in range(reps):
@@ -259,8 +262,11 @@ def main():
             f = family(step)
             fam_ms[f] = fam_ms.get(f, 0.0) + a.elapsed_time(b)
             fam_n[f] = fam_n.get(f, 0) + 1
-    fam_ms = {k: v / reps for k, v in fam_ms.items()}
+    fine_ms = {k: round(v / reps, 4) for k, v in fam_ms.items()}
+    fam_ms = {k: v / reps for k, v in fam_ms.items() if not k.startswith("gemm")}
+    fam_ms["gemm"] = sum(v for k, v in fine_ms.items() if k.startswith("gemm"))
     fam_n = {k: v // reps for k, v in fam_n.items()}
+    fam_n["gemm"] = sum(v for k, v in fam_n.items() if k.startswith("gemm"))
 
     if rank != 0:
         if world > 1:
@@ -295,6 +301,7 @@ def main():
                 "frac": ach / hbm_gbs, "traffic": None, "note": "algorithmic int8 bytes in+out; peak = %s copy bandwidth" % peak_src}
     roof["device_ms_per_step_by_family"] = {k: round(v, 4) for k, v in fam_ms.items()}
     roof["share_of_step"] = share
+    roof["gemm_ms_by_kind"] = {k: v for k, v in fine_ms.items() if k.startswith("gemm")}
     roof["tensor_fraction_of_whole_forward"] = 2.0 * macs * value / world / (2.0 * bf16_tf_sus * 1e12)
 
     cpu = None

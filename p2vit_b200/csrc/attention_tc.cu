@@ -15,6 +15,7 @@
 // ~112 KB shared memory each) so one CTA's MMA / TMA latency hides under the other's integer work.  A CTA walks
 // heads blockIdx.x, blockIdx.x + gridDim.x, ...; each head is 1 or 2 query tiles of 128 rows.
 #include <climits>
+#include <type_traits>
 #include "tc_common.cuh"
 
 namespace p2v {
@@ -49,14 +50,20 @@ struct AttTcParams {
 //   are each within a few ulps of the exact values, so the result can only differ from the reference when w is
 //   within 16 ulps of a power of two >= 2 or y within 1e-5 of 2 (`near`): those take the exact path (log2_code).
 // Returns 2^(15-big) (0 when big >= 16).
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n) {   // PTX shr: amounts > 31 give 0
+  uint32_t r;
+  asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+  return r;
+}
 __device__ __forceinline__ uint32_t prob_bits_fast(float tot, float rcp, bool& near) {
   const float y = fadd(fmul(tot, rcp), 0.5f);
-  const float w = fmul(y, 0.666666686534881591796875f);
+  // 2/3 rounded up twice: y >= 1.5 - 1 ulp always (e <= tot), so w >= 1 and the exponent field needs no clamp; the
+  // 1-ulp shift of the thresholds is inside the guard band
+  const float w = fmul(y, 0.66666674613952636718750f);
   const uint32_t wb = __float_as_uint(w);
   const uint32_t nb = wb + 16u;
   near = ((nb & 0x007fffffu) < 32u && nb >= 0x40000000u) || fabsf(fsub(y, 2.0f)) < 1e-5f;
-  const uint32_t big = uint32_t(max(int(wb >> 23) - 127, 0)) + (y >= 2.0f ? 1u : 0u);
-  return 0x8000u >> min(big, 31u);
+  return shr_clamp(y >= 2.0f ? 0x4000u : 0x8000u, (wb >> 23) - 127u);
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -169,10 +176,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int e = 0; e < 32; ++e) smax = max(smax, e < nv ? acc[e] : INT_MIN);
           }
           const int mx = sat_s8(fmul(float(smax), mult));
-          // ---- pass 2: exact row sum of exp_int(max - code)
+          // ---- pass 2: exact row sum of exp_int(max - code); only the last chunk can hold columns >= T
+          const int nfull = T >> 5;
           unsigned long long shi = 0, slo = 0;
-#pragma unroll 1
-          for (int c = 0; c < nchunks; ++c) {
+          auto sum_chunk = [&](auto masked, int c) {
             int acc[32];
             tmem_ld32(tlane + c * 32, acc);
             const int nv = T - c * 32;
@@ -180,15 +187,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int e = 0; e < 32; ++e) {
               const int d = mx - sat_s8(fmul(float(acc[e]), mult));
               const uint2 v = s_lut[d];
-              if (e < nv) { shi += v.x; slo += v.y; }
+              if (!decltype(masked)::value || e < nv) { shi += v.x; slo += v.y; }
             }
-          }
+          };
+#pragma unroll 1
+          for (int c = 0; c < nfull; ++c) sum_chunk(std::false_type{}, c);
+          if (nfull < nchunks) sum_chunk(std::true_type{}, nfull);
           const float tot = u96_to_f32(shi, slo);
           // ---- pass 3: probabilities 2^(15-code) as hi / lo byte planes in the UMMA K-major SW128 layout
           uint8_t* prow = gbase + AT_OFF_P + rloc * 128;
           const uint32_t sw = uint32_t(rloc & 7);
-#pragma unroll 1
-          for (int c = 0; c < nchunks; ++c) {
+          auto prob_chunk = [&](auto masked, int c) {
             int acc[32];
             tmem_ld32(tlane + c * 32, acc);
             const int nv = T - c * 32;
@@ -209,15 +218,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 for (int e = 0; e < 16; ++e) {
                   const uint2 v = s_lut[acc[half * 16 + e]];
                   const uint32_t big = log2_code(tot, __ull2float_rn((static_cast<unsigned long long>(v.x) << 32) | v.y));
-                  pv[e] = 0x8000u >> min(big, 31u);
+                  pv[e] = shr_clamp(0x8000u, big);
                 }
               }
               uint32_t lo[4], hi[4];
 #pragma unroll
               for (int e4 = 0; e4 < 4; ++e4) {
+                if (decltype(masked)::value) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (half * 16 + e4 * 4 + e >= nv) pv[e4 * 4 + e] = 0u;
+                  for (int e = 0; e < 4; ++e)
+                    if (half * 16 + e4 * 4 + e >= nv) pv[e4 * 4 + e] = 0u;
+                }
                 const uint32_t p01 = pv[e4 * 4] | (pv[e4 * 4 + 1] << 16), p23 = pv[e4 * 4 + 2] | (pv[e4 * 4 + 3] << 16);
                 lo[e4] = __byte_perm(p01, p23, 0x6420);
                 hi[e4] = __byte_perm(p01, p23, 0x7531);
@@ -227,7 +238,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *reinterpret_cast<uint4*>(dst + AT_P_PLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-          }
+          };
+#pragma unroll 1
+          for (int c = 0; c < nfull; ++c) prob_chunk(std::false_type{}, c);
+          if (nfull < nchunks) prob_chunk(std::true_type{}, nfull);
         }
         fence_proxy_async_smem();
         tc_fence_before();

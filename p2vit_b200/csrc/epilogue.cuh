@@ -39,13 +39,21 @@ inline EpiParams make_epi_params(const p2v_gemm_args& a) {
   return p;
 }
 
-// sat(RNE(fl(y / s))) with rs = RN(1/s).  |y*rs - fl(y/s)| <= |q| * 3 * 2^-24, so away from a tie the rounded
-// integers agree; within the guard band the IEEE quotient decides.  Saturation makes large |q| irrelevant.
-__device__ __forceinline__ float quant_div(float y, float s, float rs) {
-  const float qa = fmul(y, rs);
-  float k = rintf(qa);
-  const float d = fabsf(fsub(qa, k));
-  if (d > 0.499f && fabsf(qa) < 300.f) k = rintf(fdiv(y, s));
+// sat(RNE(fl(y / s))) with rs = RN(1/s).  |y*rs - fl(y/s)| <= |q| * 3 * 2^-24 (< 2.4e-5 for |q| < 129), so away from
+// a tie the rounded integers agree; within the guard band (`slow` is raised; ~6e-5 of the quotients) the caller redoes
+// the span with EXACT = true, i.e. with the IEEE quotient.  |q| >= 129 saturates identically on both paths.  No branch per element: the fast pass is straight-line code
+// (RNE through the 1.5*2^23 magic constant - exact for |q| < 2^22, saturating beyond), so the compiler can interleave
+// the 16 / 32 independent columns a thread owns.
+template <bool EXACT>
+__device__ __forceinline__ float quant_div(float y, float s, float rs, bool& slow) {
+  float k;
+  if (EXACT) {
+    k = rintf(fdiv(y, s));
+  } else {
+    const float qa = fmul(y, rs);
+    k = fsub(fadd(qa, 12582912.f), 12582912.f);
+    slow |= (fabsf(fsub(qa, k)) > 0.49997f) & (fabsf(qa) < 129.f);
+  }
   return fminf(fmaxf(k, -128.f), 127.f);
 }
 
@@ -82,36 +90,12 @@ __device__ __forceinline__ void stage_col_params(const EpiParams& p, float* cp, 
   cp[CP_Z * BN + t] = (ok && p.zp_corr) ? __int_as_float(__ldg(p.zp_corr + n)) : __int_as_float(0);
 }
 
-// Processes columns [col0, col0+NC) of row `row`, col0 = n0 + c0 with c0 the offset inside the staged tile.
-// NC is a multiple of 4.  Tail columns (>= N) are masked on store.
-template <int EPI, bool POT, int BN, int NC>
-__device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp, int row, int n0, int c0, const int (&acc)[NC]) {
-  if (row >= p.M) return;
+// Epilogue arithmetic for columns [col0, col0+NC) of one row; EXACT = false is the branch-free fast pass.
+template <int EPI, bool POT, int BN, int NC, bool EXACT>
+__device__ __forceinline__ void epilogue_math(const EpiParams& p, const float* cp, int row, int col0, int c0, const int (&acc)[NC],
+                                              const uint32_t (&resw)[NC / 4], int (&q)[NC], float (&f)[NC], bool& slow) {
   const int N = p.N;
-  const int col0 = n0 + c0;
-  int q[NC];
-  float f[NC];
   const bool has_zp = p.zp_corr != nullptr;
-  uint32_t resw[NC / 4];
-  if (EPI == P2V_EPI_RESIDUAL) {
-    const int8_t* rp = p.res + size_t(row) * N + col0;
-    if ((N & 15) == 0 && (NC & 15) == 0 && col0 + NC <= N) {
-#pragma unroll
-      for (int j = 0; j < NC / 16; ++j) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(rp) + j);
-        resw[4 * j] = v.x; resw[4 * j + 1] = v.y; resw[4 * j + 2] = v.z; resw[4 * j + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < NC / 4; ++j) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (col0 + 4 * j + e < N) w |= (uint32_t(uint8_t(rp[4 * j + e])) << (8 * e));
-        resw[j] = w;
-      }
-    }
-  }
   float e_sm = 0.f, e_rsm = 0.f, e_raux = 0.f;
   int tok = 0;
   if (EPI == P2V_EPI_EMBED) {
@@ -154,30 +138,66 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp
       if (EPI == P2V_EPI_F32) {
         f[j] = y;
       } else if (EPI == P2V_EPI_REQUANT) {
-        q[j] = int(quant_div(y, Ov[e], Rv[e]));
+        q[j] = int(quant_div<EXACT>(y, Ov[e], Rv[e], slow));
       } else if (EPI == P2V_EPI_DEQUANT) {
-        const float k = quant_div(y, Ov[e], Rv[e]);
+        const float k = quant_div<EXACT>(y, Ov[e], Rv[e], slow);
         q[j] = int(k);
         f[j] = fmul(k, Ov[e]);
       } else if (EPI == P2V_EPI_GELU) {
         const float g = gelu_erf(y);
-        q[j] = POT ? sat_s8(fmul(g, Rv[e])) : int(quant_div(g, Ov[e], Rv[e]));
+        q[j] = POT ? sat_s8(fmul(g, Rv[e])) : int(quant_div<EXACT>(g, Ov[e], Rv[e], slow));
       } else if (EPI == P2V_EPI_RESIDUAL) {
-        const float c = quant_div(y, Mv[e], RMv[e]);
+        const float c = quant_div<EXACT>(y, Mv[e], RMv[e], slow);
         const float t = fmul(c, Mv[e]);
         const float r = float(int(int8_t((resw[j >> 2] >> (8 * (j & 3))) & 0xffu)));
         const float z = fadd(fmul(r, RSv[e]), t);
-        q[j] = int(quant_div(z, Ov[e], Rv[e]));
+        q[j] = int(quant_div<EXACT>(z, Ov[e], Rv[e], slow));
       } else if (EPI == P2V_EPI_EMBED) {
-        const float c = quant_div(y, e_sm, e_rsm);
-        const float ecode = quant_div(fmul(c, e_sm), p.aux_scale, e_raux);
+        const float c = quant_div<EXACT>(y, e_sm, e_rsm, slow);
+        const float ecode = quant_div<EXACT>(fmul(c, e_sm), p.aux_scale, e_raux, slow);
         const int n = col0 + j;
         const float pv = n < N ? __ldg(p.pos + size_t(tok + 1) * N + n) : 0.f;
         const float v = fadd(fmul(ecode, p.aux_scale), pv);
-        q[j] = int(quant_div(v, Ov[e], Rv[e]));
+        q[j] = int(quant_div<EXACT>(v, Ov[e], Rv[e], slow));
       }
     }
   }
+}
+
+// Processes columns [col0, col0+NC) of row `row`, col0 = n0 + c0 with c0 the offset inside the staged tile.
+// NC is a multiple of 4.  Tail columns (>= N) are masked on store.  TMEM_WAIT: `acc` is the destination of an
+// in-flight tcgen05.ld; the residual codes are requested first and the wait sits right before the first use.
+template <int EPI, bool POT, int BN, int NC, bool TMEM_WAIT = false>
+__device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp, int row, int n0, int c0, const int (&acc)[NC]) {
+  const int N = p.N;
+  const int col0 = n0 + c0;
+  int q[NC];
+  float f[NC];
+  uint32_t resw[NC / 4];
+  if (EPI == P2V_EPI_RESIDUAL && row < p.M) {
+    const int8_t* rp = p.res + size_t(row) * N + col0;
+    if ((N & 15) == 0 && (NC & 15) == 0 && col0 + NC <= N) {
+#pragma unroll
+      for (int j = 0; j < NC / 16; ++j) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+        resw[4 * j] = v.x; resw[4 * j + 1] = v.y; resw[4 * j + 2] = v.z; resw[4 * j + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col0 + 4 * j + e < N) w |= (uint32_t(uint8_t(rp[4 * j + e])) << (8 * e));
+        resw[j] = w;
+      }
+    }
+  }
+  if (TMEM_WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (row >= p.M) return;
+  bool slow = false;
+  epilogue_math<EPI, POT, BN, NC, false>(p, cp, row, col0, c0, acc, resw, q, f, slow);
+  if (slow) epilogue_math<EPI, POT, BN, NC, true>(p, cp, row, col0, c0, acc, resw, q, f, slow);
   size_t orow = size_t(row);
   if (EPI == P2V_EPI_EMBED) {
     const int T = p.tokens_per_image;

@@ -122,9 +122,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (n0 + c * NCH >= p.N) break;
         int acc[NCH];
         __syncwarp();
-        if (NCH == 32) tmem_ld32(taddr + c * NCH, reinterpret_cast<int(&)[32]>(acc[0]));
-        else tmem_ld16(taddr + c * NCH, reinterpret_cast<int(&)[16]>(acc[0]));
-        epilogue_row<EPI, POT, BN, NCH>(p, cp, row, n0, c * NCH, acc);
+        if (NCH == 32) tmem_ld32_async(taddr + c * NCH, reinterpret_cast<int(&)[32]>(acc[0]));
+        else tmem_ld16_async(taddr + c * NCH, reinterpret_cast<int(&)[16]>(acc[0]));
+        epilogue_row<EPI, POT, BN, NCH, true>(p, cp, row, n0, c * NCH, acc);
       }
       tc_fence_before();
       __syncwarp();

@@ -215,6 +215,29 @@ __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
   }
 }
 
+template <bool SLOW>
+__device__ __forceinline__ uint32_t ln_pot_word(float t, float mos, const float (&g)[4], const float (&bt)[4], const float (&f)[4],
+                                                const int (&xv)[4]) {
+  int q[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float A = fmul(t, g[e]);
+    const uint32_t ab = __float_as_uint(A) & 0x7fffffffu;
+    int ex = int(ab >> 23) - 127;                  // 0 / subnormal -> N = 31, inf / nan -> N = 0 through the clamp
+    if (SLOW) {
+      if ((ab & 0x007fffffu) >= 0x007ffff0u && ab < 0x7f800000u) ex = floor_log2_as_fp32(__uint_as_float(ab));
+    }
+    const int N = min(max(7 - ex, 0), 31);
+    const float twoN = __uint_as_float(uint32_t(N + 127) << 23), rtwoN = __uint_as_float(uint32_t(127 - N) << 23);
+    const float M = fminf(floorf(fmul(__uint_as_float(ab), twoN)), 255.f);
+    const float sM = __uint_as_float(__float_as_uint(M) | (__float_as_uint(A) & 0x80000000u));
+    const float Bv = rintf(fmul(fsub(bt[e], fmul(mos, g[e])), twoN));
+    const float yq = rintf(fmul(fadd(fmul(sM, float(xv[e])), Bv), rtwoN));
+    q[e] = sat_s8(fmul(yq, f[e]));
+  }
+  return pack4_s8(q[0], q[1], q[2], q[3]);
+}
+
 // Fast path for power-of-two output scales (every minmax-calibrated model): LPR lanes share a row (8, 16 or 32, so a
 // lane owns >= 12 channels and the per-row scalar work - three IEEE divisions and a square root - is amortised), the
 // per-channel constants live in registers for the whole persistent loop, and every division by a scale is folded into
@@ -224,7 +247,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
 //   q  = sat(RNE(((yq*os)/pd)/next))  == sat(RNE(yq*f))
 // (scaling by a power of two commutes with rounding), so the codes equal the generic kernel's bit for bit.
 template <int LPR, int WPLN>
-__global__ void __launch_bounds__(128) layernorm_pot_kernel(p2v_layernorm_args a) {
+__global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_args a) {
   constexpr int GPW = 32 / LPR;                       // rows per warp iteration
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
@@ -273,24 +296,24 @@ __global__ void __launch_bounds__(128) layernorm_pot_kernel(p2v_layernorm_args a
     const float t = fdiv(s1, stdv);
     const float mos = fdiv(mean, stdv);
     uint32_t* orow = reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(row) * a.C);
+    // floor(log2|A|) is the float exponent except within 16 ulps below a power of two (floor_log2_as_fp32); rows where
+    // some channel is that close take the second instantiation, so the common loop has no branch per element.
+    bool slow = false;
 #pragma unroll
-    for (int i = 0; i < WPLN; ++i) {
-      int q[4];
+    for (int i = 0; i < WPLN; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float A = fmul(t, g[i][e]);
-        const uint32_t ab = __float_as_uint(A) & 0x7fffffffu;
-        int ex = int(ab >> 23) - 127;                  // 0 / subnormal -> N = 31, inf / nan -> N = 0 through the clamp
-        if ((ab & 0x007fffffu) >= 0x007ffff0u && ab < 0x7f800000u) ex = floor_log2_as_fp32(__uint_as_float(ab));
-        const int N = min(max(7 - ex, 0), 31);
-        const float twoN = __uint_as_float(uint32_t(N + 127) << 23), rtwoN = __uint_as_float(uint32_t(127 - N) << 23);
-        const float M = fminf(floorf(fmul(__uint_as_float(ab), twoN)), 255.f);
-        const float sM = __uint_as_float(__float_as_uint(M) | (__float_as_uint(A) & 0x80000000u));
-        const float Bv = rintf(fmul(fsub(bt[i][e], fmul(mos, g[i][e])), twoN));
-        const float yq = rintf(fmul(fadd(fmul(sM, float(xv[i][e])), Bv), rtwoN));
-        q[e] = sat_s8(fmul(yq, f[i][e]));
+        const uint32_t ab = __float_as_uint(fmul(t, g[i][e])) & 0x7fffffffu;
+        slow |= ((ab & 0x007fffffu) >= 0x007ffff0u) & (ab < 0x7f800000u);
       }
-      orow[sub + LPR * i] = pack4_s8(q[0], q[1], q[2], q[3]);
+    if (!slow) {
+#pragma unroll
+      for (int i = 0; i < WPLN; ++i)
+        orow[sub + LPR * i] = ln_pot_word<false>(t, mos, g[i], bt[i], f[i], xv[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < WPLN; ++i)
+        orow[sub + LPR * i] = ln_pot_word<true>(t, mos, g[i], bt[i], f[i], xv[i]);
     }
   }
 }

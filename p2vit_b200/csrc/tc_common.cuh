@@ -94,7 +94,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&r)[32]) {
   tmem_ld32_async(taddr, r);
   tmem_wait_ld();
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, int (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -102,6 +102,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&r)[16]) {
+  tmem_ld16_async(taddr, r);
   tmem_wait_ld();
 }
 __device__ __forceinline__ void named_barrier(uint32_t id, uint32_t threads) {
