@@ -90,7 +90,8 @@ typedef struct {
   int tokens_per_image;     /* EMBED: T (196) */
   int8_t* out_i8;           /* [M,N] (EMBED: [B*(T+1),N]) */
   float* out_f32;           /* [M,N] DEQUANT / F32 */
-  int pot_scales;           /* 1: every divisor above is an exact power of two (division == exact multiply) */
+  int pot_scales;           /* REQUANT/GELU/DEQUANT: 1 = acc_scale and out_scale are exact powers of two (division == exact
+                               multiply); RESIDUAL: 1 = acc_scale is (acc*acc_scale exact; mid/out scales stay general) */
 } p2v_gemm_args;
 
 int p2v_gemm_i8(const p2v_gemm_args* args_host, void* stream);

@@ -40,8 +40,8 @@ inline EpiParams make_epi_params(const p2v_gemm_args& a) {
 }
 
 // sat(RNE(fl(y / s))) with rs = RN(1/s).  |y*rs - fl(y/s)| <= |q| * 3 * 2^-24 (< 2.4e-5 for |q| < 129), so away from
-// a tie the rounded integers agree; within the guard band (`slow` is raised; ~6e-5 of the quotients) the caller redoes
-// the span with EXACT = true, i.e. with the IEEE quotient.  |q| >= 129 saturates identically on both paths.  No branch per element: the fast pass is straight-line code
+// a tie the rounded integers agree; within the guard band (`slow` is raised; ~6e-5 of the quotients, plus harmless
+// false alarms for saturated |q|) the caller redoes the span with EXACT = true, i.e. with the IEEE quotient.  No branch per element: the fast pass is straight-line code
 // (RNE through the 1.5*2^23 magic constant - exact for |q| < 2^22, saturating beyond), so the compiler can interleave
 // the 16 / 32 independent columns a thread owns.
 template <bool EXACT>
@@ -51,10 +51,18 @@ __device__ __forceinline__ float quant_div(float y, float s, float rs, bool& slo
     k = rintf(fdiv(y, s));
   } else {
     const float qa = fmul(y, rs);
-    k = fsub(fadd(qa, 12582912.f), 12582912.f);
-    slow |= (fabsf(fsub(qa, k)) > 0.49997f) & (fabsf(qa) < 129.f);
+    k = rintf(qa);
+    slow |= fabsf(fsub(qa, k)) > 0.49997f;
   }
   return fminf(fmaxf(k, -128.f), 127.f);
+}
+// same, result as int8 code (one saturating conversion instead of round + clamp + convert)
+template <bool EXACT>
+__device__ __forceinline__ int quant_div_s8(float y, float s, float rs, bool& slow) {
+  if (EXACT) return sat_s8(fdiv(y, s));
+  const float qa = fmul(y, rs);
+  slow |= fabsf(fsub(qa, rintf(qa))) > 0.49997f;
+  return sat_s8(qa);
 }
 
 // column-parameter tile in shared memory: CP_ROWS arrays of BN floats
@@ -134,65 +142,76 @@ __device__ __forceinline__ void epilogue_math(const EpiParams& p, const float* c
         if (EPI == P2V_EPI_DEQUANT) f[j] = fmul(float(q[j]), Ov[e]);
         continue;
       }
-      const float y = fadd(fmul(af, Sv[e]), Bv[e]);
+      // RESIDUAL with POT: acc_scale is a power of two, so acc*s is exact and fl(acc*s + b) is one fused rounding
+      const float y = (EPI == P2V_EPI_RESIDUAL && POT) ? __fmaf_rn(af, Sv[e], Bv[e]) : fadd(fmul(af, Sv[e]), Bv[e]);
       if (EPI == P2V_EPI_F32) {
         f[j] = y;
       } else if (EPI == P2V_EPI_REQUANT) {
-        q[j] = int(quant_div<EXACT>(y, Ov[e], Rv[e], slow));
+        q[j] = quant_div_s8<EXACT>(y, Ov[e], Rv[e], slow);
       } else if (EPI == P2V_EPI_DEQUANT) {
         const float k = quant_div<EXACT>(y, Ov[e], Rv[e], slow);
         q[j] = int(k);
         f[j] = fmul(k, Ov[e]);
       } else if (EPI == P2V_EPI_GELU) {
         const float g = gelu_erf(y);
-        q[j] = POT ? sat_s8(fmul(g, Rv[e])) : int(quant_div<EXACT>(g, Ov[e], Rv[e], slow));
+        q[j] = POT ? sat_s8(fmul(g, Rv[e])) : quant_div_s8<EXACT>(g, Ov[e], Rv[e], slow);
       } else if (EPI == P2V_EPI_RESIDUAL) {
         const float c = quant_div<EXACT>(y, Mv[e], RMv[e], slow);
         const float t = fmul(c, Mv[e]);
         const float r = float(int(int8_t((resw[j >> 2] >> (8 * (j & 3))) & 0xffu)));
         const float z = fadd(fmul(r, RSv[e]), t);
-        q[j] = int(quant_div<EXACT>(z, Ov[e], Rv[e], slow));
+        q[j] = quant_div_s8<EXACT>(z, Ov[e], Rv[e], slow);
       } else if (EPI == P2V_EPI_EMBED) {
         const float c = quant_div<EXACT>(y, e_sm, e_rsm, slow);
         const float ecode = quant_div<EXACT>(fmul(c, e_sm), p.aux_scale, e_raux, slow);
         const int n = col0 + j;
         const float pv = n < N ? __ldg(p.pos + size_t(tok + 1) * N + n) : 0.f;
         const float v = fadd(fmul(ecode, p.aux_scale), pv);
-        q[j] = int(quant_div<EXACT>(v, Ov[e], Rv[e], slow));
+        q[j] = quant_div_s8<EXACT>(v, Ov[e], Rv[e], slow);
       }
+    }
+  }
+}
+
+// residual codes of columns [col0, col0+NC) of `row` as packed words (RESIDUAL epilogue); issued by the caller ahead of
+// use so that the global-load latency overlaps the previous chunk's arithmetic
+template <int NC>
+__device__ __forceinline__ void load_residual(const EpiParams& p, int row, int col0, uint32_t (&resw)[NC / 4]) {
+  const int N = p.N;
+  if (row >= p.M || col0 >= N) {
+#pragma unroll
+    for (int j = 0; j < NC / 4; ++j) resw[j] = 0u;
+    return;
+  }
+  const int8_t* rp = p.res + size_t(row) * N + col0;
+  if ((N & 15) == 0 && (NC & 15) == 0 && col0 + NC <= N) {
+#pragma unroll
+    for (int j = 0; j < NC / 16; ++j) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(rp) + j);
+      resw[4 * j] = v.x; resw[4 * j + 1] = v.y; resw[4 * j + 2] = v.z; resw[4 * j + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC / 4; ++j) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (col0 + 4 * j + e < N) w |= (uint32_t(uint8_t(rp[4 * j + e])) << (8 * e));
+      resw[j] = w;
     }
   }
 }
 
 // Processes columns [col0, col0+NC) of row `row`, col0 = n0 + c0 with c0 the offset inside the staged tile.
 // NC is a multiple of 4.  Tail columns (>= N) are masked on store.  TMEM_WAIT: `acc` is the destination of an
-// in-flight tcgen05.ld; the residual codes are requested first and the wait sits right before the first use.
+// in-flight tcgen05.ld; the wait sits right before the first use.  `resw`: load_residual() of the same span.
 template <int EPI, bool POT, int BN, int NC, bool TMEM_WAIT = false>
-__device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp, int row, int n0, int c0, const int (&acc)[NC]) {
+__device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp, int row, int n0, int c0, const int (&acc)[NC],
+                                             const uint32_t (&resw)[NC / 4]) {
   const int N = p.N;
   const int col0 = n0 + c0;
   int q[NC];
   float f[NC];
-  uint32_t resw[NC / 4];
-  if (EPI == P2V_EPI_RESIDUAL && row < p.M) {
-    const int8_t* rp = p.res + size_t(row) * N + col0;
-    if ((N & 15) == 0 && (NC & 15) == 0 && col0 + NC <= N) {
-#pragma unroll
-      for (int j = 0; j < NC / 16; ++j) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(rp) + j);
-        resw[4 * j] = v.x; resw[4 * j + 1] = v.y; resw[4 * j + 2] = v.z; resw[4 * j + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < NC / 4; ++j) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (col0 + 4 * j + e < N) w |= (uint32_t(uint8_t(rp[4 * j + e])) << (8 * e));
-        resw[j] = w;
-      }
-    }
-  }
   if (TMEM_WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   if (row >= p.M) return;
   bool slow = false;
@@ -242,7 +261,8 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp
                              else        { constexpr int EPI = P2V_EPI_REQUANT;  constexpr bool POT = false; __VA_ARGS__ } break; \
       case P2V_EPI_GELU:     if (POT_RT) { constexpr int EPI = P2V_EPI_GELU;     constexpr bool POT = true;  __VA_ARGS__ } \
                              else        { constexpr int EPI = P2V_EPI_GELU;     constexpr bool POT = false; __VA_ARGS__ } break; \
-      case P2V_EPI_RESIDUAL: { constexpr int EPI = P2V_EPI_RESIDUAL; constexpr bool POT = false; __VA_ARGS__ } break; \
+      case P2V_EPI_RESIDUAL: if (POT_RT) { constexpr int EPI = P2V_EPI_RESIDUAL; constexpr bool POT = true;  __VA_ARGS__ } \
+                             else        { constexpr int EPI = P2V_EPI_RESIDUAL; constexpr bool POT = false; __VA_ARGS__ } break; \
       case P2V_EPI_EMBED:    { constexpr int EPI = P2V_EPI_EMBED;    constexpr bool POT = false; __VA_ARGS__ } break; \
       case P2V_EPI_DEQUANT:  if (POT_RT) { constexpr int EPI = P2V_EPI_DEQUANT;  constexpr bool POT = true;  __VA_ARGS__ } \
                              else        { constexpr int EPI = P2V_EPI_DEQUANT;  constexpr bool POT = false; __VA_ARGS__ } break; \

@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const int8_t* _
       }
     }
   }
-  epilogue_row<EPI, POT, 64, SIMT_NC>(p, cp, row, n0, c0, acc);
+  uint32_t resw[SIMT_NC / 4];
+  if (EPI == P2V_EPI_RESIDUAL) load_residual<SIMT_NC>(p, row, col0, resw);
+  epilogue_row<EPI, POT, 64, SIMT_NC>(p, cp, row, n0, c0, acc, resw);
 }
 
 int launch_gemm_simt(const p2v_gemm_args& a, cudaStream_t stream) {

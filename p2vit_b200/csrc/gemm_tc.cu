@@ -113,18 +113,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float* cp = col_params[g][use & 1u];
       stage_col_params<EPI, POT, BN>(p, cp, n0, tg);     // overlaps the MMA of this tile
       group_barrier(1 + g);
-      mbar_wait(bar_tfull + 8 * g, use & 1u);
-      tc_fence_after();
       const int row = m0 + int(quarter) * 32 + lane;
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + g * BN;
+      uint32_t res_next[NCH / 4];
+      if (EPI == P2V_EPI_RESIDUAL) load_residual<NCH>(p, row, n0, res_next);   // in flight while the MMA finishes
+      mbar_wait(bar_tfull + 8 * g, use & 1u);
+      tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN / NCH; ++c) {
         if (n0 + c * NCH >= p.N) break;
         int acc[NCH];
+        uint32_t res_cur[NCH / 4];
+#pragma unroll
+        for (int j = 0; j < NCH / 4; ++j) res_cur[j] = res_next[j];
         __syncwarp();
         if (NCH == 32) tmem_ld32_async(taddr + c * NCH, reinterpret_cast<int(&)[32]>(acc[0]));
         else tmem_ld16_async(taddr + c * NCH, reinterpret_cast<int(&)[16]>(acc[0]));
-        epilogue_row<EPI, POT, BN, NCH, true>(p, cp, row, n0, c * NCH, acc);
+        if (EPI == P2V_EPI_RESIDUAL && c + 1 < BN / NCH) load_residual<NCH>(p, row, n0 + (c + 1) * NCH, res_next);
+        epilogue_row<EPI, POT, BN, NCH, true>(p, cp, row, n0, c * NCH, acc, res_cur);
       }
       tc_fence_before();
       __syncwarp();

@@ -185,7 +185,8 @@ class VitEngine:
             g = p["proj"]
             steps.append((pre + "qact2", self._gemm(ops.gemm_args(ws["ao"], g.W, ops.EPI_RESIDUAL, g.acc_scale, bias=g.bias,
                                                                   out_scale=p["proj_out"], mid_scale=p["proj_mid"],
-                                                                  res_scale=p["res1_scale"], res=ws["ra"], out_i8=ws["rb"]))))
+                                                                  res_scale=p["res1_scale"], res=ws["ra"], out_i8=ws["rb"],
+                                                                  pot=intmath.is_pot(g.acc_scale)))))
             steps.append((pre + "norm2", self._ln(p["ln2"], ws["rb"], R, D, D, ws["ln"])))
             g = p["fc1"]
             steps.append((pre + "mlp.qact1", self._gemm(ops.gemm_args(ws["ln"], g.W, ops.EPI_GELU, g.acc_scale, bias=g.bias,
@@ -193,7 +194,8 @@ class VitEngine:
             g = p["fc2"]
             steps.append((pre + "qact4", self._gemm(ops.gemm_args(ws["hid"], g.W, ops.EPI_RESIDUAL, g.acc_scale, bias=g.bias,
                                                                   out_scale=p["fc2_out"], mid_scale=p["fc2_mid"],
-                                                                  res_scale=p["proj_out"], res=ws["rb"], out_i8=ws["ra"]))))
+                                                                  res_scale=p["proj_out"], res=ws["rb"], out_i8=ws["ra"],
+                                                                  pot=intmath.is_pot(g.acc_scale)))))
         steps.append(("qact2", self._ln(pl.ln_f, ws["ra"], B, D, (T + 1) * D, ws["cls"])))
         g = pl.head
         steps.append(("act_out", self._gemm(ops.gemm_args(ws["cls"], g.W, ops.EPI_DEQUANT, g.acc_scale, bias=g.bias, out_scale=pl.head_out,

@@ -149,11 +149,31 @@ def test_gemm_residual_ptf(M, N, K):
     c = (y / mid).round().clamp(-128, 127)
     z = res.float() * rs + c * mid
     ref = (z / outs).round().clamp(-128, 127)
-    for simt in (False, True):
+    for simt, pot in ((False, False), (False, True), (True, False), (True, True)):   # pot: acc_scale is a power of two (single FFMA)
         o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
         ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_RESIDUAL, acc_scale, bias=bias.to(DEV), out_scale=outs, mid_scale=mid,
-                               res_scale=rs, res=res, out_i8=o8), simt=simt)
-        assert torch.equal(o8.float(), ref), "simt=%s mismatches %d" % (simt, int((o8.float() != ref).sum()))
+                               res_scale=rs, res=res, out_i8=o8, pot=pot), simt=simt)
+        assert torch.equal(o8.float(), ref), "simt=%s pot=%s mismatches %d" % (simt, pot, int((o8.float() != ref).sum()))
+
+
+def test_gemm_residual_many_ties():
+    """scales chosen so that a large share of the quotients are exact ties (k + 1/2): exercises the exact (IEEE division) second
+    pass of the two-phase requantisation"""
+    M, N, K = 512, 256, 128
+    A, W, _ = _gemm_inputs(M, N, K, 50)
+    acc_scale = torch.full((N,), 2.0 ** -6).to(DEV)
+    bias = torch.zeros(N, device=DEV)
+    mid = torch.full((N,), 2.0 ** -5 * 3.0).to(DEV)      # y/mid = acc/6: ties whenever acc = 3 mod 6
+    rs = torch.full((N,), 0.75).to(DEV)
+    outs = torch.full((N,), 1.5).to(DEV)
+    res = _rand_codes(M, N, seed=52).to(DEV)
+    y = _acc_exact(A, W).float() * acc_scale
+    c = (y / mid).round().clamp(-128, 127)
+    ref = ((res.float() * rs + c * mid) / outs).round().clamp(-128, 127)
+    o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
+    ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_RESIDUAL, acc_scale, bias=bias, out_scale=outs, mid_scale=mid, res_scale=rs,
+                           res=res, out_i8=o8, pot=True))
+    assert torch.equal(o8.float(), ref), "mismatches %d" % int((o8.float() != ref).sum())
 
 
 def test_gemm_embed_epilogue():
