@@ -25,9 +25,11 @@ Reference map (file:line relative to /root/reference):
 `exact_sums=True` is the canonical, backend-independent variant the CUDA kernels implement: the two
 order-dependent fp32 row reductions of the reference (sum of squares in LayerNorm, layers.py:316-318;
 sum of exp_int in softmax, :416) become exactly-rounded sums (fp64/int accumulation, one final rounding
-to fp32), and LayerNorm's sqrt is the IEEE correctly-rounded one (torch's CPU sqrt is MKL VML, off by one
-ulp on ~0.1% of inputs; torch-CUDA's is IEEE).  Order independent, batch-split invariant; see DESIGN.md
-"tie adjudication".
+to fp32), LayerNorm's sqrt is the IEEE correctly-rounded one (torch's CPU sqrt is MKL VML, off by one
+ulp on ~0.1% of inputs; torch-CUDA's is IEEE), and the matmuls accumulate the integer codes exactly before
+the fp32 scale / bias operations (identical to the reference's fp32 matmul for power-of-two scales, where
+every partial sum is exact; order independent for the raw fp32 scales of ema / percentile).  Batch-split
+invariant; see DESIGN.md "tie adjudication".
 """
 import math
 
@@ -273,9 +275,11 @@ def _log_round(x):
     return big
 
 
-def int_softmax_log2(x, s, bits=4, exact_sums=False):
-    """QIntSoftmax.forward with log_i_softmax (layers.py:384-428).  x: dequantized scores."""
-    x_int = x / s
+def int_softmax_log2(x, s, bits=4, exact_sums=False, codes=None):
+    """QIntSoftmax.forward with log_i_softmax (layers.py:384-428).  x: dequantized scores.  `codes` (canonical variant
+    for raw fp32 scales): the integer codes themselves replace fl(fl(code*s)/s), which is off by one ulp from the
+    integer for ~15 % of the codes when s is not a power of two."""
+    x_int = x / s if codes is None else codes
     x_int = x_int - x_int.max(dim=-1, keepdim=True).values
     n = 32
     x0 = torch.floor(-0.6931 / s)
@@ -443,6 +447,46 @@ class VitOracle:
         qkv = x.reshape(B, N, 3, self.H, self.D // self.H).permute(2, 0, 3, 1, 4)
         return qkv[0], qkv[1], qkv[2]
 
+    # ---- canonical (exact_sums) arithmetic for the matmuls: exact integer accumulation of the codes, then the same two fp32
+    #      operations the reference performs on the accumulated value.  Identical to the reference's fp32 matmul whenever the
+    #      scales are powers of two (every product and partial sum is then exact); for raw fp32 scales (ema / percentile /
+    #      omse observers) the reference's result depends on the BLAS summation order, this one does not.
+    def _codes(self, h, aq):
+        return torch.round(h / aq.scale.reshape(-1))
+
+    def _lin(self, h, aq, wq, w, bit, bias):
+        w_hat = wq.fq(w, bit)
+        wm = w_hat.reshape(w.shape[0], -1)
+        if not self.exact or aq is None or aq.scale.numel() != 1 or bool((aq.zp != 0).any()):
+            return F.linear(h, wm, bias)
+        ws = wq.scale[bit].reshape(-1, 1).float()
+        wc = torch.round(wm / ws)
+        acc = (self._codes(h, aq).double() @ wc.double().T).float()
+        acc_scale = (aq.scale.reshape(-1).float() * ws.reshape(-1)).reshape(*([1] * (h.dim() - 1)), -1)
+        y = acc * acc_scale
+        return y if bias is None else y + bias
+
+    def _attention(self, h, q1, qs, q2, B):
+        """h: dequantized qkv (attn.qact1 output) -> dequantized attn.qact2 output, plus the score / probability taps"""
+        dh = self.D // self.H
+        qh, kh, vh = self._heads(h)
+        canonical = self.exact and not bool((q1.zp != 0).any() or (qs.zp != 0).any() or (q2.zp != 0).any())
+        if not canonical:
+            a = qs((qh @ kh.transpose(-2, -1)) * dh ** -0.5)
+            p = int_softmax_log2(a, qs.scale, 4, self.exact)
+            return a, p, q2((p @ vh).transpose(1, 2).reshape(B, -1, self.D))
+        s1, sa, s2 = q1.scale.reshape(()).double(), qs.scale.reshape(()).double(), q2.scale.reshape(()).double()
+        cq, ck, cv = (torch.round(t / q1.scale.reshape(())).double() for t in (qh, kh, vh))
+        S = (cq @ ck.transpose(-2, -1)).float()
+        mult = (s1 * s1 * dh ** -0.5 / sa).float()
+        ca = torch.clamp(torch.round(S * mult), -128, 127)
+        a = ca * qs.scale.reshape(())
+        p = int_softmax_log2(a, qs.scale, 4, True, codes=ca)
+        O = ((p.double() * 32768.0) @ cv).float()
+        omult = (s1 / s2 / 32768.0).float()
+        c2 = torch.clamp(torch.round(O * omult), -128, 127)
+        return a, p, (c2 * q2.scale.reshape(())).transpose(1, 2).reshape(B, -1, self.D)
+
     # ---- calibration forward (FP values + observers), test_quant.py:275-312
     @torch.no_grad()
     def calibrate(self, x):
@@ -521,8 +565,13 @@ class VitOracle:
         if self.input_quant:
             x = q["qact_input"](x)
             tap("qact_input", x)
-        w = q["patch_embed.proj"].fq(sd["patch_embed.proj.weight"], wname(bits[0]))
-        x = F.conv2d(x, w, sd["patch_embed.proj.bias"], (self.P, self.P)).flatten(2).transpose(1, 2)
+        if self.input_quant and self.exact:
+            P, gs = self.P, x.shape[-1] // self.P
+            rows = x.reshape(B, 3, gs, P, gs, P).permute(0, 2, 4, 1, 3, 5).reshape(B, gs * gs, 3 * P * P)
+            x = self._lin(rows, q["qact_input"], q["patch_embed.proj"], sd["patch_embed.proj.weight"], wname(bits[0]), sd["patch_embed.proj.bias"])
+        else:
+            w = q["patch_embed.proj"].fq(sd["patch_embed.proj.weight"], wname(bits[0]))
+            x = F.conv2d(x, w, sd["patch_embed.proj.bias"], (self.P, self.P)).flatten(2).transpose(1, 2)
         x = q["patch_embed.qact"](x)
         tap("patch_embed.qact", x)
         x = torch.cat((sd["cls_token"].expand(B, -1, -1), x), dim=1)
@@ -539,18 +588,15 @@ class VitOracle:
             tap(p + "norm1", h)
             h = q[p + "attn.qact0"](h / cs_a.reshape(1, 1, -1))
             tap(p + "attn.qact0", h)
-            w = q[p + "attn.qkv"].fq(sd[p + "attn.qkv.weight"] * cs_a.reshape(1, -1), wname(b4[0]))
-            h = q[p + "attn.qact1"](F.linear(h, w, sd[p + "attn.qkv.bias"]))
+            h = q[p + "attn.qact1"](self._lin(h, q[p + "attn.qact0"], q[p + "attn.qkv"], sd[p + "attn.qkv.weight"] * cs_a.reshape(1, -1),
+                                              wname(b4[0]), sd[p + "attn.qkv.bias"]))
             tap(p + "attn.qact1", h)
-            qh, kh, vh = self._heads(h)
-            a = q[p + "attn.qact_attn1"]((qh @ kh.transpose(-2, -1)) * (self.D // self.H) ** -0.5)
+            a, pr, h = self._attention(h, q[p + "attn.qact1"], q[p + "attn.qact_attn1"], q[p + "attn.qact2"], B)
             tap(p + "attn.qact_attn1", a)
-            a = int_softmax_log2(a, q[p + "attn.qact_attn1"].scale, 4, self.exact)
-            tap(p + "attn.log_int_softmax", a)
-            h = q[p + "attn.qact2"]((a @ vh).transpose(1, 2).reshape(B, -1, self.D))
+            tap(p + "attn.log_int_softmax", pr)
             tap(p + "attn.qact2", h)
-            w = q[p + "attn.proj"].fq(sd[p + "attn.proj.weight"], wname(b4[1]))
-            h = q[p + "attn.qact3"](F.linear(h, w, sd[p + "attn.proj.bias"]))
+            h = q[p + "attn.qact3"](self._lin(h, q[p + "attn.qact2"], q[p + "attn.proj"], sd[p + "attn.proj.weight"], wname(b4[1]),
+                                              sd[p + "attn.proj.bias"]))
             tap(p + "attn.qact3", h)
             x = q[p + "qact2"](x + h)
             tap(p + "qact2", x)
@@ -558,11 +604,11 @@ class VitOracle:
             tap(p + "norm2", h)
             h = q[p + "mlp.qact0"](h / cs_m.reshape(1, 1, -1))
             tap(p + "mlp.qact0", h)
-            w = q[p + "mlp.fc1"].fq(sd[p + "mlp.fc1.weight"] * cs_m.reshape(1, -1), wname(b4[2]))
-            h = q[p + "mlp.qact1"](F.gelu(F.linear(h, w, sd[p + "mlp.fc1.bias"])))
+            h = q[p + "mlp.qact1"](F.gelu(self._lin(h, q[p + "mlp.qact0"], q[p + "mlp.fc1"], sd[p + "mlp.fc1.weight"] * cs_m.reshape(1, -1),
+                                                    wname(b4[2]), sd[p + "mlp.fc1.bias"])))
             tap(p + "mlp.qact1", h)
-            w = q[p + "mlp.fc2"].fq(sd[p + "mlp.fc2.weight"], wname(b4[3]))
-            h = q[p + "mlp.qact2"](F.linear(h, w, sd[p + "mlp.fc2.bias"]))
+            h = q[p + "mlp.qact2"](self._lin(h, q[p + "mlp.qact1"], q[p + "mlp.fc2"], sd[p + "mlp.fc2.weight"], wname(b4[3]),
+                                             sd[p + "mlp.fc2.bias"]))
             tap(p + "mlp.qact2", h)
             x = q[p + "qact4"](x + h)
             tap(p + "qact4", x)
@@ -570,6 +616,5 @@ class VitOracle:
         x = self._int_ln(x, "norm", last, q["qact2"])[:, 0]
         x = q["qact2"](x)
         tap("qact2", x)
-        w = q["head"].fq(sd["head.weight"], wname(bits[-1]))
-        x = q["act_out"](F.linear(x, w, sd["head.bias"]))
+        x = q["act_out"](self._lin(x, q["qact2"], q["head"], sd["head.weight"], wname(bits[-1]), sd["head.bias"]))
         return x

@@ -55,9 +55,6 @@ class VitPlan:
             raise ValueError("bit_config needs %d entries (1 + 4*depth + 1), got %d" % (4 * L + 2, len(bits)))
         if any(b not in (4, 8) for b in bits):
             raise ValueError("bit_config entries must be 4 or 8 (registered weight bit types int4/int8)")
-        if not m.input_quant:
-            raise NotImplementedError("input_quant=False (ViT-L: fp32 pixels into the patch embedding, SURVEY Q15) is not "
-                                      "on the int8 path yet")
         if not all(isinstance(x, QIntLayerNorm) and x.mode == "int" for x in [m.norm] + [b.norm1 for b in m.blocks]):
             raise NotImplementedError("the integer engine needs QIntLayerNorm in 'int' mode (Config(ptf=True))")
         if not m.cfg.INT_SOFTMAX:
@@ -66,12 +63,22 @@ class VitPlan:
         self.P = m.patch_size
         self.T = m.patch_embed.num_patches
         # ---- stem
-        self.s_in = float(_sym_scale(m.qact_input, "qact_input"))
         pe = m.patch_embed
-        self.g_embed = _Gemm(pe.proj, pe.proj.weight, bits[0], _sym_scale(m.qact_input, "qact_input"), dev)
+        self.input_quant = bool(m.input_quant)
+        if self.input_quant:
+            self.s_in = float(_sym_scale(m.qact_input, "qact_input"))
+            self.g_embed = _Gemm(pe.proj, pe.proj.weight, bits[0], _sym_scale(m.qact_input, "qact_input"), dev)
+        else:
+            # ViT-L (vit_fquant.py:1063): raw fp32 pixels meet fake-quantized weights, so the patch embedding is an
+            # fp32 GEMM in the reference too; only its output enters the integer domain (patch_embed.qact).
+            pe.proj._set_bits(bits[0])
+            codes, ws = pe.proj.weight_codes(pe.proj.weight)
+            self.w_embed_hat = (codes.float() * ws.reshape(-1, 1)).contiguous()
+            self.b_embed = pe.proj.bias.detach().float().contiguous()
         self.s_pe = _vec(_sym_scale(pe.qact, "patch_embed.qact"), 1, dev)
         s_e = _sym_scale(m.qact_embed, "qact_embed").to(dev)
         self.s_e = float(s_e)
+        self.s_e_vec = _vec(s_e, 1, dev)
         s_p = _sym_scale(m.qact_pos, "qact_pos").to(dev)
         s0 = _vec(_sym_scale(m.qact1, "qact1"), D, dev)
         pos = m.pos_embed.detach().float()
@@ -164,15 +171,27 @@ class VitEngine:
         R = B * (T + 1)
         i8 = lambda *s: torch.empty(s, dtype=torch.int8, device=dev)
         ws = dict(img=torch.empty((B, 3, T_side(pl), T_side(pl)), dtype=torch.float32, device=dev),
-                  cols=i8(B * T, pl.g_embed.K), ra=i8(R, D), rb=i8(R, D), ln=i8(R, D), qkv=i8(R, 3 * D), ao=i8(R, D),
+                  cols=i8(B * T, 3 * pl.P * pl.P), ra=i8(R, D), rb=i8(R, D), ln=i8(R, D), qkv=i8(R, 3 * D), ao=i8(R, D),
                   hid=i8(R, pl.blocks[0]["fc1"].N), cls=i8(B, D),
                   logits=torch.empty((B, pl.head.N), dtype=torch.float32, device=dev), logit_codes=i8(B, pl.head.N))
         steps = []
-        g = pl.g_embed
-        steps.append(("patchify", lambda: ops.quantize_patchify(ws["img"], pl.P, pl.s_in, out=ws["cols"])))
-        steps.append(("embed", self._gemm(ops.gemm_args(ws["cols"], g.W, ops.EPI_EMBED, g.acc_scale, bias=g.bias, out_scale=pl.s_r0,
-                                                        mid_scale=pl.s_pe, pos=pl.pos_hat, aux_scale=pl.s_e, tokens_per_image=T,
-                                                        out_i8=ws["ra"]))))
+        if pl.input_quant:
+            g = pl.g_embed
+            steps.append(("patchify", lambda: ops.quantize_patchify(ws["img"], pl.P, pl.s_in, out=ws["cols"])))
+            steps.append(("embed", self._gemm(ops.gemm_args(ws["cols"], g.W, ops.EPI_EMBED, g.acc_scale, bias=g.bias, out_scale=pl.s_r0,
+                                                            mid_scale=pl.s_pe, pos=pl.pos_hat, aux_scale=pl.s_e, tokens_per_image=T,
+                                                            out_i8=ws["ra"]))))
+        else:
+            def embed_fp32():
+                P, gs = pl.P, int(round(T ** 0.5))
+                rows = ws["img"].reshape(B, 3, gs, P, gs, P).permute(0, 2, 4, 1, 3, 5).reshape(B * T, 3 * P * P)
+                y = torch.nn.functional.linear(rows, pl.w_embed_hat, pl.b_embed).reshape(B, T, D)
+                y = ops.fake_quant(y, pl.s_pe)                                      # patch_embed.qact
+                y = ops.fake_quant(y, pl.s_e_vec)                                   # qact_embed (class row handled by `cls`)
+                y = y + pl.pos_hat[1:].reshape(1, T, D)
+                ws["ra"].reshape(B, T + 1, D)[:, 1:].copy_(ops.quantize(y.contiguous(), pl.s_r0))   # qact1 (PTF)
+            steps.append(("patchify", lambda: None))
+            steps.append(("embed", embed_fp32))
         steps.append(("cls", lambda: ops.fill_cls_rows(ws["ra"], pl.cls_row, B, T, D)))
         for i, p in enumerate(pl.blocks):
             pre = "blocks.%d." % i

@@ -135,6 +135,11 @@ class QConv2d(nn.Conv2d, _QWeightMixin):
         if not self.quant:
             return self._fp_conv(x, self.weight)
         self._set_bits(bit_config)
+        if getattr(x, "_p2v_codes", None) is None:
+            # input_quant=False models (ViT-L, vit_fquant.py:1063): raw fp32 pixels meet fake-quantized weights, so
+            # this convolution is an fp32 GEMM in the reference as well - not a fallback of the int8 path
+            wq, ws = self.weight_codes(self.weight)
+            return self._fp_conv(x, (wq.float() * ws.reshape(-1, 1)).reshape(self.weight.shape))
         codes, a_scale, a_zp = _require_codes(x, "QConv2d")
         k = self.kernel_size[0]
         B, Cin, H, W = x.shape
