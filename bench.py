@@ -28,7 +28,6 @@ sys.path.insert(0, ROOT)
 from p2vit_b200 import synth  # noqa: E402
 
 # MACs per image = L*(12*N*D^2 + 2*N^2*D) + 196*768*D + 1000*D
-GMAC = {"deit_tiny": 1.2537, "deit_small": 4.5989, "deit_base": 17.5638, "vit_base": 17.5638, "vit_micro": None}
 
 
 def macs_per_image(name):
@@ -108,6 +107,26 @@ def load_state(name):
     return {k[6:]: g[k] for k in g.files if k.startswith("state/")}
 
 
+def make_bit_config(kind, model):
+    """1 + 4*depth + 1 entries.  'mixed': the sampling rule of the reference's search (test_quant.py:323-341): first layer 8 bit,
+    the attention pair and the MLP pair of a block share a width, sum(MACs_i * bits_i) <= 1.1 * sum(MACs_i * 4), seed 0."""
+    n = 4 * model.depth + 2
+    if kind in ("8", "4"):
+        return [int(kind)] * n
+    import random
+    rnd = random.Random(0)
+    flops = model.flops_list()
+    budget = 1.1 * sum(f * 4 for f in flops)
+    while True:
+        cfg = [8]
+        for _ in range(model.depth):
+            a, m = rnd.choice([4, 8]), rnd.choice([4, 8])
+            cfg += [a, a, m, m]
+        cfg.append(rnd.choice([4, 8]))
+        if sum(f * b for f, b in zip(flops, cfg)) <= budget:
+            return cfg
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -119,12 +138,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--golden-state", action="store_true", help="load the reference-calibrated state instead of calibrating on the GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bits", default="8", help="'8', '4' or 'mixed' (seeded {4,8} draw under the 1.1 x 4-bit budget of test_quant.py:323-341)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    workload = "%s W8A8 PoT minmax, 224x224, batch %d/GPU" % (args.model, args.batch)
+    workload = "%s W%sA8 PoT minmax, 224x224, batch %d/GPU" % (args.model, args.bits if args.bits != "mixed" else "4/8", args.batch)
 
     if args.impl == "reference":
         if rank != 0:
@@ -164,7 +184,7 @@ def main():
         calibrate_model(model, synth.synth_images(e - s, seed=0, start=s).to(dev))
         calib_src = "calibrated on the GPU(s) from %d synthetic images" % args.calib
     calib_s = time.time() - t0
-    bits = [8] * (4 * model.depth + 2)
+    bits = make_bit_config(args.bits, model)
     B = args.batch
     eng = VitEngine(model, use_graph=True)
     model._engine = eng
@@ -313,7 +333,7 @@ def main():
     line = {"metric": "images/sec (224^2, int8 PoT)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 (int32 accumulate, fp32 requant epilogue)", "data": "synthetic",
-            "config": {"workload": workload, "global_batch": B * world, "bit_config": "[8]*%d" % len(bits), "calibration": calib_src,
+            "config": {"workload": workload, "global_batch": B * world, "bit_config": ("[%s]*%d" % (args.bits, len(bits))) if args.bits in ("8", "4") else "".join(str(b) for b in bits), "calibration": calib_src,
                        "calibration_seconds": round(calib_s, 2), "l2": "inputs larger than L2 (fp32 images %.0f MB + int8 workspace per step)" % (B * 3 * 224 * 224 * 4 / 1e6),
                        "parallelism": "dp%d (batch sharded, no collective in the forward)" % world, "cuda_graph": True},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 * world, "d2h_bytes_per_step": B * 1000 * 4 * world,
