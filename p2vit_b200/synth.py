@@ -16,7 +16,7 @@ import zlib
 import numpy as np
 import torch
 
-__all__ = ["VIT_CONFIGS", "synth_vit_state_dict", "synth_images"]
+__all__ = ["VIT_CONFIGS", "SWIN_CONFIGS", "synth_vit_state_dict", "synth_swin_state_dict", "synth_images"]
 
 # name -> dict(embed_dim, depth, num_heads, input_quant)      vit_fquant.py:942-1074
 VIT_CONFIGS = {
@@ -67,6 +67,57 @@ def synth_vit_state_dict(embed_dim, depth, num_heads=None, seed=0, patch=16, in_
     n("norm.weight", (D,), 0.15, 1.0)
     n("norm.bias", (D,), 0.02)
     n("head.weight", (num_classes, D), 0.08)
+    sd["head.bias"] = torch.zeros(num_classes, dtype=torch.float32)
+    return sd
+
+
+# name -> dict(embed_dim, depths, num_heads)      swin_quant.py:917-995 (window 7, patch 4, mlp_ratio 4, input_quant=True)
+SWIN_CONFIGS = {
+    "swin_micro": dict(embed_dim=32, depths=(2, 2), num_heads=(1, 2)),          # test-only size: stages 56x56 and 28x28
+    "swin_tiny": dict(embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24)),
+    "swin_small": dict(embed_dim=96, depths=(2, 2, 18, 2), num_heads=(3, 6, 12, 24)),
+    "swin_base": dict(embed_dim=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32)),
+}
+
+
+def synth_swin_state_dict(embed_dim, depths, num_heads, seed=0, patch=4, in_chans=3, num_classes=1000, mlp_ratio=4, window=7, **_):
+    """parameter names of models/swin_quant.py (SwinTransformer :636-914); `downsample.reduction.bias` is the all-zero bias the
+    reference needs to calibrate its bias-free QLinear."""
+    sd = {}
+    n = lambda name, shape, std, mean=0.0: sd.__setitem__(name, _normal(seed, name, shape, std, mean))
+    C0 = embed_dim
+    n("patch_embed.proj.weight", (C0, in_chans, patch, patch), 0.15)
+    n("patch_embed.proj.bias", (C0,), 0.1)
+    n("patch_embed.norm.weight", (C0,), 0.15, 1.0)
+    n("patch_embed.norm.bias", (C0,), 0.1)
+    for i, (depth, heads) in enumerate(zip(depths, num_heads)):
+        C = C0 * 2 ** i
+        Hd = int(C * mlp_ratio)
+        for j in range(depth):
+            p = "layers.%d.blocks.%d." % (i, j)
+            n(p + "norm1.weight", (C,), 0.15, 1.0)
+            n(p + "norm1.bias", (C,), 0.1)
+            n(p + "attn.relative_position_bias_table", ((2 * window - 1) ** 2, heads), 0.5)
+            n(p + "attn.qkv.weight", (3 * C, C), 0.9 / C ** 0.5)
+            n(p + "attn.qkv.bias", (3 * C,), 0.1)
+            n(p + "attn.proj.weight", (C, C), 0.5 / C ** 0.5)
+            n(p + "attn.proj.bias", (C,), 0.05)
+            n(p + "norm2.weight", (C,), 0.15, 1.0)
+            n(p + "norm2.bias", (C,), 0.1)
+            n(p + "mlp.fc1.weight", (Hd, C), 0.7 / C ** 0.5)
+            n(p + "mlp.fc1.bias", (Hd,), 0.1)
+            n(p + "mlp.fc2.weight", (C, Hd), 0.6 / Hd ** 0.5)
+            n(p + "mlp.fc2.bias", (C,), 0.05)
+        if i < len(depths) - 1:
+            p = "layers.%d.downsample." % i
+            n(p + "norm.weight", (4 * C,), 0.15, 1.0)
+            n(p + "norm.bias", (4 * C,), 0.1)
+            n(p + "reduction.weight", (2 * C, 4 * C), 0.7 / (4 * C) ** 0.5)
+            sd[p + "reduction.bias"] = torch.zeros(2 * C, dtype=torch.float32)
+    Cf = C0 * 2 ** (len(depths) - 1)
+    n("norm.weight", (Cf,), 0.15, 1.0)
+    n("norm.bias", (Cf,), 0.02)
+    n("head.weight", (num_classes, Cf), 0.3)
     sd["head.bias"] = torch.zeros(num_classes, dtype=torch.float32)
     return sd
 
