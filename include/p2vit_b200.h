@@ -90,6 +90,8 @@ typedef struct {
   int tokens_per_image;     /* EMBED: T (196) */
   int8_t* out_i8;           /* [M,N] (EMBED: [B*(T+1),N]) */
   float* out_f32;           /* [M,N] DEQUANT / F32 */
+  const int32_t* row_map;   /* [M] or NULL (REQUANT/GELU/RESIDUAL): output row (and residual row) of GEMM row m - Swin window
+                               reverse + inverse cyclic shift fused into the store (swin_quant.py:426-436) */
   int pot_scales;           /* REQUANT/GELU/DEQUANT: 1 = acc_scale and out_scale are exact powers of two (division == exact
                                multiply); RESIDUAL: 1 = acc_scale is (acc*acc_scale exact; mid/out scales stay general) */
 } p2v_gemm_args;
@@ -122,6 +124,10 @@ typedef struct {
   int pot_scales;           /* 1: out_scale, post_div, next_scale are powers of two */
   int8_t* out_i8;           /* [rows,C] */
   float* out_f32;           /* optional [rows,C]: y_q * out_scale (eager QIntLayerNorm.forward result) */
+  const int32_t* out_row_map; /* [rows] or NULL: destination row of out_i8 for input row r - Swin cyclic shift + window partition
+                                 fused into the store (swin_quant.py:408-419) */
+  int clamp_mid;            /* 1: y_q is clamped to [-128,127] first - a QAct at the LayerNorm's own output scale sits between the
+                               LayerNorm and the smoothing divide (Swin: norm2 -> qact3 -> Mlp, swin_quant.py:439-446) */
 } p2v_layernorm_args;
 
 int p2v_layernorm_int(const p2v_layernorm_args* args_host, void* stream);
@@ -167,6 +173,41 @@ typedef struct {
 int p2v_attention_i8(const p2v_attention_args* args_host, void* stream);
 /* same contract, always on CUDA cores (dp4a); used by tests to cross-check the tcgen05 kernel */
 int p2v_attention_i8_simt(const p2v_attention_args* args_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Swin window attention between attn.qact1 and attn.qact3            (swin_quant.py:211-249)
+ *   S = q k^T (int32, head scale factored out);  c1 = sat(RNE(S * score_mult))           qact_attn1
+ *   c2 = sat(RNE(fl(fl(c1*s_attn1) + bias[h,i,j]) / s_attn2))                             + quantized rel-pos bias -> qact2
+ *   x_int = c2 + mask_code * [label_i != label_j]      (SW-MSA mask -100 added after qact2, as integer -100/s_attn2)
+ *   p = int_softmax_log2(x_int);  O = sum_j 2^(15-code_j) v_j;  out = sat(RNE(O * out_mult))              qact3
+ * qkv: int8 [nWin_total, T, 3, H, dh] in window order; out: int8 [nWin_total, T, H*dh]; T = ws*ws <= 64, dh = 32.
+ * bias: fp32 [H, T, T] dequantized qact_table(relative_position_bias_table)[relative_position_index];
+ * labels: int8 [windows_per_image, T] SW-MSA region labels or NULL (no shift); window w uses labels[w % windows_per_image].
+ * lut_dev: table for s_attn2; masked entries use the table's clamped tail (the host checks -100/s_attn2 reaches it).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n_windows, T, H, dh, windows_per_image;
+  const int8_t* qkv;
+  int8_t* out;
+  float score_mult;         /* s_q^2 * dh^-0.5 / s_attn1 */
+  float s_attn1, s_attn2;
+  const float* bias;
+  const int8_t* labels;
+  int mask_code;            /* RNE(-100 / s_attn2) (negative) */
+  uint32_t mask_exp_int;    /* exp_int of a masked entry: the clamped tail floor((1/0.35815147)/s_attn2^2) of int_exp
+                               (layers.py:396-410 with x_int = 32*x0) */
+  float out_mult;           /* 2^-15 * s_v / s_attn3 */
+  const p2v_softmax_lut* lut_dev;
+} p2v_window_attention_args;
+
+int p2v_window_attention_i8(const p2v_window_attention_args* args_host, void* stream);
+
+/* Patch merging gather (swin_quant.py:512-519): out[r, k*C:(k+1)*C] = in[src_rows[r*segs + k], :]  (int8 rows of C bytes) */
+int p2v_gather_rows_i8(const int8_t* in, int8_t* out, const int32_t* src_rows, int rows_out, int segs, int C, void* stream);
+
+/* Token average pooling + QAct (swin_quant.py:904-905): codes [B, T, C] at scale s_in ->
+ * out[b, c] = sat(RNE(fl(fl(float(sum_t codes) * s_in) / T) / s_out))   (the sum of codes is exact) */
+int p2v_avgpool_quant_i8(const int8_t* in, int8_t* out, int B, int T, int C, float s_in, float s_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Calibration observers                           (observer/minmax.py:15-32, ptf.py:13-30, base.py:16-29)

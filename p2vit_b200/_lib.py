@@ -24,6 +24,7 @@ class GemmArgs(C.Structure):
         ("res", C.c_void_p), ("pos", C.c_void_p),
         ("aux_scale", C.c_float), ("tokens_per_image", C.c_int),
         ("out_i8", C.c_void_p), ("out_f32", C.c_void_p),
+        ("row_map", C.c_void_p),
         ("pot_scales", C.c_int),
     ]
 
@@ -37,6 +38,17 @@ class LayerNormArgs(C.Structure):
         ("out_scale", C.c_void_p), ("post_div", C.c_void_p),
         ("next_scale", C.c_float), ("pot_scales", C.c_int),
         ("out_i8", C.c_void_p), ("out_f32", C.c_void_p),
+        ("out_row_map", C.c_void_p), ("clamp_mid", C.c_int),
+    ]
+
+
+class WindowAttentionArgs(C.Structure):
+    _fields_ = [
+        ("n_windows", C.c_int), ("T", C.c_int), ("H", C.c_int), ("dh", C.c_int), ("windows_per_image", C.c_int),
+        ("qkv", C.c_void_p), ("out", C.c_void_p),
+        ("score_mult", C.c_float), ("s_attn1", C.c_float), ("s_attn2", C.c_float),
+        ("bias", C.c_void_p), ("labels", C.c_void_p), ("mask_code", C.c_int), ("mask_exp_int", C.c_uint32),
+        ("out_mult", C.c_float), ("lut_dev", C.c_void_p),
     ]
 
 
@@ -68,6 +80,9 @@ SYMBOLS = {
     "p2v_int_softmax_log2": (_I, [_P, _P, _I64, _I, _P, _P]),
     "p2v_attention_i8": (_I, [C.POINTER(AttentionArgs), _P]),
     "p2v_attention_i8_simt": (_I, [C.POINTER(AttentionArgs), _P]),
+    "p2v_window_attention_i8": (_I, [C.POINTER(WindowAttentionArgs), _P]),
+    "p2v_gather_rows_i8": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "p2v_avgpool_quant_i8": (_I, [_P, _P, _I, _I, _I, _F, _F, _P]),
     "p2v_minmax_per_channel": (_I, [_P, _P, _I64, _I, _I64, _P]),
     "p2v_quant_mse_scores": (_I, [_P, _I64, _I, _I64, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
 }

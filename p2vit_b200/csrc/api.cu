@@ -40,6 +40,9 @@ int launch_softmax(const int8_t* scores, uint8_t* out, int64_t rows, int n, cons
 int launch_attention(const p2v_attention_args& a, cudaStream_t stream);
 int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream);
 bool attention_tc_supported(const p2v_attention_args& a);
+int launch_window_attention(const p2v_window_attention_args& a, uint32_t e_mask, cudaStream_t stream);
+int launch_gather_rows(const int8_t* in, int8_t* out, const int32_t* src, int rows_out, int segs, int C, cudaStream_t stream);
+int launch_avgpool_quant(const int8_t* in, int8_t* out, int B, int T, int C, float s_in, float s_out, cudaStream_t stream);
 int launch_minmax(const float* x, float* minmax, int64_t n, int C, int64_t inner, cudaStream_t stream);
 int launch_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales, const float* zps, int K, int n_scale,
                       int per_channel_out, int lo, int hi, double* out, cudaStream_t stream);
@@ -133,6 +136,23 @@ int p2v_attention_i8(const p2v_attention_args* a, void* stream) {
 int p2v_attention_i8_simt(const p2v_attention_args* a, void* stream) {
   if (int r = validate_attention(a)) return r;
   return launch_attention(*a, (cudaStream_t)stream);
+}
+int p2v_window_attention_i8(const p2v_window_attention_args* a, void* stream) {
+  P2V_REQUIRE(a && a->qkv && a->out && a->bias && a->lut_dev, "window_attention: missing pointers");
+  P2V_REQUIRE(a->n_windows > 0 && a->H > 0 && a->T > 0 && a->T <= 64, "window_attention: T=%d unsupported (1..64)", a->T);
+  P2V_REQUIRE(a->dh == 32 || a->dh == 64, "window_attention: head dim %d unsupported (32 or 64)", a->dh);
+  P2V_REQUIRE(a->windows_per_image > 0 && a->mask_code <= 0, "window_attention: bad mask arguments");
+  P2V_REQUIRE((reinterpret_cast<uintptr_t>(a->qkv) & 15) == 0, "window_attention: qkv must be 16-byte aligned");
+  return launch_window_attention(*a, a->mask_exp_int, (cudaStream_t)stream);
+}
+int p2v_gather_rows_i8(const int8_t* in, int8_t* out, const int32_t* src_rows, int rows_out, int segs, int C, void* stream) {
+  P2V_REQUIRE(in && out && src_rows && rows_out > 0 && segs > 0 && C > 0 && C % 16 == 0, "gather_rows: bad arguments (C %% 16 == 0)");
+  P2V_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "gather_rows: 16-byte alignment");
+  return launch_gather_rows(in, out, src_rows, rows_out, segs, C, (cudaStream_t)stream);
+}
+int p2v_avgpool_quant_i8(const int8_t* in, int8_t* out, int B, int T, int C, float s_in, float s_out, void* stream) {
+  P2V_REQUIRE(in && out && B > 0 && T > 0 && C > 0 && s_in > 0.f && s_out > 0.f, "avgpool_quant: bad arguments");
+  return launch_avgpool_quant(in, out, B, T, C, s_in, s_out, (cudaStream_t)stream);
 }
 int p2v_minmax_per_channel(const float* x, float* minmax, int64_t n, int C, int64_t inner, void* stream) {
   P2V_REQUIRE(x && minmax && n > 0 && C > 0 && inner > 0 && n % (int64_t(C) * inner) == 0, "minmax: bad arguments");

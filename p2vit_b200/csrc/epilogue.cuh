@@ -22,6 +22,7 @@ struct EpiParams {  // device-side copy of p2v_gemm_args (pointers only)
   const float* mid_scale;
   const float* res_scale;
   const int8_t* res;
+  const int32_t* row_map;
   const float* pos;
   float aux_scale;
   int tokens_per_image;
@@ -34,6 +35,7 @@ inline EpiParams make_epi_params(const p2v_gemm_args& a) {
   p.M = a.M; p.N = a.N; p.K = a.K;
   p.acc_scale = a.acc_scale; p.bias = a.bias; p.zp_corr = a.zp_corr; p.out_scale = a.out_scale;
   p.mid_scale = a.mid_scale; p.res_scale = a.res_scale; p.res = a.res; p.pos = a.pos;
+  p.row_map = a.row_map;
   p.aux_scale = a.aux_scale; p.tokens_per_image = a.tokens_per_image;
   p.out_i8 = a.out_i8; p.out_f32 = a.out_f32;
   return p;
@@ -183,7 +185,7 @@ __device__ __forceinline__ void load_residual(const EpiParams& p, int row, int c
     for (int j = 0; j < NC / 4; ++j) resw[j] = 0u;
     return;
   }
-  const int8_t* rp = p.res + size_t(row) * N + col0;
+  const int8_t* rp = p.res + size_t(p.row_map ? __ldg(p.row_map + row) : row) * N + col0;
   if ((N & 15) == 0 && (NC & 15) == 0 && col0 + NC <= N) {
 #pragma unroll
     for (int j = 0; j < NC / 16; ++j) {
@@ -217,7 +219,7 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp
   bool slow = false;
   epilogue_math<EPI, POT, BN, NC, false>(p, cp, row, col0, c0, acc, resw, q, f, slow);
   if (slow) epilogue_math<EPI, POT, BN, NC, true>(p, cp, row, col0, c0, acc, resw, q, f, slow);
-  size_t orow = size_t(row);
+  size_t orow = size_t(p.row_map ? __ldg(p.row_map + row) : row);
   if (EPI == P2V_EPI_EMBED) {
     const int T = p.tokens_per_image;
     orow = size_t(row / T) * (T + 1) + (row % T) + 1;

@@ -206,9 +206,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
           const float yq = rintf(fmul(fadd(fmul(fmul(sgn, M), float(xv[i][e])), Bv), pow2i(-N)));  // :336
           const float deq = fmul(yq, os[e]);                                                       // :337
           yf[e] = deq;
-          q[e] = sat_s8(div_by<POT>(div_by<POT>(deq, pd[e]), a.next_scale));
+          const float mid = a.clamp_mid ? fmul(fminf(fmaxf(yq, -128.f), 127.f), os[e]) : deq;       // QAct at the LN's own scale
+          q[e] = sat_s8(div_by<POT>(div_by<POT>(mid, pd[e]), a.next_scale));
         }
-        if (a.out_i8) reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(row) * a.C)[w] = pack4_s8(q[0], q[1], q[2], q[3]);
+        if (a.out_i8) reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(a.out_row_map ? __ldg(a.out_row_map + row) : row) * a.C)[w] = pack4_s8(q[0], q[1], q[2], q[3]);
         if (a.out_f32) reinterpret_cast<float4*>(a.out_f32 + int64_t(row) * a.C)[w] = make_float4(yf[0], yf[1], yf[2], yf[3]);
       }
     }
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
 
 template <bool SLOW>
 __device__ __forceinline__ uint32_t ln_pot_word(float t, float mos, const float (&g)[4], const float (&bt)[4], const float (&f)[4],
-                                                const int (&xv)[4]) {
+                                                const int (&xv)[4], float clamp_hi) {
   int q[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -232,7 +233,8 @@ __device__ __forceinline__ uint32_t ln_pot_word(float t, float mos, const float 
     const float M = fminf(floorf(fmul(__uint_as_float(ab), twoN)), 255.f);
     const float sM = __uint_as_float(__float_as_uint(M) | (__float_as_uint(A) & 0x80000000u));
     const float Bv = rintf(fmul(fsub(bt[e], fmul(mos, g[e])), twoN));
-    const float yq = rintf(fmul(fadd(fmul(sM, float(xv[e])), Bv), rtwoN));
+    float yq = rintf(fmul(fadd(fmul(sM, float(xv[e])), Bv), rtwoN));
+    yq = fminf(fmaxf(yq, -clamp_hi - 1.f), clamp_hi);       // clamp_mid: [-128,127]; otherwise +-inf bounds (no-op)
     q[e] = sat_s8(fmul(yq, f[e]));
   }
   return pack4_s8(q[0], q[1], q[2], q[3]);
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
     }
   }
   const float Cf = float(a.C), s1 = a.in_scale_min, s1c = fdiv(s1, Cf);
+  const float clamp_hi = a.clamp_mid ? 127.f : __int_as_float(0x7f800000);
   for (int row = warp_global * GPW + grp; row < a.rows; row += row_stride) {
     const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
     int xv[WPLN][4];
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
     const float stdv = fmul(s1c, __fsqrt_rn(fsub(fmul(Cf, S2f), fmul(S1f, S1f))));
     const float t = fdiv(s1, stdv);
     const float mos = fdiv(mean, stdv);
-    uint32_t* orow = reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(row) * a.C);
+    uint32_t* orow = reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(a.out_row_map ? __ldg(a.out_row_map + row) : row) * a.C);
     // floor(log2|A|) is the float exponent except within 16 ulps below a power of two (floor_log2_as_fp32); rows where
     // some channel is that close take the second instantiation, so the common loop has no branch per element.
     bool slow = false;
@@ -309,11 +312,11 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
     if (!slow) {
 #pragma unroll
       for (int i = 0; i < WPLN; ++i)
-        orow[sub + LPR * i] = ln_pot_word<false>(t, mos, g[i], bt[i], f[i], xv[i]);
+        orow[sub + LPR * i] = ln_pot_word<false>(t, mos, g[i], bt[i], f[i], xv[i], clamp_hi);
     } else {
 #pragma unroll
       for (int i = 0; i < WPLN; ++i)
-        orow[sub + LPR * i] = ln_pot_word<true>(t, mos, g[i], bt[i], f[i], xv[i]);
+        orow[sub + LPR * i] = ln_pot_word<true>(t, mos, g[i], bt[i], f[i], xv[i], clamp_hi);
     }
   }
 }

@@ -6,7 +6,7 @@ import torch
 
 from . import _lib
 from ._lib import (EPI_DEQUANT, EPI_EMBED, EPI_F32, EPI_GELU, EPI_REQUANT, EPI_RESIDUAL,  # noqa: F401
-                   AttentionArgs, GemmArgs, LayerNormArgs, check, ptr, stream)
+                   AttentionArgs, GemmArgs, LayerNormArgs, WindowAttentionArgs, check, ptr, stream)
 
 
 def _scale_vec(scale, device):
@@ -66,7 +66,7 @@ def quantize_patchify(img, patch, scale, zero_point=0.0, lo=-128, hi=127, out=No
 
 
 def gemm_args(A, W, epilogue, acc_scale, bias=None, out_scale=None, mid_scale=None, res_scale=None, res=None, pos=None,
-              aux_scale=0.0, tokens_per_image=0, out_i8=None, out_f32=None, pot=False, zp_corr=None):
+              aux_scale=0.0, tokens_per_image=0, out_i8=None, out_f32=None, pot=False, zp_corr=None, row_map=None):
     M, K = A.shape
     N = W.shape[0]
     assert W.shape[1] == K
@@ -79,6 +79,7 @@ def gemm_args(A, W, epilogue, acc_scale, bias=None, out_scale=None, mid_scale=No
     a.res, a.pos = ptr(res), ptr(pos)
     a.aux_scale, a.tokens_per_image = float(aux_scale), int(tokens_per_image)
     a.out_i8, a.out_f32 = ptr(out_i8), ptr(out_f32)
+    a.row_map = ptr(row_map)
     a.pot_scales = 1 if pot else 0
     return a
 
@@ -94,7 +95,7 @@ def fill_cls_rows(out, cls_row, B, T, N):
 
 
 def layernorm_args(x, rows, Cn, row_stride, in_mult, in_scale_min, gamma, beta, out_scale, post_div, next_scale, pot,
-                   out_i8=None, out_f32=None):
+                   out_i8=None, out_f32=None, out_row_map=None, clamp_mid=False):
     a = LayerNormArgs()
     a.rows, a.C = rows, Cn
     a.x, a.x_row_stride = ptr(x), row_stride
@@ -103,6 +104,7 @@ def layernorm_args(x, rows, Cn, row_stride, in_mult, in_scale_min, gamma, beta, 
     a.out_scale, a.post_div = ptr(out_scale), ptr(post_div)
     a.next_scale, a.pot_scales = float(next_scale), 1 if pot else 0
     a.out_i8, a.out_f32 = ptr(out_i8), ptr(out_f32)
+    a.out_row_map, a.clamp_mid = ptr(out_row_map), 1 if clamp_mid else 0
     return a
 
 
@@ -133,6 +135,29 @@ def attention(args, simt=False):
     lib = _lib.load()
     fn = lib.p2v_attention_i8_simt if simt else lib.p2v_attention_i8
     check(fn(C.byref(args), stream()), "attention_i8_simt" if simt else "attention_i8")
+
+
+def window_attention_args(qkv, out, n_windows, T, H, dh, windows_per_image, score_mult, s_attn1, s_attn2, bias, labels, mask_code,
+                          mask_exp_int, out_mult, lut_dev):
+    a = WindowAttentionArgs()
+    a.n_windows, a.T, a.H, a.dh, a.windows_per_image = n_windows, T, H, dh, windows_per_image
+    a.qkv, a.out = ptr(qkv), ptr(out)
+    a.score_mult, a.s_attn1, a.s_attn2 = float(score_mult), float(s_attn1), float(s_attn2)
+    a.bias, a.labels, a.mask_code, a.mask_exp_int = ptr(bias), ptr(labels), int(mask_code), int(mask_exp_int)
+    a.out_mult, a.lut_dev = float(out_mult), ptr(lut_dev)
+    return a
+
+
+def window_attention(args):
+    check(_lib.load().p2v_window_attention_i8(C.byref(args), stream()), "window_attention_i8")
+
+
+def gather_rows(x, out, src_rows, rows_out, segs, Cn):
+    check(_lib.load().p2v_gather_rows_i8(ptr(x), ptr(out), ptr(src_rows), rows_out, segs, Cn, stream()), "gather_rows_i8")
+
+
+def avgpool_quant(x, out, B, T, Cn, s_in, s_out):
+    check(_lib.load().p2v_avgpool_quant_i8(ptr(x), ptr(out), B, T, Cn, float(s_in), float(s_out), stream()), "avgpool_quant_i8")
 
 
 def minmax_per_channel(x):

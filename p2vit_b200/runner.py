@@ -15,6 +15,7 @@ import torch.nn.functional as F
 from . import synth
 from .config import Config
 from .ptq import QIntLayerNorm
+from .swin import SwinTransformer, swin_base_patch4_window7_224, swin_small_patch4_window7_224, swin_tiny_patch4_window7_224
 from .vit import (VisionTransformer, deit_base_patch16_224, deit_small_patch16_224, deit_tiny_patch16_224,
                   vit_base_patch16_224, vit_large_patch16_224)
 
@@ -27,12 +28,26 @@ def str2model(name):
         "deit_base": deit_base_patch16_224,
         "vit_base": vit_base_patch16_224,
         "vit_large": vit_large_patch16_224,
+        "swin_tiny": swin_tiny_patch4_window7_224,
+        "swin_small": swin_small_patch4_window7_224,
+        "swin_base": swin_base_patch4_window7_224,
     }[name]
 
 
 def build_model(name, cfg=None, seed=0, device="cuda"):
     """Model `name` (a factory name or the test-only 'vit_micro') with seeded synthetic weights on `device`."""
     cfg = cfg or Config()
+    if name in synth.SWIN_CONFIGS:
+        c = synth.SWIN_CONFIGS[name]
+        if name == "swin_micro":
+            model = SwinTransformer(patch_size=4, window_size=7, embed_dim=c["embed_dim"], depths=c["depths"], num_heads=c["num_heads"],
+                                    norm_layer=QIntLayerNorm, input_quant=True, cfg=cfg)
+        else:
+            model = str2model(name)(pretrained=False, cfg=cfg)
+        sd = synth.synth_swin_state_dict(**c, seed=seed)
+        res = model.load_state_dict({k: v for k, v in sd.items() if not k.endswith("reduction.bias")}, strict=False)
+        assert not res.unexpected_keys and all("relative_position_index" in k or "attn_mask" in k for k in res.missing_keys), res
+        return model.to(device).eval()
     c = synth.VIT_CONFIGS[name]
     if name == "vit_micro":
         model = VisionTransformer(patch_size=16, embed_dim=c["embed_dim"], depth=c["depth"], num_heads=c["num_heads"], mlp_ratio=4,

@@ -259,7 +259,85 @@ class Block(nn.Module):
 _Q_TYPES = (QConv2d, QLinear, QAct, QIntSoftmax)
 
 
-class VisionTransformer(nn.Module):
+class QuantModelMixin:
+    """flag protocol and calibrated-state exchange shared by the ViT and Swin model classes"""
+
+    # ---- flag protocol (vit_fquant.py:797-828)
+    def model_quant(self, flag="on"):
+        if flag == "on":
+            self.quant = True
+        for m in self.modules():
+            if type(m) in _Q_TYPES:
+                m.quant = True
+            if self.cfg.INT_NORM and type(m) is QIntLayerNorm and flag != "off":
+                m.mode = "int"
+        self._engine = None
+
+    def model_dequant(self):
+        self.quant = False
+        for m in self.modules():
+            if type(m) in _Q_TYPES:
+                m.quant = False
+            if type(m) is QIntLayerNorm:
+                m.mode = "ln"
+
+    def model_open_calibrate(self):
+        for m in self.modules():
+            if type(m) in _Q_TYPES:
+                m.calibrate = True
+
+    def model_open_last_calibrate(self):
+        for m in self.modules():
+            if type(m) in _Q_TYPES:
+                m.last_calibrate = True
+
+    def model_close_calibrate(self):
+        for m in self.modules():
+            if type(m) in _Q_TYPES:
+                m.calibrate = False
+
+    # ---- calibrated state exchange (names = module paths; shared with oracle/ and tests/golden)
+    def export_quant_state(self):
+        st = {}
+        for name, m in self.named_modules():
+            if isinstance(m, QAct) and m.quantizer.scale is not None:
+                st[name + ".scale"] = m.quantizer.scale.detach().reshape(-1).float().cpu()
+                st[name + ".zero_point"] = m.quantizer.zero_point.detach().reshape(-1).long().cpu()
+            elif isinstance(m, (QLinear, QConv2d)):
+                for bit, s in m.quantizer.dic_scale.items():
+                    st["%s.scale.%s" % (name, bit)] = s.detach().reshape(-1).float().cpu()
+                    st["%s.zero_point.%s" % (name, bit)] = m.quantizer.dic_zero_point[bit].detach().reshape(-1).long().cpu()
+            if isinstance(m, _SmoothedLinear) and m.channel_scale is not None:
+                st[name + ".channel_scale"] = m.channel_scale.detach().float().cpu()
+        return st
+
+    def load_quant_state(self, st):
+        dev = next(self.parameters()).device
+        t = lambda v, dt: torch.as_tensor(v).to(device=dev, dtype=dt)
+        for name, m in self.named_modules():
+            if isinstance(m, QAct) and (name + ".scale") in st:
+                m.quantizer.scale = t(st[name + ".scale"], torch.float32)
+                m.quantizer.zero_point = t(st[name + ".zero_point"], torch.int64)
+            elif isinstance(m, (QLinear, QConv2d)):
+                for bit in ("uint3", "uint4", "int4", "int8"):
+                    k = "%s.scale.%s" % (name, bit)
+                    if k in st:
+                        m.quantizer.dic_scale[bit] = t(st[k], torch.float32)
+                        m.quantizer.dic_zero_point[bit] = t(st["%s.zero_point.%s" % (name, bit)], torch.int64)
+        for name, m in self.named_modules():   # second pass: the children's quantizers are filled now
+            if isinstance(m, _SmoothedLinear) and (name + ".channel_scale") in st:
+                cs = t(st[name + ".channel_scale"], torch.float32)
+                lin, qa = (m.qkv, m.qact0) if hasattr(m, "qkv") else (m.fc1, m.qact0)
+                m.channel_scale = cs
+                m.best_scale = [cs, cs]
+                m.best_act_scale = [qa.quantizer.scale] * 2
+                m.best_act_zp = [qa.quantizer.zero_point] * 2
+                m.best_weight_scale = [lin.quantizer.dic_scale] * 2
+                m.best_weight_zp = [lin.quantizer.dic_zero_point] * 2
+        self._engine = None
+
+
+class VisionTransformer(nn.Module, QuantModelMixin):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
                  mlp_ratio=4.0, qkv_bias=True, qk_scale=None, representation_size=None, drop_rate=0.0, attn_drop_rate=0.0,
                  drop_path_rate=0.0, hybrid_backbone=None, norm_layer=None, quant=False, calibrate=False, input_quant=False,
@@ -315,40 +393,6 @@ class VisionTransformer(nn.Module):
     def get_classifier(self):
         return self.head
 
-    # ---- flag protocol (vit_fquant.py:797-828)
-    def model_quant(self, flag="on"):
-        if flag == "on":
-            self.quant = True
-        for m in self.modules():
-            if type(m) in _Q_TYPES:
-                m.quant = True
-            if self.cfg.INT_NORM and type(m) is QIntLayerNorm and flag != "off":
-                m.mode = "int"
-        self._engine = None
-
-    def model_dequant(self):
-        self.quant = False
-        for m in self.modules():
-            if type(m) in _Q_TYPES:
-                m.quant = False
-            if type(m) is QIntLayerNorm:
-                m.mode = "ln"
-
-    def model_open_calibrate(self):
-        for m in self.modules():
-            if type(m) in _Q_TYPES:
-                m.calibrate = True
-
-    def model_open_last_calibrate(self):
-        for m in self.modules():
-            if type(m) in _Q_TYPES:
-                m.last_calibrate = True
-
-    def model_close_calibrate(self):
-        for m in self.modules():
-            if type(m) in _Q_TYPES:
-                m.calibrate = False
-
     # ---- module-by-module forward (calibration, FP, eager quantized)
     def forward_features(self, x, FLOPs, global_distance, bit_config, global_plot, hessian_statistic=False):
         B = x.shape[0]
@@ -396,45 +440,6 @@ class VisionTransformer(nn.Module):
             self._engine = VitEngine(self)
         return self._engine(x, bit_config), self.flops_list(), []
 
-    # ---- calibrated state exchange (names = module paths; shared with oracle/ and tests/golden)
-    def export_quant_state(self):
-        st = {}
-        for name, m in self.named_modules():
-            if isinstance(m, QAct) and m.quantizer.scale is not None:
-                st[name + ".scale"] = m.quantizer.scale.detach().reshape(-1).float().cpu()
-                st[name + ".zero_point"] = m.quantizer.zero_point.detach().reshape(-1).long().cpu()
-            elif isinstance(m, (QLinear, QConv2d)):
-                for bit, s in m.quantizer.dic_scale.items():
-                    st["%s.scale.%s" % (name, bit)] = s.detach().reshape(-1).float().cpu()
-                    st["%s.zero_point.%s" % (name, bit)] = m.quantizer.dic_zero_point[bit].detach().reshape(-1).long().cpu()
-            if isinstance(m, (Attention, Mlp)) and m.channel_scale is not None:
-                st[name + ".channel_scale"] = m.channel_scale.detach().float().cpu()
-        return st
-
-    def load_quant_state(self, st):
-        dev = self.cls_token.device
-        t = lambda v, dt: torch.as_tensor(v).to(device=dev, dtype=dt)
-        for name, m in self.named_modules():
-            if isinstance(m, QAct) and (name + ".scale") in st:
-                m.quantizer.scale = t(st[name + ".scale"], torch.float32)
-                m.quantizer.zero_point = t(st[name + ".zero_point"], torch.int64)
-            elif isinstance(m, (QLinear, QConv2d)):
-                for bit in ("uint3", "uint4", "int4", "int8"):
-                    k = "%s.scale.%s" % (name, bit)
-                    if k in st:
-                        m.quantizer.dic_scale[bit] = t(st[k], torch.float32)
-                        m.quantizer.dic_zero_point[bit] = t(st["%s.zero_point.%s" % (name, bit)], torch.int64)
-        for name, m in self.named_modules():   # second pass: the children's quantizers are filled now
-            if isinstance(m, (Attention, Mlp)) and (name + ".channel_scale") in st:
-                cs = t(st[name + ".channel_scale"], torch.float32)
-                lin, qa = (m.qkv, m.qact0) if isinstance(m, Attention) else (m.fc1, m.qact0)
-                m.channel_scale = cs
-                m.best_scale = [cs, cs]
-                m.best_act_scale = [qa.quantizer.scale] * 2
-                m.best_act_zp = [qa.quantizer.zero_point] * 2
-                m.best_weight_scale = [lin.quantizer.dic_scale] * 2
-                m.best_weight_zp = [lin.quantizer.dic_zero_point] * 2
-        self._engine = None
 
 
 def _vit(embed_dim, depth, num_heads, input_quant, quant, calibrate, cfg, **kwargs):
