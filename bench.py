@@ -30,7 +30,12 @@ from p2vit_b200 import synth  # noqa: E402
 # MACs per image = L*(12*N*D^2 + 2*N^2*D) + 196*768*D + 1000*D
 
 
+SWIN_GMAC = {"swin_tiny": 4.4906e9, "swin_micro": None}
+
+
 def macs_per_image(name):
+    if name in synth.SWIN_CONFIGS:
+        return SWIN_GMAC.get(name) or 0.0
     c = synth.VIT_CONFIGS[name]
     D, L, N = c["embed_dim"], c["depth"], 197
     return L * (12 * N * D * D + 2 * N * N * D) + 196 * 768 * D + 1000 * D
@@ -171,6 +176,9 @@ def main():
     from p2vit_b200 import Config, build_model, calibrate_model, ops
     from p2vit_b200.engine import VitEngine
     from p2vit_b200.runner import shard_range
+    from p2vit_b200.swin_engine import SwinEngine
+
+    is_swin = args.model in synth.SWIN_CONFIGS
 
     model = build_model(args.model, Config(True, True, "minmax"), seed=0, device=dev)
     t0 = time.time()
@@ -184,13 +192,23 @@ def main():
         calibrate_model(model, synth.synth_images(e - s, seed=0, start=s).to(dev))
         calib_src = "calibrated on the GPU(s) from %d synthetic images" % args.calib
     calib_s = time.time() - t0
-    bits = make_bit_config(args.bits, model)
     B = args.batch
-    eng = VitEngine(model, use_graph=True)
+    if is_swin:
+        bits = [8]
+        eng = SwinEngine(model, use_graph=True)
+        eng_input = lambda: eng.static_input(B)
+        eng_run = lambda: eng.run_static(B)
+        eng_prog = lambda: eng._program(B)
+    else:
+        bits = make_bit_config(args.bits, model)
+        eng = VitEngine(model, use_graph=True)
+        eng_input = lambda: eng.static_input(B, bits)
+        eng_run = lambda: eng.run_static(B, bits)
+        eng_prog = lambda: eng._program(tuple(bits), B)
     model._engine = eng
     host = synth.synth_images(min(B, 64), seed=1, start=rank * B)
     host = host.repeat((B + host.shape[0] - 1) // host.shape[0], 1, 1, 1)[:B].contiguous().pin_memory()
-    img = eng.static_input(B, bits)
+    img = eng_input()
     img.copy_(host, non_blocking=True)
     torch.cuda.synchronize()
 
@@ -201,7 +219,7 @@ def main():
 
     # ---------------- value: inputs resident in HBM, CUDA-graph replay of the whole forward
     for _ in range(args.warmup):
-        eng.run_static(B, bits)
+        eng_run()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -209,7 +227,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        eng.run_static(B, bits)
+        eng_run()
     ev1.record()
     barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
@@ -256,10 +274,29 @@ def main():
     sampler.stop_flag = True
 
     # ---------------- per-kernel-family device time (eager launches, CUDA events on the launching stream)
-    prog = eng._program(tuple(bits), B)
+    prog = eng_prog()
     fam_ms, fam_n = {}, {}
 
     def family(step):
+        if is_swin:
+            parts = step.split(".")
+            tail2 = ".".join(parts[-2:])
+            if step == "patchify" or parts[-1] == "gather" or step == "qact3":
+                return "remap"
+            if tail2 == "attn.qact3":
+                return "attention"
+            if step in ("patch_embed.qact", "qact2") or tail2 in ("mlp.qact0", "downsample.qact1") or \
+                    (parts[-1] == "qact1" and len(parts) >= 2 and parts[-2].isdigit()):
+                return "layernorm"
+            if tail2 == "attn.qact1":
+                return "gemm_qkv"
+            if tail2 == "mlp.qact1":
+                return "gemm_fc1"
+            if parts[-1] == "qact2" and len(parts) >= 2 and parts[-2].isdigit():
+                return "gemm_proj"
+            if parts[-1] == "qact4":
+                return "gemm_fc2"
+            return "gemm_other"
         if step in ("patchify", "cls"):
             return step
         if "norm" in step or step == "qact2" and "blocks" not in step:
@@ -298,19 +335,24 @@ def main():
     value = total_imgs / (ms_value * 1e-3)
     e2e = total_imgs / (ms_e2e * 1e-3)
     macs = macs_per_image(args.model)
-    c = synth.VIT_CONFIGS[args.model]
-    D, L, T1 = c["embed_dim"], c["depth"], 197
+    if is_swin:
+        D, L, T1 = 0, 0, 0
+    else:
+        c = synth.VIT_CONFIGS[args.model]
+        D, L, T1 = c["embed_dim"], c["depth"], 197
     top = max(fam_ms, key=fam_ms.get)
     share = {k: round(v / sum(fam_ms.values()), 4) for k, v in fam_ms.items()}
     if top == "gemm":
-        lin_macs = L * 12 * T1 * D * D + 196 * 768 * D + 1000 * D
+        lin_macs = 4.3504e9 if is_swin else L * 12 * T1 * D * D + 196 * 768 * D + 1000 * D     # Swin-T linear part: SURVEY 8(d)
         ach = 2.0 * lin_macs * B / (fam_ms["gemm"] * 1e-3) / 1e12
         peak = 2.0 * bf16_tf_sus
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (all %d launches of a step)" % fam_n["gemm"], "achieved": ach, "peak": peak,
                 "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "note": "int8 ops; peak = 2 x %s sustained bf16 cuBLAS (%.0f TF) since MEASURED_PEAKS has no int8 figure (nominal int8 dense 4500)" % (peak_src, bf16_tf_sus)}
     else:
-        if top == "attention":
+        if is_swin:
+            by = B * 56 * 56 * 96 * 4 * 6               # qkv codes in + attention codes out: 4*tokens*C bytes per block, ~constant per stage pair
+        elif top == "attention":
             by = L * B * (T1 * 3 * D + T1 * D)          # qkv codes in, attention codes out
         elif top == "layernorm":
             by = (2 * L) * B * T1 * D * 2
@@ -326,9 +368,22 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        ips, spstep, cores, _, ref_logits = cpu_reference_run(args.model, 8, 2, 1)
-        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-               "sample": "oracle/port.py (reference algorithm, torch CPU fp32 fake-quant) forward, batch 8 x 2 steps"}
+        if is_swin:
+            from oracle.swin_port import SwinOracle
+            torch.set_num_threads(os.cpu_count())
+            cs = synth.SWIN_CONFIGS[args.model]
+            o = SwinOracle(synth.synth_swin_state_dict(**cs, seed=0), **cs)
+            o.load_state({k: v.numpy() for k, v in model.export_quant_state().items()})
+            xs = synth.synth_images(4, seed=1)
+            o.forward_quant(xs)
+            t0 = time.time()
+            o.forward_quant(xs)
+            cpu = {"value": 4 / (time.time() - t0), "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": "oracle/swin_port.py (reference algorithm, torch CPU fp32 fake-quant) forward, batch 4 x 1 step, GPU-calibrated state"}
+        else:
+            ips, spstep, cores, _, ref_logits = cpu_reference_run(args.model, 8, 2, 1)
+            cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                   "sample": "oracle/port.py (reference algorithm, torch CPU fp32 fake-quant) forward, batch 8 x 2 steps"}
 
     line = {"metric": "images/sec (224^2, int8 PoT)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -338,7 +393,7 @@ def main():
                        "parallelism": "dp%d (batch sharded, no collective in the forward)" % world, "cuda_graph": True},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 * world, "d2h_bytes_per_step": B * 1000 * 4 * world,
                     "ms_per_step": ms_e2e / args.steps, "path": "pinned host fp32 images -> H2D (copy stream, double buffered) -> model(x, bit_config) -> logits D2H"},
-            "gpu_launches": eng.launches_per_forward(bits) * args.steps,
+            "gpu_launches": (eng.launches_per_forward() if is_swin else eng.launches_per_forward(bits)) * args.steps,
             "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
