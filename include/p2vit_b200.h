@@ -90,11 +90,25 @@ typedef struct {
   int tokens_per_image;     /* EMBED: T (196) */
   int8_t* out_i8;           /* [M,N] (EMBED: [B*(T+1),N]) */
   float* out_f32;           /* [M,N] DEQUANT / F32 */
+  const void* gelu_table;   /* GELU with pot_scales: optional p2v_gelu_table (device) built by p2v_build_gelu_table for this
+                               out_scale; NULL = evaluate erf per element */
   const int32_t* row_map;   /* [M] or NULL (REQUANT/GELU/RESIDUAL): output row (and residual row) of GEMM row m - Swin window
                                reverse + inverse cyclic shift fused into the store (swin_quant.py:426-436) */
   int pot_scales;           /* REQUANT/GELU/DEQUANT: 1 = acc_scale and out_scale are exact powers of two (division == exact
                                multiply); RESIDUAL: 1 = acc_scale is (acc*acc_scale exact; mid/out scales stay general) */
 } p2v_gemm_args;
+
+/* Step table of  y -> sat(RNE(gelu_erf(y) / out_scale))  for a power-of-two out_scale (layers_quant.py:373-375).  The
+ * code is piecewise constant in y; the table cuts [-8.5, 128*out_scale + 0.5) into segments of width out_scale/2 (at most
+ * one code change each) and stores the code below / above the change and the exact fp32 threshold, found by bisection on
+ * the kernels' own gelu_erf.  The epilogue looks the code up and re-evaluates erf only for y within 8 ulps of a threshold
+ * (and for the rare segments flagged non-monotone), so its result is identical to the direct evaluation.
+ * Layout: header {float y0, inv_w; int32 n, reserved} then n entries {float threshold; uint32 below | above<<8 | slow<<31}. */
+#define P2V_GELU_TABLE_MAX_ENTRIES 4096
+#define P2V_GELU_TABLE_BYTES (16 + 8 * P2V_GELU_TABLE_MAX_ENTRIES)
+/* returns 0 and fills `table_dev` (P2V_GELU_TABLE_BYTES bytes), or 3 if out_scale needs more than the maximum number of
+ * entries / is not a power of two (the caller then passes gelu_table = NULL) */
+int p2v_build_gelu_table(float out_scale, void* table_dev, void* stream);
 
 int p2v_gemm_i8(const p2v_gemm_args* args_host, void* stream);
 /* same contract on CUDA cores (dp4a); used by tests to cross-check the tcgen05 kernel */

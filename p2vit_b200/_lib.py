@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libp2vit_b200.so")
 
 EPI_REQUANT, EPI_GELU, EPI_RESIDUAL, EPI_EMBED, EPI_DEQUANT, EPI_F32 = range(6)
+GELU_TABLE_BYTES = 16 + 8 * 4096
 
 
 class GemmArgs(C.Structure):
@@ -24,7 +25,7 @@ class GemmArgs(C.Structure):
         ("res", C.c_void_p), ("pos", C.c_void_p),
         ("aux_scale", C.c_float), ("tokens_per_image", C.c_int),
         ("out_i8", C.c_void_p), ("out_f32", C.c_void_p),
-        ("row_map", C.c_void_p),
+        ("gelu_table", C.c_void_p), ("row_map", C.c_void_p),
         ("pot_scales", C.c_int),
     ]
 
@@ -73,6 +74,7 @@ SYMBOLS = {
     "p2v_fake_quant_f32": (_I, [_P, _P, _P, _I64, _I, _I64, _P, _I, _F, _I, _I, _P]),
     "p2v_dequantize_i8": (_I, [_P, _P, _I64, _I, _I64, _P, _I, _F, _P]),
     "p2v_quantize_patchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _I, _I, _P]),
+    "p2v_build_gelu_table": (_I, [_F, _P, _P]),
     "p2v_gemm_i8": (_I, [C.POINTER(GemmArgs), _P]),
     "p2v_gemm_i8_simt": (_I, [C.POINTER(GemmArgs), _P]),
     "p2v_fill_cls_rows": (_I, [_P, _P, _I, _I, _I, _P]),

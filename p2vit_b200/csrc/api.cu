@@ -27,6 +27,7 @@ int check_launch(const char* what) {
 }
 
 int launch_gemm_simt(const p2v_gemm_args& a, cudaStream_t stream);
+int launch_build_gelu_table(float out_scale, void* table_dev, cudaStream_t stream);
 int launch_gemm_tc(const p2v_gemm_args& a, cudaStream_t stream);
 int launch_quantize(const float* x, int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale,
                     float zp, int lo, int hi, cudaStream_t stream);
@@ -98,6 +99,10 @@ int p2v_quantize_patchify(const float* img, int8_t* out, int B, int Cin, int H, 
   P2V_REQUIRE(P % 4 == 0 && W % 4 == 0, "patchify: P and W must be multiples of 4");
   P2V_REQUIRE(lo >= -128 && hi <= 127, "patchify: int8 carrier only");
   return launch_patchify(img, out, B, Cin, H, W, P, scale, zp, lo, hi, (cudaStream_t)stream);
+}
+int p2v_build_gelu_table(float out_scale, void* table_dev, void* stream) {
+  P2V_REQUIRE(table_dev != nullptr && (reinterpret_cast<uintptr_t>(table_dev) & 15) == 0, "build_gelu_table: table must be 16-byte aligned");
+  return launch_build_gelu_table(out_scale, table_dev, (cudaStream_t)stream);
 }
 int p2v_gemm_i8(const p2v_gemm_args* a, void* stream) {
   if (int r = validate_gemm(a)) return r;

@@ -53,6 +53,23 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmul(fmul(x, 0.5f), fadd(1.0f, e));
 }
 
+// ---- GELU step table (include/p2vit_b200.h: p2v_build_gelu_table)
+struct GeluTabHeader { float y0, inv_w; int n, reserved; };
+struct GeluTab { const uint2* entries; int n; float inv_w, off; };   // entries may live in shared or global memory
+// the reference arithmetic: qact1(gelu(y)) for a power-of-two output scale (ro = 1/out_scale)
+__device__ __forceinline__ int gelu_code_direct(float y, float ro) { return sat_s8(fmul(gelu_erf(y), ro)); }
+// segment of y; the SAME expression builds the table and looks it up, so its own rounding is immaterial
+__device__ __forceinline__ int gelu_segment(float y, float inv_w, float off, int n) {
+  return min(max(__float2int_rd(__fmaf_rn(y, inv_w, off)), 0), n - 1);
+}
+// code of y from its table entry; `slow` is raised when y is within 8 ulps of the entry's threshold or the entry is flagged
+__device__ __forceinline__ int gelu_code_table(float y, uint2 e, bool& slow) {
+  const int d = __float_as_int(y) - int(e.x);
+  slow |= (unsigned(d + 8) <= 16u) | (int(e.y) < 0);
+  const uint32_t sel = y >= __uint_as_float(e.x) ? 0x9991u : 0x8880u;     // prmt selectors: sign-extended byte 1 / byte 0
+  return int(__byte_perm(e.y, 0u, sel));
+}
+
 // floor(log2(|a|)) for finite non-zero a (normal or subnormal)
 __device__ __forceinline__ int ilog2f(float a) {
   uint32_t u = __float_as_uint(a) & 0x7fffffffu;

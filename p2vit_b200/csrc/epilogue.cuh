@@ -9,6 +9,7 @@
 // when the quotient is within 1e-3 of a rounding tie - the result is always identical to
 // rint(__fdiv_rn(y, s)) (see DESIGN.md "exact fast requantisation").
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 namespace p2v {
@@ -28,6 +29,8 @@ struct EpiParams {  // device-side copy of p2v_gemm_args (pointers only)
   int tokens_per_image;
   int8_t* out_i8;
   float* out_f32;
+  const void* gelu_table;   // device p2v_gelu_table or NULL
+  int dbg;   // P2V_DBG experiments (perf triage only): bit 0 = skip the global stores, bit 1 = skip residual loads
 };
 
 inline EpiParams make_epi_params(const p2v_gemm_args& a) {
@@ -36,8 +39,11 @@ inline EpiParams make_epi_params(const p2v_gemm_args& a) {
   p.acc_scale = a.acc_scale; p.bias = a.bias; p.zp_corr = a.zp_corr; p.out_scale = a.out_scale;
   p.mid_scale = a.mid_scale; p.res_scale = a.res_scale; p.res = a.res; p.pos = a.pos;
   p.row_map = a.row_map;
+  p.gelu_table = a.gelu_table;
   p.aux_scale = a.aux_scale; p.tokens_per_image = a.tokens_per_image;
   p.out_i8 = a.out_i8; p.out_f32 = a.out_f32;
+  static const int dbg = getenv("P2V_DBG") ? atoi(getenv("P2V_DBG")) : 0;
+  p.dbg = dbg;
   return p;
 }
 
@@ -103,7 +109,7 @@ __device__ __forceinline__ void stage_col_params(const EpiParams& p, float* cp, 
 // Epilogue arithmetic for columns [col0, col0+NC) of one row; EXACT = false is the branch-free fast pass.
 template <int EPI, bool POT, int BN, int NC, bool EXACT>
 __device__ __forceinline__ void epilogue_math(const EpiParams& p, const float* cp, int row, int col0, int c0, const int (&acc)[NC],
-                                              const uint32_t (&resw)[NC / 4], int (&q)[NC], float (&f)[NC], bool& slow) {
+                                              const uint32_t (&resw)[NC / 4], int (&q)[NC], float (&f)[NC], bool& slow, const GeluTab& gt) {
   const int N = p.N;
   const bool has_zp = p.zp_corr != nullptr;
   float e_sm = 0.f, e_rsm = 0.f, e_raux = 0.f;
@@ -155,8 +161,12 @@ __device__ __forceinline__ void epilogue_math(const EpiParams& p, const float* c
         q[j] = int(k);
         f[j] = fmul(k, Ov[e]);
       } else if (EPI == P2V_EPI_GELU) {
-        const float g = gelu_erf(y);
-        q[j] = POT ? sat_s8(fmul(g, Rv[e])) : quant_div_s8<EXACT>(g, Ov[e], Rv[e], slow);
+        if (POT && !EXACT && gt.entries != nullptr) {
+          q[j] = gelu_code_table(y, gt.entries[gelu_segment(y, gt.inv_w, gt.off, gt.n)], slow);
+        } else {
+          const float g = gelu_erf(y);
+          q[j] = POT ? sat_s8(fmul(g, Rv[e])) : quant_div_s8<EXACT>(g, Ov[e], Rv[e], slow);
+        }
       } else if (EPI == P2V_EPI_RESIDUAL) {
         const float c = quant_div<EXACT>(y, Mv[e], RMv[e], slow);
         const float t = fmul(c, Mv[e]);
@@ -180,7 +190,7 @@ __device__ __forceinline__ void epilogue_math(const EpiParams& p, const float* c
 template <int NC>
 __device__ __forceinline__ void load_residual(const EpiParams& p, int row, int col0, uint32_t (&resw)[NC / 4]) {
   const int N = p.N;
-  if (row >= p.M || col0 >= N) {
+  if (row >= p.M || col0 >= N || (p.dbg & 2)) {
 #pragma unroll
     for (int j = 0; j < NC / 4; ++j) resw[j] = 0u;
     return;
@@ -209,7 +219,7 @@ __device__ __forceinline__ void load_residual(const EpiParams& p, int row, int c
 // in-flight tcgen05.ld; the wait sits right before the first use.  `resw`: load_residual() of the same span.
 template <int EPI, bool POT, int BN, int NC, bool TMEM_WAIT = false>
 __device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp, int row, int n0, int c0, const int (&acc)[NC],
-                                             const uint32_t (&resw)[NC / 4]) {
+                                             const uint32_t (&resw)[NC / 4], const GeluTab& gt) {
   const int N = p.N;
   const int col0 = n0 + c0;
   int q[NC];
@@ -217,8 +227,8 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp
   if (TMEM_WAIT) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   if (row >= p.M) return;
   bool slow = false;
-  epilogue_math<EPI, POT, BN, NC, false>(p, cp, row, col0, c0, acc, resw, q, f, slow);
-  if (slow) epilogue_math<EPI, POT, BN, NC, true>(p, cp, row, col0, c0, acc, resw, q, f, slow);
+  epilogue_math<EPI, POT, BN, NC, false>(p, cp, row, col0, c0, acc, resw, q, f, slow, gt);
+  if (slow) epilogue_math<EPI, POT, BN, NC, true>(p, cp, row, col0, c0, acc, resw, q, f, slow, gt);
   size_t orow = size_t(p.row_map ? __ldg(p.row_map + row) : row);
   if (EPI == P2V_EPI_EMBED) {
     const int T = p.tokens_per_image;
@@ -235,6 +245,7 @@ __device__ __forceinline__ void epilogue_row(const EpiParams& p, const float* cp
     }
     if (EPI == P2V_EPI_F32 || p.out_i8 == nullptr) return;
   }
+  if (p.dbg & 1) { if (q[0] == 12345) p.out_i8[0] = 1; return; }
   int8_t* o8 = p.out_i8 + orow * N + col0;
   if ((N & 15) == 0 && (NC & 15) == 0 && col0 + NC <= N) {
 #pragma unroll

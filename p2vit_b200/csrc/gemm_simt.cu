@@ -39,7 +39,13 @@ __global__ void __launch_bounds__(SIMT_THREADS) gemm_simt_kernel(const int8_t* _
   }
   uint32_t resw[SIMT_NC / 4];
   if (EPI == P2V_EPI_RESIDUAL) load_residual<SIMT_NC>(p, row, col0, resw);
-  epilogue_row<EPI, POT, 64, SIMT_NC>(p, cp, row, n0, c0, acc, resw);
+  GeluTab gt{nullptr, 0, 0.f, 0.f};
+  if (EPI == P2V_EPI_GELU && POT && p.gelu_table) {
+    const GeluTabHeader hd = *reinterpret_cast<const GeluTabHeader*>(p.gelu_table);
+    gt = GeluTab{reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(p.gelu_table) + sizeof(GeluTabHeader)), hd.n, hd.inv_w,
+                 -hd.y0 * hd.inv_w};
+  }
+  epilogue_row<EPI, POT, 64, SIMT_NC>(p, cp, row, n0, c0, acc, resw, gt);
 }
 
 int launch_gemm_simt(const p2v_gemm_args& a, cudaStream_t stream) {

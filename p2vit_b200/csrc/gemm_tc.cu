@@ -28,7 +28,7 @@ constexpr int TC_THREADS = 64 + TC_GROUPS * 128;
 
 __device__ __forceinline__ void group_barrier(uint32_t id) { named_barrier(id, 128); }
 
-template <int BN, int STAGES, int EPI, bool POT>
+template <int BN, int STAGES, int EPI, bool POT, bool GTAB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p, int tiles_m, int tiles_n) {
   constexpr uint32_t A_BYTES = BM * BK, B_BYTES = BN * BK, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -54,6 +54,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     tmem_alloc<TMEM_COLS>(smem_u32(&tmem_slot));
+  }
+  GeluTab gt{nullptr, 0, 0.f, 0.f};
+  if (GTAB) {   // the step table of qact1(gelu(.)) moves to shared memory behind the operand ring
+    const GeluTabHeader hd = *reinterpret_cast<const GeluTabHeader*>(p.gelu_table);
+    uint2* s_tab = reinterpret_cast<uint2*>(smem_raw + (stage0 - smem_u32(smem_raw)) + STAGES * STAGE_BYTES);
+    const uint2* src = reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(p.gelu_table) + sizeof(GeluTabHeader));
+    for (int i = threadIdx.x; i < hd.n; i += TC_THREADS) s_tab[i] = __ldg(src + i);
+    gt = GeluTab{s_tab, hd.n, hd.inv_w, -hd.y0 * hd.inv_w};
   }
   tc_fence_before();
   __syncthreads();
@@ -130,7 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (NCH == 32) tmem_ld32_async(taddr + c * NCH, reinterpret_cast<int(&)[32]>(acc[0]));
         else tmem_ld16_async(taddr + c * NCH, reinterpret_cast<int(&)[16]>(acc[0]));
         if (EPI == P2V_EPI_RESIDUAL && c + 1 < BN / NCH) load_residual<NCH>(p, row, n0 + (c + 1) * NCH, res_next);
-        epilogue_row<EPI, POT, BN, NCH, true>(p, cp, row, n0, c * NCH, acc, res_cur);
+        epilogue_row<EPI, POT, BN, NCH, true>(p, cp, row, n0, c * NCH, acc, res_cur, gt);
       }
       tc_fence_before();
       __syncwarp();
@@ -173,7 +181,7 @@ int make_tmap_i8(CUtensorMap* m, const void* ptr, int rows, int cols, int box_ro
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool GTAB>
 static int launch_tc_bn(const p2v_gemm_args& a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   if (int r = make_tmap_i8(&tmA, a.A, a.M, a.K, BM)) return r;
@@ -184,24 +192,32 @@ static int launch_tc_bn(const p2v_gemm_args& a, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(tiles_m * tiles_n, sms);
-  constexpr size_t smem = size_t(STAGES) * (BM * BK + BN * BK) + 1024;
-  P2V_DISPATCH_EPI(a.epilogue, a.pot_scales != 0, {
-    auto kern = gemm_tc_kernel<BN, STAGES, EPI, POT>;
-    static bool attr = false;
-    if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      P2V_REQUIRE(e == cudaSuccess, "gemm_tc: cannot set %zu bytes of dynamic shared memory: %s", smem, cudaGetErrorString(e));
-      attr = true;
-    }
-    kern<<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, p, tiles_m, tiles_n);
-  });
+  constexpr size_t smem = size_t(STAGES) * (BM * BK + BN * BK) + 1024 + (GTAB ? 8 * P2V_GELU_TABLE_MAX_ENTRIES : 0);
+#define P2V_TC_LAUNCH(EPI_, POT_)                                                                                          \
+  {                                                                                                                        \
+    auto kern = gemm_tc_kernel<BN, STAGES, EPI_, POT_, GTAB>;                                                              \
+    static bool attr = false;                                                                                              \
+    if (!attr) {                                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));                  \
+      P2V_REQUIRE(e == cudaSuccess, "gemm_tc: cannot set %zu bytes of dynamic shared memory: %s", smem, cudaGetErrorString(e)); \
+      attr = true;                                                                                                         \
+    }                                                                                                                      \
+    kern<<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, p, tiles_m, tiles_n);                                               \
+  }
+  if (GTAB) {
+    P2V_TC_LAUNCH(P2V_EPI_GELU, true)
+  } else {
+    P2V_DISPATCH_EPI(a.epilogue, a.pot_scales != 0, P2V_TC_LAUNCH(EPI, POT));
+  }
+#undef P2V_TC_LAUNCH
   count_launch();
   return check_launch("gemm_tc");
 }
 
 int launch_gemm_tc(const p2v_gemm_args& a, cudaStream_t stream) {
-  // BN = 128: 32 KB / smem stage, 5 stages, 4 x 128 TMEM columns
-  return launch_tc_bn<128, 5>(a, stream);
+  // BN = 128: 32 KB / smem stage, 4 x 128 TMEM columns; 5 stages, or 4 stages + the 32 KB GELU step table
+  if (a.epilogue == P2V_EPI_GELU && a.pot_scales && a.gelu_table) return launch_tc_bn<128, 4, true>(a, stream);
+  return launch_tc_bn<128, 5, false>(a, stream);
 }
 
 }  // namespace p2v

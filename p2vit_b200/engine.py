@@ -124,6 +124,7 @@ class VitPlan:
             p["fc1"] = _Gemm(mlp.fc1, mlp.fc1.weight * cs_m.reshape(1, -1), b4[2], m0, dev)
             p["fc1_out"] = _vec(m1, p["fc1"].N, dev)
             p["fc1_pot"] = intmath.is_pot(m1)
+            p["gelu_tab"] = ops.gelu_table(float(m1), dev) if p["fc1_pot"] else None
             p["fc2"] = _Gemm(mlp.fc2, mlp.fc2.weight, b4[3], m1, dev)
             p["fc2_mid"] = _vec(_sym_scale(mlp.qact2, "mlp.qact2"), D, dev)
             s_b4 = _vec(_sym_scale(blk.qact4, "block.qact4"), D, dev)
@@ -209,7 +210,7 @@ class VitEngine:
             steps.append((pre + "norm2", self._ln(p["ln2"], ws["rb"], R, D, D, ws["ln"])))
             g = p["fc1"]
             steps.append((pre + "mlp.qact1", self._gemm(ops.gemm_args(ws["ln"], g.W, ops.EPI_GELU, g.acc_scale, bias=g.bias,
-                                                                      out_scale=p["fc1_out"], out_i8=ws["hid"], pot=p["fc1_pot"]))))
+                                                                      out_scale=p["fc1_out"], out_i8=ws["hid"], pot=p["fc1_pot"], gelu_table=p["gelu_tab"]))))
             g = p["fc2"]
             steps.append((pre + "qact4", self._gemm(ops.gemm_args(ws["hid"], g.W, ops.EPI_RESIDUAL, g.acc_scale, bias=g.bias,
                                                                   out_scale=p["fc2_out"], mid_scale=p["fc2_mid"],

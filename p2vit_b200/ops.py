@@ -66,7 +66,7 @@ def quantize_patchify(img, patch, scale, zero_point=0.0, lo=-128, hi=127, out=No
 
 
 def gemm_args(A, W, epilogue, acc_scale, bias=None, out_scale=None, mid_scale=None, res_scale=None, res=None, pos=None,
-              aux_scale=0.0, tokens_per_image=0, out_i8=None, out_f32=None, pot=False, zp_corr=None, row_map=None):
+              aux_scale=0.0, tokens_per_image=0, out_i8=None, out_f32=None, pot=False, zp_corr=None, row_map=None, gelu_table=None):
     M, K = A.shape
     N = W.shape[0]
     assert W.shape[1] == K
@@ -80,8 +80,25 @@ def gemm_args(A, W, epilogue, acc_scale, bias=None, out_scale=None, mid_scale=No
     a.aux_scale, a.tokens_per_image = float(aux_scale), int(tokens_per_image)
     a.out_i8, a.out_f32 = ptr(out_i8), ptr(out_f32)
     a.row_map = ptr(row_map)
+    a.gelu_table = ptr(gelu_table)
     a.pot_scales = 1 if pot else 0
     return a
+
+
+_gelu_tables = {}
+
+
+def gelu_table(out_scale, device):
+    """device-resident step table of y -> qact(gelu(y)) for a power-of-two output scale (None if the scale is not tabulable);
+    cached per (scale, device)"""
+    key = (float(out_scale), str(device))
+    if key not in _gelu_tables:
+        t = torch.empty(_lib.GELU_TABLE_BYTES, dtype=torch.uint8, device=device)
+        rc = _lib.load().p2v_build_gelu_table(float(out_scale), ptr(t), stream())
+        if rc not in (0, 3):
+            check(rc, "build_gelu_table")
+        _gelu_tables[key] = t if rc == 0 else None
+    return _gelu_tables[key]
 
 
 def gemm(args, simt=False):

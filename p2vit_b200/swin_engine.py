@@ -147,6 +147,7 @@ class SwinPlan:
                 p["fc1"] = _Gemm(mlp.fc1, mlp.fc1.weight * cs.reshape(1, -1), 8, m0, dev)
                 p["fc1_out"] = _vec(m1, p["fc1"].N, dev)
                 p["fc1_pot"] = intmath.is_pot(m1)
+                p["gelu_tab"] = ops.gelu_table(float(m1), dev) if p["fc1_pot"] else None
                 p["fc2"] = _Gemm(mlp.fc2, mlp.fc2.weight, 8, m1, dev)
                 p["fc2_mid"] = _vec(_sym_scale(mlp.qact2, "mlp.qact2"), C, dev)
                 s_b4 = _vec(_sym_scale(blk.qact4, "block.qact4"), C, dev)
@@ -239,7 +240,7 @@ class SwinEngine:
                 steps.append((pre + "mlp.qact0", ln(p["ln2"], rb, R, C, lnb, clamp_mid=True)))
                 g1 = p["fc1"]
                 steps.append((pre + "mlp.qact1", gemm(ops.gemm_args(lnb, g1.W, ops.EPI_GELU, g1.acc_scale, bias=g1.bias, out_scale=p["fc1_out"],
-                                                                    out_i8=hid, pot=p["fc1_pot"]))))
+                                                                    out_i8=hid, pot=p["fc1_pot"], gelu_table=p["gelu_tab"]))))
                 g2 = p["fc2"]
                 steps.append((pre + "qact4", gemm(ops.gemm_args(hid, g2.W, ops.EPI_RESIDUAL, g2.acc_scale, bias=g2.bias, out_scale=p["fc2_out"],
                                                                 mid_scale=p["fc2_mid"], res_scale=p["proj_out"], res=rb, out_i8=ra,

@@ -135,6 +135,33 @@ def test_gemm_gelu(M, N, K):
         assert d.max() <= 1 and (d != 0).float().mean() < 2e-5, (float(d.max()), float((d != 0).float().mean()))
 
 
+@pytest.mark.parametrize("log2so", [-3, -4, -5, -6, -7])
+def test_gemm_gelu_step_table_equals_direct_erf(log2so):
+    """the GELU step table (p2v_build_gelu_table) must reproduce the direct erf epilogue bit for bit: random pre-activations and a
+    fine sweep (accumulator scale 2^-16, per-column biases spread over [-9, 5]) that lands many y within ulps of the thresholds"""
+    so = 2.0 ** log2so
+    tab = ops.gelu_table(so, DEV)
+    assert tab is not None
+    M, N, K = 2048, 256, 64
+    A, W, _ = _gemm_inputs(M, N, K, 70 + log2so)
+    outs = torch.full((N,), so, device=DEV)
+    for acc_scale, bias in ((2.0 ** -12, torch.randn(N) * 0.5), (2.0 ** -16, torch.linspace(-9.0, 5.0, N)), (2.0 ** -20, torch.linspace(-1.5, 0.5, N))):
+        s = torch.full((N,), acc_scale, device=DEV)
+        res = []
+        for table, simt in ((None, False), (tab, False), (tab, True)):
+            o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
+            ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_GELU, s, bias=bias.to(DEV), out_scale=outs, out_i8=o8, pot=True, gelu_table=table),
+                     simt=simt)
+            res.append(o8)
+        assert torch.equal(res[0], res[1]), "tcgen05: %d codes differ between table and direct erf" % int((res[0] != res[1]).sum())
+        assert torch.equal(res[0], res[2]), "simt: %d codes differ between table and direct erf" % int((res[0] != res[2]).sum())
+        assert int(res[0].float().abs().sum()) > 0
+
+
+def test_gelu_table_rejects_unsupported_scales():
+    assert ops.gelu_table(0.3, DEV) is None and ops.gelu_table(2.0 ** -9, DEV) is None
+
+
 @pytest.mark.parametrize("M,N,K", [(394, 384, 384), (300, 384, 1536), (197, 192, 768)])
 def test_gemm_residual_ptf(M, N, K):
     A, W, bias = _gemm_inputs(M, N, K, 40)
