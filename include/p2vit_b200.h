@@ -111,6 +111,11 @@ typedef struct {
 int p2v_build_gelu_table(float out_scale, void* table_dev, void* stream);
 
 int p2v_gemm_i8(const p2v_gemm_args* args_host, void* stream);
+/* Two tcgen05 kernels implement p2v_gemm_i8 with identical results: csrc/gemm_pair.cu (CTA pairs, cta_group::2, TMA-staged
+ * output; REQUANT / GELU / RESIDUAL with int8 output, N % 16 == 0, no row_map / zp_corr) and csrc/gemm_tc.cu (everything
+ * else and small M).  variant: 0 = automatic (default), 1 = always gemm_tc.cu, 2 = gemm_pair.cu whenever it applies
+ * (tests cross-check the two). Process-wide, not thread safe. */
+void p2v_set_gemm_variant(int variant);
 /* same contract on CUDA cores (dp4a); used by tests to cross-check the tcgen05 kernel */
 int p2v_gemm_i8_simt(const p2v_gemm_args* args_host, void* stream);
 /* EMBED helper: writes the B class-token rows: out[b*(T+1), n] = cls_row[n] */

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libp2vit_b200.so")
+LIB_PATH = os.environ.get("P2V_LIB") or os.path.join(_HERE, "csrc", "libp2vit_b200.so")   # P2V_LIB: experiment builds (tools/)
 
 EPI_REQUANT, EPI_GELU, EPI_RESIDUAL, EPI_EMBED, EPI_DEQUANT, EPI_F32 = range(6)
 GELU_TABLE_BYTES = 16 + 8 * 4096
@@ -77,6 +77,7 @@ SYMBOLS = {
     "p2v_build_gelu_table": (_I, [_F, _P, _P]),
     "p2v_gemm_i8": (_I, [C.POINTER(GemmArgs), _P]),
     "p2v_gemm_i8_simt": (_I, [C.POINTER(GemmArgs), _P]),
+    "p2v_set_gemm_variant": (None, [_I]),
     "p2v_fill_cls_rows": (_I, [_P, _P, _I, _I, _I, _P]),
     "p2v_layernorm_int": (_I, [C.POINTER(LayerNormArgs), _P]),
     "p2v_int_softmax_log2": (_I, [_P, _P, _I64, _I, _P, _P]),

@@ -29,6 +29,7 @@ int check_launch(const char* what) {
 int launch_gemm_simt(const p2v_gemm_args& a, cudaStream_t stream);
 int launch_build_gelu_table(float out_scale, void* table_dev, cudaStream_t stream);
 int launch_gemm_tc(const p2v_gemm_args& a, cudaStream_t stream);
+void set_gemm_variant(int v);
 int launch_quantize(const float* x, int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale,
                     float zp, int lo, int hi, cudaStream_t stream);
 int launch_dequantize(const int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale, float zp,
@@ -108,6 +109,7 @@ int p2v_gemm_i8(const p2v_gemm_args* a, void* stream) {
   if (int r = validate_gemm(a)) return r;
   return launch_gemm_tc(*a, (cudaStream_t)stream);
 }
+void p2v_set_gemm_variant(int variant) { set_gemm_variant(variant); }
 int p2v_gemm_i8_simt(const p2v_gemm_args* a, void* stream) {
   if (int r = validate_gemm(a)) return r;
   return launch_gemm_simt(*a, (cudaStream_t)stream);

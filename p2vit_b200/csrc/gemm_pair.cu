@@ -1,0 +1,631 @@
+// Block GEMMs (qkv / proj / fc1 / fc2) on CTA pairs: int8 x int8 -> int32 tcgen05.mma.cta_group::2 with the QAct
+// epilogues fused, built for the case the old one-tile-per-group kernel (gemm_tc.cu) handles badly: K is short
+// (384..1536), so the kernel is bound by the epilogue's instruction issue, by L2 -> SM operand traffic and by
+// uncoalesced row-wise stores, not by the tensor pipe.
+//
+//   * cluster of 2 CTAs = one 256 x BN output tile (BN in {128, 192, 256}); each CTA loads its own 128 rows of A and
+//     HALF of the W tile (TMA, SWIZZLE_128B); the leader CTA issues M256 x BN x K32 MMAs that read both halves, so a CTA
+//     pulls (128 + BN/2) * K bytes per 128 x BN outputs - half the W traffic of cta_group::1;
+//   * accumulators: 2 TMEM stages of 256 columns in each CTA; all 16 epilogue warps drain stage s while the MMAs of
+//     the next tile fill stage s^1;
+//   * epilogue warp = 32 rows (its TMEM lane quarter) x BN/4 columns, in chunks of 16 columns; the tcgen05.ld of chunk
+//     c+1 is in flight while chunk c is computed; per-column constants live in a warp-private shared-memory table,
+//     fetched one tile ahead;
+//   * output codes are staged in shared memory (swizzled, conflict-free 16-byte writes) and leave with one TMA store
+//     per warp and tile; the residual stream of the RESIDUAL epilogue arrives the same way (TMA load issued by the
+//     producer warp one tile ahead) and is overwritten in place by the output;
+//   * requantisation without F2I / FRND (both run on the 16-lane XU pipe): RNE through the 1.5*2^23 magic constant,
+//     saturation by clamping the biased float, the code is its low byte.  Division by a non-power-of-two scale s:
+//     RNE(y * r_lo) == RNE(y * r_hi) for r_lo < 1/s < r_hi (4 ulps apart) proves RNE(fl(y / s)) without dividing;
+//     the rare disagreement re-runs the chunk with the IEEE division for the columns concerned.
+//
+// Same results, bit for bit, as gemm_tc.cu / gemm_simt.cu (tests/test_gpu_ops.py cross-checks the three).
+#include <algorithm>
+#include "tc_common.cuh"
+#include "epilogue.cuh"
+
+namespace p2v {
+
+constexpr int PBM = 128;                 // rows per CTA (pair tile: 256)
+constexpr int PBK = 128;                 // K bytes per pipeline stage (one 128-byte swizzle row)
+constexpr int P_EPI_WARPS = 16;
+constexpr int P_THREADS = 128 + P_EPI_WARPS * 32;   // warpgroup 0: TMA producer, MMA issuer, 2 idle warps; warpgroups 1-4: epilogue
+constexpr int P_ACC_COLS = 256;          // TMEM columns per accumulator stage
+constexpr uint32_t P_A_BYTES = PBM * PBK;
+constexpr uint32_t P_B_BYTES = 128 * PBK;   // room for BN/2 <= 128 rows of W
+constexpr uint32_t P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
+constexpr uint32_t P_WARP_STG = 32 * 64;    // staging bytes per warp: 32 rows x <= 64 columns
+constexpr uint32_t P_SLOT_BYTES = P_EPI_WARPS * P_WARP_STG;   // one full-width staging slot (W = 64)
+constexpr float RMAGIC = 12582912.f;        // 1.5 * 2^23: x + RMAGIC has RNE(x) in its low mantissa bits for |x| < 2^22
+constexpr float RMAGIC_LO = RMAGIC - 128.f, RMAGIC_HI = RMAGIC + 127.f;
+
+struct PairGeom {
+  int BN;        // columns per pair tile
+  int W;         // columns per epilogue warp = BN / 4 (32, 48 or 64)
+  int tiles_n, tiles;   // pair tiles
+  int nkb;       // k blocks
+  int swz;       // staging swizzle: 0 none (48-byte rows), 1 SWIZZLE_32B, 2 SWIZZLE_64B
+  int nslot_log2;   // RESIDUAL: residual / output staging slots in flight (2 or 4 slots of 512 * W bytes)
+};
+// -DPAIR_TRACE (tools/pair_trace.py): CTA pair 0 writes clock64 stamps of its producer / MMA / first epilogue warp per tile
+// into the buffer passed as out_f32; not compiled into the product library.
+#ifdef PAIR_TRACE
+#define PTRACE(role, tile, slot_)                                                                                   \
+  do {                                                                                                              \
+    if (p.out_f32 != nullptr && pair == 0 && (tile) < 64)                                                           \
+      reinterpret_cast<long long*>(p.out_f32)[((int(rank) * 3 + (role)) * 64 + int(tile)) * 4 + (slot_)] = clock64(); \
+  } while (0)
+#else
+#define PTRACE(role, tile, slot_) do {} while (0)
+#endif
+struct TileIter {   // pair tiles t = pair, pair + npairs, ... as (row block, column block), column fastest
+  int mt, nt, dm, dn, tiles_n;
+  __device__ TileIter(uint32_t pair, uint32_t npairs, int tn) : mt(int(pair) / tn), nt(int(pair) % tn), dm(int(npairs) / tn), dn(int(npairs) % tn), tiles_n(tn) {}
+  __device__ void next() {
+    nt += dn; mt += dm;
+    if (nt >= tiles_n) { nt -= tiles_n; ++mt; }
+  }
+};
+
+// ---- parameter rows (warp-private table: rows of 64 floats)
+template <int EPI, bool POT>
+__host__ __device__ constexpr int prm_rows() {
+  return EPI == P2V_EPI_RESIDUAL ? 9 : (POT ? (EPI == P2V_EPI_GELU ? 3 : 2) : 5);
+}
+enum { PR_S = 0, PR_B = 1, PR_RO = 2,                 // POT GELU: 1/out_scale
+       PR_OLO = 2, PR_OHI = 3, PR_O = 4,              // general REQUANT / GELU
+       PR_MLO = 2, PR_MHI = 3, PR_M = 4, PR_RS = 5, PR_ROLO = 6, PR_ROHI = 7, PR_RO_ = 8 };   // RESIDUAL
+
+// ---- cluster / 2-SM primitives
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (release at CTA scope) as in CUTLASS' ClusterBarrier::arrive(cta_id): the hand-off it guards is
+  // TMEM (ordered by tcgen05.fence), and a cluster-scope release costs a full memory barrier per tile and warp
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on a barrier of either CTA of the pair (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t base, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// arrives (once the MMAs issued so far have completed) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+// tcgen05.wait::ld with the destination registers as in/out operands: no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld16(int (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
+// ---- exact requantisation helpers
+// r_lo < 1/d < r_hi, 2..4 ulps either side of rs = RN(1/d): fl(y/d) lies between y*r_lo and y*r_hi
+__device__ __forceinline__ float recip_lo(float rs) { return __fmaf_rn(rs, -0x1p-22f, rs); }
+__device__ __forceinline__ float recip_hi(float rs) { return __fmaf_rn(rs, 0x1p-22f, rs); }
+
+// clamp(RNE(fl(y / d)), -128, 127) + RMAGIC.  Fast pass: `flag` collects the columns whose two bounds round differently
+// (or saturate far out); EXACT pass: those columns take the IEEE division.
+template <bool EXACT, bool CLAMP = false>
+__device__ __forceinline__ float quant_iv(float y, float rlo, float rhi, float d, uint32_t& flag) {
+  const float tlo = __fmaf_rn(y, rlo, RMAGIC);
+  float thi = __fmaf_rn(y, rhi, RMAGIC);
+  const uint32_t diff = __float_as_uint(tlo) ^ __float_as_uint(thi);
+  if (EXACT) {
+    if (diff) thi = fadd(fminf(fmaxf(rintf(fdiv(y, d)), -128.f), 127.f), RMAGIC);
+  } else {
+    flag |= diff;
+  }
+  return CLAMP ? fminf(fmaxf(thi, RMAGIC_LO), RMAGIC_HI) : thi;     // final codes are saturated by pack4_sat
+}
+// RNE(x) + RMAGIC for x already on the output grid (power-of-two scales); saturated by pack4_sat
+__device__ __forceinline__ float quant_pot(float x) { return fadd(x, RMAGIC); }
+
+// four magic-biased floats (RMAGIC + RNE(x), not clamped) -> four saturated int8 codes in one word.  The bit pattern of
+// x + RMAGIC is monotone in x over all finite x (the sum is positive above -1.5*2^23, sign bit set below), so
+// sat_s8(bits - bits(RMAGIC)) == clamp(RNE(x), -128, 127) whatever the magnitude of x; cvt.pack.sat saturates two
+// values per instruction (a -> byte 0, b -> byte 1, c's low half -> the upper half of the result).
+__device__ __forceinline__ uint32_t pack4_sat(float a, float b, float c, float d) {
+  const int ia = int(__float_as_uint(a)) - 0x4B400000, ib = int(__float_as_uint(b)) - 0x4B400000;
+  const int ic = int(__float_as_uint(c)) - 0x4B400000, id = int(__float_as_uint(d)) - 0x4B400000;
+  uint32_t hi, out;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(id), "r"(ic), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(ib), "r"(ia), "r"(hi));
+  return out;
+}
+
+// One chunk: 16 accumulator columns of one row -> 16 output codes (4 packed words).  prm = this warp's table + the
+// chunk's column offset.  `resx` = the row's 16 residual codes with the sign bits flipped (code + 128 as u8).
+template <int EPI, bool POT, bool EXACT>
+__device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const int (&acc)[16], const uint4 resx, uint4& out,
+                                           uint32_t& flag) {
+  uint32_t ow[4];
+  const uint32_t rw[4] = {resx.x, resx.y, resx.z, resx.w};
+#pragma unroll
+  for (int j4 = 0; j4 < 16; j4 += 4) {
+    const float4 S4 = *reinterpret_cast<const float4*>(prm + PR_S * 64 + j4);
+    const float4 B4 = *reinterpret_cast<const float4*>(prm + PR_B * 64 + j4);
+    const float Sv[4] = {S4.x, S4.y, S4.z, S4.w}, Bv[4] = {B4.x, B4.y, B4.z, B4.w};
+    float t[4];
+    if (EPI == P2V_EPI_RESIDUAL) {
+      const float4 a4 = *reinterpret_cast<const float4*>(prm + PR_MLO * 64 + j4);
+      const float4 b4 = *reinterpret_cast<const float4*>(prm + PR_MHI * 64 + j4);
+      const float4 c4 = *reinterpret_cast<const float4*>(prm + PR_M * 64 + j4);
+      const float4 d4 = *reinterpret_cast<const float4*>(prm + PR_RS * 64 + j4);
+      const float4 e4 = *reinterpret_cast<const float4*>(prm + PR_ROLO * 64 + j4);
+      const float4 f4 = *reinterpret_cast<const float4*>(prm + PR_ROHI * 64 + j4);
+      const float MLv[4] = {a4.x, a4.y, a4.z, a4.w}, MHv[4] = {b4.x, b4.y, b4.z, b4.w}, Mv[4] = {c4.x, c4.y, c4.z, c4.w};
+      const float RSv[4] = {d4.x, d4.y, d4.z, d4.w}, OLv[4] = {e4.x, e4.y, e4.z, e4.w}, OHv[4] = {f4.x, f4.y, f4.z, f4.w};
+      float Ov[4] = {1.f, 1.f, 1.f, 1.f};
+      if (EXACT) {
+        const float4 g4 = *reinterpret_cast<const float4*>(prm + PR_RO_ * 64 + j4);
+        Ov[0] = g4.x; Ov[1] = g4.y; Ov[2] = g4.z; Ov[3] = g4.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float af = __int2float_rn(acc[j4 + e]);
+        const float y = POT ? __fmaf_rn(af, Sv[e], Bv[e]) : fadd(fmul(af, Sv[e]), Bv[e]);
+        const float k = fsub(quant_iv<EXACT, true>(y, MLv[e], MHv[e], Mv[e], flag), RMAGIC);        // qact after the GEMM (code)
+        const float tt = fmul(k, Mv[e]);
+        // residual code: byte e of the word (sign already flipped) -> 2^23 + (code + 128) -> code, exactly
+        const float r = fsub(__uint_as_float(__byte_perm(rw[j4 >> 2], 0x4B000000u, 0x7540 + e)), 8388736.f);
+        const float z = fadd(fmul(r, RSv[e]), tt);
+        t[e] = quant_iv<EXACT>(z, OLv[e], OHv[e], Ov[e], flag);
+      }
+    } else if (POT && EPI == P2V_EPI_REQUANT) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) t[e] = quant_pot(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]));   // S, B pre-divided by out_scale
+    } else if (POT && EPI == P2V_EPI_GELU) {
+      const float4 R4 = *reinterpret_cast<const float4*>(prm + PR_RO * 64 + j4);
+      const float Rv[4] = {R4.x, R4.y, R4.z, R4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float y = __fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]);
+        t[e] = __fmaf_rn(gelu_erf(y), Rv[e], RMAGIC);      // g * 2^k is exact
+      }
+    } else {
+      const float4 a4 = *reinterpret_cast<const float4*>(prm + PR_OLO * 64 + j4);
+      const float4 b4 = *reinterpret_cast<const float4*>(prm + PR_OHI * 64 + j4);
+      const float OLv[4] = {a4.x, a4.y, a4.z, a4.w}, OHv[4] = {b4.x, b4.y, b4.z, b4.w};
+      float Ov[4] = {1.f, 1.f, 1.f, 1.f};
+      if (EXACT) {
+        const float4 g4 = *reinterpret_cast<const float4*>(prm + PR_O * 64 + j4);
+        Ov[0] = g4.x; Ov[1] = g4.y; Ov[2] = g4.z; Ov[3] = g4.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float y = fadd(fmul(__int2float_rn(acc[j4 + e]), Sv[e]), Bv[e]);
+        if (EPI == P2V_EPI_GELU) y = gelu_erf(y);
+        t[e] = quant_iv<EXACT>(y, OLv[e], OHv[e], Ov[e], flag);
+      }
+    }
+    ow[j4 >> 2] = pack4_sat(t[0], t[1], t[2], t[3]);
+  }
+  out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+// The rare second pass of a chunk (some column's reciprocal bounds disagreed): the same arithmetic with the IEEE division
+// where needed, 4 columns at a time in a rolled loop over private copies so that it costs the fast path no registers.
+template <int EPI, bool POT>
+__device__ __noinline__ void pair_chunk_exact_words(const float* __restrict__ prm, const int* __restrict__ acc, const uint32_t* __restrict__ rw,
+                                                    uint32_t* __restrict__ ow) {
+#pragma unroll 1
+  for (int j4 = 0; j4 < 16; j4 += 4) {
+    float t[4];
+    uint32_t flag = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = j4 + e;
+      const float af = __int2float_rn(acc[c]);
+      const float S = prm[PR_S * 64 + c], B = prm[PR_B * 64 + c];
+      if (EPI == P2V_EPI_RESIDUAL) {
+        const float y = POT ? __fmaf_rn(af, S, B) : fadd(fmul(af, S), B);
+        const float M = prm[PR_M * 64 + c];
+        const float k = fsub(quant_iv<true, true>(y, prm[PR_MLO * 64 + c], prm[PR_MHI * 64 + c], M, flag), RMAGIC);
+        const float r = fsub(__uint_as_float(__byte_perm(rw[j4 >> 2], 0x4B000000u, 0x7540 + e)), 8388736.f);
+        const float z = fadd(fmul(r, prm[PR_RS * 64 + c]), fmul(k, M));
+        t[e] = quant_iv<true>(z, prm[PR_ROLO * 64 + c], prm[PR_ROHI * 64 + c], prm[PR_RO_ * 64 + c], flag);
+      } else {
+        float y = fadd(fmul(af, S), B);
+        if (EPI == P2V_EPI_GELU) y = gelu_erf(y);
+        t[e] = quant_iv<true>(y, prm[PR_OLO * 64 + c], prm[PR_OHI * 64 + c], prm[PR_O * 64 + c], flag);
+      }
+    }
+    ow[j4 >> 2] = pack4_sat(t[0], t[1], t[2], t[3]);
+  }
+}
+template <int EPI, bool POT>
+__device__ __forceinline__ void pair_chunk_exact(const float* __restrict__ prm, const int (&acc)[16], const uint4 resx, uint4& out) {
+  int a[16];
+  uint32_t rw[4] = {resx.x, resx.y, resx.z, resx.w}, ow[4];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = acc[j];
+  pair_chunk_exact_words<EPI, POT>(prm, a, rw, ow);
+  out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+// per-column constants of columns n (lane's first) and n + 32 (second, if < W): raw values, fetched one tile ahead
+struct RawCol { float s, b, o, m, rs; };
+template <int EPI>
+__device__ __forceinline__ RawCol load_raw_col(const EpiParams& p, int n, bool ok) {
+  RawCol r;
+  ok = ok && n < p.N;
+  r.s = ok ? __ldg(p.acc_scale + n) : 0.f;
+  r.b = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
+  r.o = ok ? __ldg(p.out_scale + n) : 1.f;
+  r.m = (EPI == P2V_EPI_RESIDUAL && ok) ? __ldg(p.mid_scale + n) : 1.f;
+  r.rs = (EPI == P2V_EPI_RESIDUAL && ok) ? __ldg(p.res_scale + n) : 0.f;
+  return r;
+}
+template <int EPI, bool POT>
+__device__ __forceinline__ void store_col(float* prm, int c, const RawCol& r) {
+  const float ro = __frcp_rn(r.o);     // == fdiv(1, o): both correctly rounded
+  if (EPI == P2V_EPI_RESIDUAL) {
+    const float rm = __frcp_rn(r.m);
+    prm[PR_S * 64 + c] = r.s; prm[PR_B * 64 + c] = r.b;
+    prm[PR_MLO * 64 + c] = recip_lo(rm); prm[PR_MHI * 64 + c] = recip_hi(rm); prm[PR_M * 64 + c] = r.m;
+    prm[PR_RS * 64 + c] = r.rs;
+    prm[PR_ROLO * 64 + c] = recip_lo(ro); prm[PR_ROHI * 64 + c] = recip_hi(ro); prm[PR_RO_ * 64 + c] = r.o;
+  } else if (POT && EPI == P2V_EPI_REQUANT) {
+    prm[PR_S * 64 + c] = fmul(r.s, ro); prm[PR_B * 64 + c] = fmul(r.b, ro);   // exact: ro is a power of two
+  } else if (POT) {
+    prm[PR_S * 64 + c] = r.s; prm[PR_B * 64 + c] = r.b; prm[PR_RO * 64 + c] = ro;
+  } else {
+    prm[PR_S * 64 + c] = r.s; prm[PR_B * 64 + c] = r.b;
+    prm[PR_OLO * 64 + c] = recip_lo(ro); prm[PR_OHI * 64 + c] = recip_hi(ro); prm[PR_O * 64 + c] = r.o;
+  }
+}
+
+template <int STAGES, int EPI, bool POT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                 const __grid_constant__ CUtensorMap tmR, EpiParams p, PairGeom g) {
+  constexpr bool RESID = EPI == P2V_EPI_RESIDUAL;
+  constexpr int NSLOT = RESID ? 2 : 1;            // staging bytes in units of full-width slots
+  constexpr int ROWS = prm_rows<EPI, POT>();
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 12];
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg = ring + STAGES * P_STAGE_BYTES;
+  float* prm_all = reinterpret_cast<float*>(smem_raw + (stg - smem_u32(smem_raw)) + NSLOT * P_SLOT_BYTES);
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * STAGES]), bar_tempty = bar_tfull + 16;
+  const uint32_t bar_rfull = bar_tfull + 32, bar_sempty = bar_tfull + 64;     // up to 4 residual slots each
+  const uint32_t slot_bytes = uint32_t(P_EPI_WARPS) * 32u * uint32_t(g.W), warp_stg = 32u * uint32_t(g.W);
+  const uint32_t slot_mask = (1u << g.nslot_log2) - 1u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 2 * P_EPI_WARPS);     // every epilogue warp of both CTAs
+    }
+    for (int a = 0; a < 4; ++a) {
+      mbar_init(bar_rfull + 8 * a, 1);
+      mbar_init(bar_sempty + 8 * a, P_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_pair(smem_u32(&tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  // XX = 1 control warp + 4 epilogue warps -> 24 + 4 * 120 registers per lane
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (lane == 0) {
+      tma_prefetch_map(&tmA);
+      tma_prefetch_map(&tmB);
+      if (RESID) tma_prefetch_map(&tmR);
+      const uint32_t full0 = mapa_u32(bar_full, 0);       // the leader's full barriers collect both CTAs' bytes
+      const uint32_t bhalf_bytes = uint32_t(g.BN / 2) * PBK;
+      uint32_t itk = 0, it = 0;
+      TileIter ti(pair, npairs, g.tiles_n);
+      for (uint32_t t = pair; t < uint32_t(g.tiles); t += npairs, ++it, ti.next()) {
+        const int mt = ti.mt, nt = ti.nt;
+        const int m0 = mt * 256 + int(rank) * PBM, nb0 = nt * g.BN + int(rank) * (g.BN / 2);
+        PTRACE(2, it, 0);
+        for (int kb = 0; kb < g.nkb; ++kb, ++itk) {
+          const uint32_t s = itk % STAGES, ph = (itk / STAGES) & 1u;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+          if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2u * (P_A_BYTES + bhalf_bytes));
+          const uint32_t sa = ring + s * P_STAGE_BYTES;
+          tma_load_2d_pair(sa, &tmA, full0 + 8 * s, kb * PBK, m0);
+          tma_load_2d_pair(sa + P_A_BYTES, &tmB, full0 + 8 * s, kb * PBK, nb0);
+        }
+        PTRACE(2, it, 1);
+        if (RESID) {   // residual codes of this tile, straight into the staging slot the epilogue will overwrite
+          const uint32_t slot = it & slot_mask, u = it >> g.nslot_log2;
+          mbar_wait(bar_sempty + 8 * slot, (u & 1u) ^ 1u);
+          mbar_expect_tx(bar_rfull + 8 * slot, slot_bytes);
+          for (int e = 0; e < P_EPI_WARPS; ++e) {
+            const int q = e & 3, cg = e >> 2;
+            tma_load_2d(stg + slot * slot_bytes + e * warp_stg, &tmR, bar_rfull + 8 * slot, nt * g.BN + cg * g.W, m0 + q * 32);
+          }
+          PTRACE(2, it, 2);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_i8_idesc(256, g.BN, true, true);
+      uint32_t itk = 0, it = 0;
+      for (uint32_t t = pair; t < uint32_t(g.tiles); t += npairs, ++it) {
+        const uint32_t a = it & 1u, use = it >> 1;
+        PTRACE(0, it, 0);
+        mbar_wait(bar_tempty + 8 * a, (use & 1u) ^ 1u);
+        tc_fence_after();
+        PTRACE(0, it, 1);
+        const uint32_t d_tmem = tmem_base + a * P_ACC_COLS;
+        for (int kb = 0; kb < g.nkb; ++kb, ++itk) {
+          const uint32_t s = itk % STAGES, ph = (itk / STAGES) & 1u;
+          mbar_wait(bar_full + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = ring + s * P_STAGE_BYTES, sb = sa + P_A_BYTES;
+          const int ksteps = min(PBK / 32, (p.K - kb * PBK + 31) / 32);
+          for (int k = 0; k < ksteps; ++k)
+            umma_i8_pair(d_tmem, make_kmajor_sw128_desc(sa + k * 32), make_kmajor_sw128_desc(sb + k * 32), idesc, uint32_t(kb > 0 || k > 0));
+          tc_commit_pair(bar_empty + 8 * s, 3);    // both CTAs' producers may refill the stage
+        }
+        tc_commit_pair(bar_tfull + 8 * a, 3);      // accumulator complete in both CTAs' TMEM
+        PTRACE(0, it, 2);
+      }
+    }
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+  } else {
+    // ================= epilogue: 16 warps, warp = 32 rows x W columns =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int e = warp - 4;
+    const uint32_t quarter = uint32_t(warp) & 3u;         // TMEM lane quarter this warp may read
+    const int cg = e >> 2;
+    const int W = g.W, nch = W >> 4;
+    float* prm = prm_all + e * ROWS * 64;
+    const uint32_t tempty0 = mapa_u32(bar_tempty, 0);
+    // byte offset of this lane's 16-byte chunk c inside the warp's staging block (row pitch W bytes)
+    const uint32_t row_off = uint32_t(lane) * uint32_t(W);
+    const uint32_t xr = g.swz == 2 ? (uint32_t(lane) >> 1) & 3u : (g.swz == 1 ? (uint32_t(lane) >> 2) & 1u : 0u);
+    RawCol nx0, nx1;
+    TileIter ti(pair, npairs, g.tiles_n);
+    {
+      const int n0 = ti.nt * g.BN + cg * W;
+      nx0 = load_raw_col<EPI>(p, n0 + lane, pair < uint32_t(g.tiles));
+      nx1 = load_raw_col<EPI>(p, n0 + 32 + lane, pair < uint32_t(g.tiles) && 32 + lane < W);
+    }
+    uint32_t it = 0;
+    int pending_slot = -1;     // RESID: staging slot whose store has been issued but not yet released to the producer
+    for (uint32_t t = pair; t < uint32_t(g.tiles); t += npairs, ++it) {
+      const int mt = ti.mt, nt = ti.nt;
+      ti.next();
+      const int m0 = mt * 256 + int(rank) * PBM + int(quarter) * 32, n0 = nt * g.BN + cg * W;
+      const uint32_t a = it & 1u, use = it >> 1;
+      const uint32_t slot = RESID ? (it & slot_mask) : 0u, ruse = it >> g.nslot_log2;
+      const uint32_t my_stg = stg + slot * slot_bytes + uint32_t(e) * warp_stg;
+      // this tile's column constants (fetched during the previous tile), then fetch the next tile's
+      __syncwarp();
+      store_col<EPI, POT>(prm, lane, nx0);
+      if (32 + lane < W) store_col<EPI, POT>(prm, 32 + lane, nx1);
+      __syncwarp();
+      {
+        const uint32_t tn = t + npairs;
+        const int nn0 = ti.nt * g.BN + cg * W;
+        nx0 = load_raw_col<EPI>(p, nn0 + lane, tn < uint32_t(g.tiles));
+        nx1 = load_raw_col<EPI>(p, nn0 + 32 + lane, tn < uint32_t(g.tiles) && 32 + lane < W);
+      }
+      if (e == 0 && lane == 0) PTRACE(1, it, 0);
+      if (RESID) mbar_wait(bar_rfull + 8 * slot, ruse & 1u);
+      if (e == 0 && lane == 0) PTRACE(1, it, 1);
+      mbar_wait(bar_tfull + 8 * a, use & 1u);
+      tc_fence_after();
+      if (e == 0 && lane == 0) PTRACE(1, it, 2);
+      const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + a * P_ACC_COLS + uint32_t(cg * W);
+      int accA[16], accB[16];
+      tmem_ld16_async(taddr, accA);
+      // one 16-column chunk: wait for its accumulators, start the next chunk's tcgen05.ld (or hand the TMEM stage back), compute, stage
+      auto do_chunk = [&](int c, int (&cur)[16], int (&nxt)[16]) {
+        __syncwarp();
+        tmem_wait_ld16(cur);
+        if (c + 1 < nch) {
+          tmem_ld16_async(taddr + (c + 1) * 16, nxt);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * a);
+        }
+        const uint32_t caddr = my_stg + row_off + ((uint32_t(c) ^ xr) << 4);
+        uint4 resx = make_uint4(0, 0, 0, 0);
+        if (RESID) {
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(resx.x), "=r"(resx.y), "=r"(resx.z), "=r"(resx.w) : "r"(caddr));
+          resx.x ^= 0x80808080u; resx.y ^= 0x80808080u; resx.z ^= 0x80808080u; resx.w ^= 0x80808080u;
+        }
+        uint4 o;
+        uint32_t flag = 0;
+        pair_chunk<EPI, POT, false>(prm + c * 16, cur, resx, o, flag);
+        if (!(POT && EPI != P2V_EPI_RESIDUAL)) {
+          if (flag) pair_chunk_exact<EPI, POT>(prm + c * 16, cur, resx, o);
+        }
+        if (c == 0) {
+          if (!RESID) {                     // the previous tile's store must have finished reading this block
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+          } else if (pending_slot >= 0) {   // release the previous tile's slot to the producer (its store was issued a chunk ago)
+            if (lane == 0) { bulk_wait_read0(); mbar_arrive(bar_sempty + 8 * uint32_t(pending_slot)); }
+            pending_slot = -1;
+          }
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+      };
+#pragma unroll 1
+      for (int c = 0; c < nch; c += 2) {
+        do_chunk(c, accA, accB);
+        if (c + 1 < nch) do_chunk(c + 1, accB, accA);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmO, my_stg, n0, m0);
+        bulk_commit();
+        if (e == 0) PTRACE(1, it, 3);
+      }
+      if (RESID) pending_slot = int(slot);
+    }
+    if (lane == 0) {
+      bulk_wait_all();
+      // no arrive on bar_sempty here: the producer has no further tile to load
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer may still be signalling this CTA's barriers / reading its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static int make_tmap_rows(CUtensorMap* m, const void* ptr, int rows, int cols, int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+  encode_tiled_fn enc = get_tensor_map_encoder();
+  P2V_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(cols)};
+  cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  P2V_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d box=%dx%d", int(r), rows, cols, box_rows, box_cols);
+  return 0;
+}
+
+bool gemm_pair_supported(const p2v_gemm_args& a) {
+  const int e = a.epilogue;
+  if (e != P2V_EPI_REQUANT && e != P2V_EPI_GELU && e != P2V_EPI_RESIDUAL) return false;
+  if (a.row_map || a.zp_corr || !a.out_i8) return false;
+  if (a.N % 16 || a.K % 16) return false;
+  if (reinterpret_cast<uintptr_t>(a.out_i8) & 15) return false;
+  if (e == P2V_EPI_RESIDUAL && (reinterpret_cast<uintptr_t>(a.res) & 15)) return false;
+  return true;
+}
+
+static int max_pairs() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached = std::max(1, sms / 2);
+  }
+  return cached;
+}
+
+template <int STAGES, int EPI, bool POT>
+static int launch_pair(const p2v_gemm_args& a, const PairGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                       const CUtensorMap& tmR, cudaStream_t stream) {
+  constexpr int NSLOT = EPI == P2V_EPI_RESIDUAL ? 2 : 1;
+  constexpr size_t smem = 1024 + size_t(STAGES) * P_STAGE_BYTES + NSLOT * P_SLOT_BYTES + size_t(P_EPI_WARPS) * prm_rows<EPI, POT>() * 64 * 4;
+  static_assert(smem <= 227 * 1024 - 512, "shared memory budget");
+  auto kern = gemm_pair_kernel<STAGES, EPI, POT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    P2V_REQUIRE(e == cudaSuccess, "gemm_pair: cannot set %zu bytes of dynamic shared memory: %s", smem, cudaGetErrorString(e));
+    attr = true;
+  }
+  const int grid = 2 * std::min(g.tiles, max_pairs());
+  EpiParams p = make_epi_params(a);
+  kern<<<grid, P_THREADS, smem, stream>>>(tmA, tmB, tmO, tmR, p, g);
+  count_launch();
+  return check_launch("gemm_pair");
+}
+
+int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
+  P2V_REQUIRE(gemm_pair_supported(a), "gemm_pair: unsupported arguments");
+  // column tile: least makespan in column units over the CTA pairs, ties to the wider tile (less operand traffic)
+  const int tiles_m = (a.M + 255) / 256, pairs = max_pairs();
+  int best_bn = 128;
+  long best_cost = -1;
+  for (int bn : {256, 192, 128}) {
+    const long tn = (a.N + bn - 1) / bn;
+    const long waves = (long(tiles_m) * tn + pairs - 1) / pairs;
+    const long cost = waves * bn;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
+  }
+  PairGeom g;
+  g.BN = best_bn;
+  g.W = best_bn / 4;
+  g.tiles_n = (a.N + best_bn - 1) / best_bn;
+  g.tiles = tiles_m * g.tiles_n;
+  g.nkb = (a.K + PBK - 1) / PBK;
+  g.swz = g.W == 64 ? 2 : (g.W == 32 ? 1 : 0);
+  g.nslot_log2 = a.epilogue == P2V_EPI_RESIDUAL ? (g.W == 32 ? 2 : 1) : 0;
+  const CUtensorMapSwizzle oswz = g.W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (g.W == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUtensorMap tmA, tmB, tmO, tmR;
+  if (int r = make_tmap_rows(&tmA, a.A, a.M, a.K, PBK, PBM, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
+  if (int r = make_tmap_rows(&tmB, a.W, a.N, a.K, PBK, g.BN / 2, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
+  if (int r = make_tmap_rows(&tmO, a.out_i8, a.M, a.N, g.W, 32, oswz)) return r;
+  tmR = tmO;
+  if (a.epilogue == P2V_EPI_RESIDUAL)
+    if (int r = make_tmap_rows(&tmR, a.res, a.M, a.N, g.W, 32, oswz)) return r;
+  const bool pot = a.pot_scales != 0;
+  switch (a.epilogue) {
+    case P2V_EPI_REQUANT:
+      return pot ? launch_pair<5, P2V_EPI_REQUANT, true>(a, g, tmA, tmB, tmO, tmR, stream)
+                 : launch_pair<5, P2V_EPI_REQUANT, false>(a, g, tmA, tmB, tmO, tmR, stream);
+    case P2V_EPI_GELU:
+      return pot ? launch_pair<5, P2V_EPI_GELU, true>(a, g, tmA, tmB, tmO, tmR, stream)
+                 : launch_pair<5, P2V_EPI_GELU, false>(a, g, tmA, tmB, tmO, tmR, stream);
+    default:
+      return pot ? launch_pair<3, P2V_EPI_RESIDUAL, true>(a, g, tmA, tmB, tmO, tmR, stream)
+                 : launch_pair<3, P2V_EPI_RESIDUAL, false>(a, g, tmA, tmB, tmO, tmR, stream);
+  }
+}
+
+}  // namespace p2v

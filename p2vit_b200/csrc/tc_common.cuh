@@ -29,12 +29,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// try_wait suspends in hardware for a bounded time per call; the iteration cap turns a protocol bug into a
-// trap (reported as a launch error by the next API call) instead of a hung GPU.
+// try_wait suspends in hardware for a bounded time per call; a wait that lasts longer than 2 s of wall clock is a protocol
+// bug and becomes a trap (reported as a launch error by the next API call) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    __nanosleep(64);       // keep the issue slots for the warps that have work
+    if ((++spins & 63u) == 0u) {
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

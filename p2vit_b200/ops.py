@@ -101,6 +101,11 @@ def gelu_table(out_scale, device):
     return _gelu_tables[key]
 
 
+def set_gemm_variant(variant):
+    """0 = automatic, 1 = csrc/gemm_tc.cu always, 2 = csrc/gemm_pair.cu whenever it applies (tests cross-check the two)"""
+    _lib.load().p2v_set_gemm_variant(int(variant))
+
+
 def gemm(args, simt=False):
     lib = _lib.load()
     fn = lib.p2v_gemm_i8_simt if simt else lib.p2v_gemm_i8

@@ -162,6 +162,99 @@ def test_gelu_table_rejects_unsupported_scales():
     assert ops.gelu_table(0.3, DEV) is None and ops.gelu_table(2.0 ** -9, DEV) is None
 
 
+# ---- the CTA-pair kernel (csrc/gemm_pair.cu) against the one-tile kernel (csrc/gemm_tc.cu) and exact references
+PAIR_SHAPES = [(2 * 197 * 6 + 57, 384, 384),   # BN = 128, ragged M
+               (1300, 1152, 384),              # BN = 192
+               (1100, 1536, 384),              # BN = 256
+               (1024, 384, 1536),              # long K (fc2)
+               (700, 96, 96), (900, 288, 96),  # Swin stage 1: N below one tile, K below one k-block
+               (1500, 576, 192), (1030, 2304, 768), (515, 1000 - 8, 64)]
+
+
+def _run_variants(make_args, M, N):
+    outs = []
+    try:
+        for v in (1, 2):
+            ops.set_gemm_variant(v)
+            o8 = torch.full((M, N), 77, dtype=torch.int8, device=DEV)
+            ops.gemm(make_args(o8))
+            torch.cuda.synchronize()
+            outs.append(o8)
+    finally:
+        ops.set_gemm_variant(0)
+    return outs
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES)
+@pytest.mark.parametrize("pot", [True, False])
+def test_gemm_pair_requant(M, N, K, pot):
+    A, W, bias = _gemm_inputs(M, N, K, 120)
+    acc_scale = (torch.full((N,), 2.0 ** -13) if pot else torch.rand(N) * 1e-4 + 1e-4).to(DEV)
+    out_scale = (torch.full((N,), 2.0 ** -4) if pot else torch.rand(N) * 0.05 + 0.03).to(DEV)
+    y = _acc_exact(A, W).float() * acc_scale + bias.to(DEV)
+    ref = (y / out_scale).round().clamp(-128, 127)
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), bias.to(DEV)
+    old, new = _run_variants(lambda o8: ops.gemm_args(Ad, Wd, ops.EPI_REQUANT, acc_scale, bias=bd, out_scale=out_scale, out_i8=o8, pot=pot), M, N)
+    assert torch.equal(new.float(), ref), "pair kernel: %d mismatches vs the exact reference" % int((new.float() != ref).sum())
+    assert torch.equal(old, new)
+
+
+@pytest.mark.parametrize("M,N,K", PAIR_SHAPES[:6])
+@pytest.mark.parametrize("pot", [True, False])
+def test_gemm_pair_residual(M, N, K, pot):
+    A, W, bias = _gemm_inputs(M, N, K, 140)
+    torch.manual_seed(141)
+    fac = torch.tensor([1.0, 2.0, 4.0, 8.0])
+    acc_scale = (torch.full((N,), 2.0 ** -14) if pot else torch.rand(N) * 3e-5 + 5e-5).to(DEV)
+    mid = (0.00931 * fac[torch.randint(0, 4, (N,))]).to(DEV)
+    rs = (0.0123 * fac[torch.randint(0, 4, (N,))]).to(DEV)
+    outs = (0.0171 * fac[torch.randint(0, 4, (N,))]).to(DEV)
+    res = _rand_codes(M, N, seed=142).to(DEV)
+    y = _acc_exact(A, W).float() * acc_scale + bias.to(DEV)
+    c = (y / mid).round().clamp(-128, 127)
+    ref = ((res.float() * rs + c * mid) / outs).round().clamp(-128, 127)
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), bias.to(DEV)
+    old, new = _run_variants(lambda o8: ops.gemm_args(Ad, Wd, ops.EPI_RESIDUAL, acc_scale, bias=bd, out_scale=outs, mid_scale=mid,
+                                                       res_scale=rs, res=res, out_i8=o8, pot=pot), M, N)
+    assert torch.equal(new.float(), ref), "pair kernel: %d mismatches vs the exact reference" % int((new.float() != ref).sum())
+    assert torch.equal(old, new)
+
+
+def test_gemm_pair_residual_many_ties():
+    """quotients that are exact ties (k + 1/2) and saturated values: the reciprocal-bounds test must send them to the IEEE division"""
+    M, N, K = 1536, 256, 128
+    A, W, _ = _gemm_inputs(M, N, K, 150)
+    acc_scale = torch.full((N,), 2.0 ** -6).to(DEV)
+    bias = torch.zeros(N, device=DEV)
+    mid = torch.full((N,), 2.0 ** -5 * 3.0).to(DEV)      # y/mid = acc/6: ties whenever acc = 3 mod 6
+    rs = torch.full((N,), 0.75).to(DEV)
+    outs = torch.full((N,), 1.5).to(DEV)
+    res = _rand_codes(M, N, seed=152).to(DEV)
+    y = _acc_exact(A, W).float() * acc_scale
+    c = (y / mid).round().clamp(-128, 127)
+    ref = ((res.float() * rs + c * mid) / outs).round().clamp(-128, 127)
+    Ad, Wd = A.to(DEV), W.to(DEV)
+    old, new = _run_variants(lambda o8: ops.gemm_args(Ad, Wd, ops.EPI_RESIDUAL, acc_scale, bias=bias, out_scale=outs, mid_scale=mid,
+                                                       res_scale=rs, res=res, out_i8=o8, pot=True), M, N)
+    assert torch.equal(new.float(), ref), int((new.float() != ref).sum())
+    assert torch.equal(old, new)
+
+
+@pytest.mark.parametrize("M,N,K", [(1182 + 31, 1536, 384), (1100, 768, 192), (1040, 3072, 768)])
+@pytest.mark.parametrize("pot", [True, False])
+def test_gemm_pair_gelu(M, N, K, pot):
+    A, W, bias = _gemm_inputs(M, N, K, 160)
+    acc_scale = (torch.full((N,), 2.0 ** -13) if pot else torch.rand(N) * 1e-4 + 1e-4).to(DEV)
+    out_scale = (torch.full((N,), 2.0 ** -6) if pot else torch.rand(N) * 0.01 + 0.01).to(DEV)
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), bias.to(DEV)
+    old, new = _run_variants(lambda o8: ops.gemm_args(Ad, Wd, ops.EPI_GELU, acc_scale, bias=bd, out_scale=out_scale, out_i8=o8, pot=pot), M, N)
+    assert torch.equal(old, new), "%d codes differ between the two tcgen05 kernels" % int((old != new).sum())
+    y = _acc_exact(A, W).float() * acc_scale + bd
+    ref = (torch.nn.functional.gelu(y) / out_scale).round().clamp(-128, 127)
+    d = (new.float() - ref).abs()
+    assert d.max() <= 1 and (d != 0).float().mean() < 2e-5
+
+
 @pytest.mark.parametrize("M,N,K", [(394, 384, 384), (300, 384, 1536), (197, 192, 768)])
 def test_gemm_residual_ptf(M, N, K):
     A, W, bias = _gemm_inputs(M, N, K, 40)
