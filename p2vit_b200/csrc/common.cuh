@@ -44,6 +44,22 @@ __device__ __forceinline__ uint32_t pack4_s8(int a, int b, int c, int d) {
   return (uint32_t(a) & 0xffu) | ((uint32_t(b) & 0xffu) << 8) | ((uint32_t(c) & 0xffu) << 16) | (uint32_t(d) << 24);
 }
 
+// ---- rounding / saturation without the XU pipe (F2I and FRND run on 16 lanes per SM)
+constexpr float RMAGIC = 12582912.f;        // 1.5 * 2^23: x + RMAGIC has RNE(x) in its low mantissa bits for |x| < 2^22
+// four magic-biased floats (RMAGIC + RNE(x), not clamped) -> four saturated int8 codes in one word.  The bit pattern of
+// x + RMAGIC is monotone in x over all finite x (the sum is positive above -1.5*2^23, sign bit set below), so
+// sat_s8(bits - bits(RMAGIC)) == clamp(RNE(x), -128, 127) whatever the magnitude of x; cvt.pack.sat saturates two
+// values per instruction (a -> byte 0, b -> byte 1, c's low half -> the upper half of the result).
+__device__ __forceinline__ uint32_t pack4_sat(float a, float b, float c, float d) {
+  const int ia = int(__float_as_uint(a)) - 0x4B400000, ib = int(__float_as_uint(b)) - 0x4B400000;
+  const int ic = int(__float_as_uint(c)) - 0x4B400000, id = int(__float_as_uint(d)) - 0x4B400000;
+  uint32_t hi, out;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(id), "r"(ic), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(ib), "r"(ia), "r"(hi));
+  return out;
+}
+
+
 // torch's nn.GELU() (erf form): x * 0.5 * (1 + erf(x * sqrt(1/2)))   (ATen cpu/Activation: vectorized
 // x * kAlpha -> erf -> +1 -> * x * 0.5).  erff differs from Sleef's by <= 1 ulp on rare inputs; those
 // only matter at rounding ties (DESIGN.md "tie adjudication").

@@ -36,7 +36,6 @@ constexpr uint32_t P_B_BYTES = 128 * PBK;   // room for BN/2 <= 128 rows of W
 constexpr uint32_t P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
 constexpr uint32_t P_WARP_STG = 32 * 64;    // staging bytes per warp: 32 rows x <= 64 columns
 constexpr uint32_t P_SLOT_BYTES = P_EPI_WARPS * P_WARP_STG;   // one full-width staging slot (W = 64)
-constexpr float RMAGIC = 12582912.f;        // 1.5 * 2^23: x + RMAGIC has RNE(x) in its low mantissa bits for |x| < 2^22
 constexpr float RMAGIC_LO = RMAGIC - 128.f, RMAGIC_HI = RMAGIC + 127.f;
 
 struct PairGeom {
@@ -157,19 +156,6 @@ __device__ __forceinline__ float quant_iv(float y, float rlo, float rhi, float d
 }
 // RNE(x) + RMAGIC for x already on the output grid (power-of-two scales); saturated by pack4_sat
 __device__ __forceinline__ float quant_pot(float x) { return fadd(x, RMAGIC); }
-
-// four magic-biased floats (RMAGIC + RNE(x), not clamped) -> four saturated int8 codes in one word.  The bit pattern of
-// x + RMAGIC is monotone in x over all finite x (the sum is positive above -1.5*2^23, sign bit set below), so
-// sat_s8(bits - bits(RMAGIC)) == clamp(RNE(x), -128, 127) whatever the magnitude of x; cvt.pack.sat saturates two
-// values per instruction (a -> byte 0, b -> byte 1, c's low half -> the upper half of the result).
-__device__ __forceinline__ uint32_t pack4_sat(float a, float b, float c, float d) {
-  const int ia = int(__float_as_uint(a)) - 0x4B400000, ib = int(__float_as_uint(b)) - 0x4B400000;
-  const int ic = int(__float_as_uint(c)) - 0x4B400000, id = int(__float_as_uint(d)) - 0x4B400000;
-  uint32_t hi, out;
-  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(id), "r"(ic), "r"(0));
-  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(ib), "r"(ia), "r"(hi));
-  return out;
-}
 
 // One chunk: 16 accumulator columns of one row -> 16 output codes (4 packed words).  prm = this warp's table + the
 // chunk's column offset.  `resx` = the row's 16 residual codes with the sign bits flipped (code + 128 as u8).

@@ -240,6 +240,32 @@ __device__ __forceinline__ uint32_t ln_pot_word(float t, float mos, const float 
   return pack4_s8(q[0], q[1], q[2], q[3]);
 }
 
+// The same arithmetic for the common case 2^-24 <= |A| < 2^8 with integer / magic-constant tricks (results identical):
+//   N = 7 - (E - 127) with E the biased exponent of A, so 2^N and 2^-N are exponent-field subtractions;
+//   M = floor(|A| * 2^N) = the top 8 bits of A's significand, and sign(A) * M as a float is A with its low 16 mantissa bits
+//   cleared and its exponent set to 7:  (bits(A) & 0x807f0000) | 0x43000000;
+//   RNE(v) for |v| < 2^22 = (v + 1.5*2^23) - 1.5*2^23, fused with the preceding power-of-two scaling into one FFMA;
+//   the final saturation to int8 is pack4_sat's.  `mant_max` collects max(mantissa(A)) for the caller's corner-case test.
+__device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const float (&g)[4], const float (&bt)[4], const float (&f)[4],
+                                                     const int (&xv)[4], bool clamp_mid, uint32_t& mant_max) {
+  float r[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const uint32_t Ab = __float_as_uint(fmul(t, g[e]));
+    const uint32_t Ef = Ab & 0x7f800000u;
+    mant_max = max(mant_max, Ab & 0x007fffffu);
+    const float twoN = __uint_as_float(0x82800000u - Ef);            // 2^(134 - E)
+    const float rtwoN = __uint_as_float(Ef - 0x03800000u);           // 2^(E - 134)
+    const float sM = __uint_as_float((Ab & 0x807f0000u) | 0x43000000u);
+    const float Bv = rintf(fmul(fsub(bt[e], fmul(mos, g[e])), twoN));
+    const float sum = fadd(fmul(sM, __int2float_rn(xv[e])), Bv);
+    float yq = fsub(__fmaf_rn(sum, rtwoN, RMAGIC), RMAGIC);          // RNE(sum / 2^N)
+    if (clamp_mid) yq = fminf(fmaxf(yq, -128.f), 127.f);
+    r[e] = __fmaf_rn(yq, f[e], RMAGIC);                              // RNE(yq * f) + RMAGIC, saturated below
+  }
+  return pack4_sat(r[0], r[1], r[2], r[3]);
+}
+
 // Fast path for power-of-two output scales (every minmax-calibrated model): LPR lanes share a row (8, 16 or 32, so a
 // lane owns >= 12 channels and the per-row scalar work - three IEEE divisions and a square root - is amortised), the
 // per-channel constants live in registers for the whole persistent loop, and every division by a scale is folded into
@@ -277,6 +303,16 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
   }
   const float Cf = float(a.C), s1 = a.in_scale_min, s1c = fdiv(s1, Cf);
   const float clamp_hi = a.clamp_mid ? 127.f : __int_as_float(0x7f800000);
+  float gmin = __int_as_float(0x7f800000), gmax = 0.f;     // bounds of |g'| over the row's channels (NaN-free: fminf / fmaxf drop NaN)
+#pragma unroll
+  for (int i = 0; i < WPLN; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { gmin = fminf(gmin, fabsf(g[i][e])); gmax = fmaxf(gmax, fabsf(g[i][e])); }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  }
   for (int row = warp_global * GPW + grp; row < a.rows; row += row_stride) {
     const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
     int xv[WPLN][4];
@@ -299,25 +335,23 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
     const float t = fdiv(s1, stdv);
     const float mos = fdiv(mean, stdv);
     uint32_t* orow = reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(a.out_row_map ? __ldg(a.out_row_map + row) : row) * a.C);
-    // floor(log2|A|) is the float exponent except within 16 ulps below a power of two (floor_log2_as_fp32); rows where
-    // some channel is that close take the second instantiation, so the common loop has no branch per element.
-    bool slow = false;
+    // Fast element loop (ln_pot_fast_word): no conversion / rounding instruction except one FRND.  It needs every |A| = |t*g'| in
+    // [2^-24, 2^8) (N = 7 - floor(log2|A|) unclamped) - checked per row against the row-independent bounds of |g'| - and no
+    // mantissa of A within 16 ulps below a power of two (floor_log2_as_fp32's corner) - collected by the loop itself.  Rows that
+    // fail either test (or have std == 0 / non-finite statistics) are redone with the reference-order code.
+    const bool in_range = fmul(t, gmax) < 256.f && fmul(t, gmin) >= 0x1p-24f;
+    uint32_t qw[WPLN];
+    uint32_t mant_max = 0;
+    if (in_range) {
 #pragma unroll
-    for (int i = 0; i < WPLN; ++i)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t ab = __float_as_uint(fmul(t, g[i][e])) & 0x7fffffffu;
-        slow |= ((ab & 0x007fffffu) >= 0x007ffff0u) & (ab < 0x7f800000u);
-      }
-    if (!slow) {
-#pragma unroll
-      for (int i = 0; i < WPLN; ++i)
-        orow[sub + LPR * i] = ln_pot_word<false>(t, mos, g[i], bt[i], f[i], xv[i], clamp_hi);
-    } else {
-#pragma unroll
-      for (int i = 0; i < WPLN; ++i)
-        orow[sub + LPR * i] = ln_pot_word<true>(t, mos, g[i], bt[i], f[i], xv[i], clamp_hi);
+      for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_fast_word(t, mos, g[i], bt[i], f[i], xv[i], a.clamp_mid != 0, mant_max);
     }
+    if (!in_range || mant_max >= 0x007ffff0u) {
+#pragma unroll
+      for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_word<true>(t, mos, g[i], bt[i], f[i], xv[i], clamp_hi);
+    }
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) orow[sub + LPR * i] = qw[i];
   }
 }
 
