@@ -21,6 +21,7 @@
 //
 // Same results, bit for bit, as gemm_tc.cu / gemm_simt.cu (tests/test_gpu_ops.py cross-checks the three).
 #include <algorithm>
+#include <cstdlib>
 #include "tc_common.cuh"
 #include "epilogue.cuh"
 
@@ -33,36 +34,61 @@ constexpr int P_THREADS = 128 + P_EPI_WARPS * 32;   // warpgroup 0: TMA producer
 constexpr int P_ACC_COLS = 256;          // TMEM columns per accumulator stage
 constexpr uint32_t P_A_BYTES = PBM * PBK;
 constexpr uint32_t P_B_BYTES = 128 * PBK;   // room for BN/2 <= 128 rows of W
-constexpr uint32_t P_STAGE_BYTES = P_A_BYTES + P_B_BYTES;
-constexpr uint32_t P_WARP_STG = 32 * 64;    // staging bytes per warp: 32 rows x <= 64 columns
-constexpr uint32_t P_SLOT_BYTES = P_EPI_WARPS * P_WARP_STG;   // one full-width staging slot (W = 64)
+
 constexpr float RMAGIC_LO = RMAGIC - 128.f, RMAGIC_HI = RMAGIC + 127.f;
 
 struct PairGeom {
   int BN;        // columns per pair tile
   int W;         // columns per epilogue warp = BN / 4 (32, 48 or 64)
-  int tiles_n, tiles;   // pair tiles
+  int tiles_m, tiles_n, tiles;   // pair tiles
   int nkb;       // k blocks
   int swz;       // staging swizzle: 0 none (48-byte rows), 1 SWIZZLE_32B, 2 SWIZZLE_64B
   int nslot_log2;   // RESIDUAL: residual / output staging slots in flight (2 or 4 slots of 512 * W bytes)
+  int nstages;      // operand ring depth (<= P_MAX_STAGES)
+  int bres;         // 1: this CTA's half of the W column tile (all of K) stays resident in shared memory, only A streams;
+                    //    tiles are then walked row-block fastest in one contiguous range per CTA pair, so W is reloaded only
+                    //    when the range crosses into the next column tile.  0: A and W stream together, tiles column fastest.
+  uint32_t stage_bytes, off_bres, off_stg, off_prm;   // shared-memory layout relative to the 1024-aligned base
 };
+constexpr int P_MAX_STAGES = 8;
+
 // -DPAIR_TRACE (tools/pair_trace.py): CTA pair 0 writes clock64 stamps of its producer / MMA / first epilogue warp per tile
 // into the buffer passed as out_f32; not compiled into the product library.
 #ifdef PAIR_TRACE
 #define PTRACE(role, tile, slot_)                                                                                   \
   do {                                                                                                              \
     if (p.out_f32 != nullptr && pair == 0 && (tile) < 64)                                                           \
-      reinterpret_cast<long long*>(p.out_f32)[((int(rank) * 3 + (role)) * 64 + int(tile)) * 4 + (slot_)] = clock64(); \
+      reinterpret_cast<long long*>(p.out_f32)[((int(rank) * 19 + (role)) * 64 + int(tile)) * 4 + (slot_)] = clock64(); \
   } while (0)
 #else
 #define PTRACE(role, tile, slot_) do {} while (0)
 #endif
-struct TileIter {   // pair tiles t = pair, pair + npairs, ... as (row block, column block), column fastest
-  int mt, nt, dm, dn, tiles_n;
-  __device__ TileIter(uint32_t pair, uint32_t npairs, int tn) : mt(int(pair) / tn), nt(int(pair) % tn), dm(int(npairs) / tn), dn(int(npairs) % tn), tiles_n(tn) {}
+
+// The pair's tiles in execution order.  Streaming mode: t = pair, pair + npairs, ... with the column block fastest (the pairs
+// running at the same time share A row blocks through L2).  Resident-W mode: the contiguous range [pair*T/P, (pair+1)*T/P) of
+// the row-block-fastest order, so the column block changes at most a few times per pair.
+struct TileIter {
+  int mt, nt, left;      // current tile, tiles left including it
+  int dm, dn, tiles_m, tiles_n, bres;
+  __device__ TileIter(const PairGeom& g, uint32_t pair, uint32_t npairs) : tiles_m(g.tiles_m), tiles_n(g.tiles_n), bres(g.bres) {
+    if (bres) {
+      const long long T = g.tiles;
+      const int t0 = int(T * pair / npairs), t1 = int(T * (pair + 1) / npairs);
+      left = t1 - t0;
+      nt = t0 / tiles_m; mt = t0 % tiles_m; dm = dn = 0;
+    } else {
+      left = int(pair) < g.tiles ? (g.tiles - 1 - int(pair)) / int(npairs) + 1 : 0;
+      mt = int(pair) / tiles_n; nt = int(pair) % tiles_n; dm = int(npairs) / tiles_n; dn = int(npairs) % tiles_n;
+    }
+  }
   __device__ void next() {
-    nt += dn; mt += dm;
-    if (nt >= tiles_n) { nt -= tiles_n; ++mt; }
+    --left;
+    if (bres) {
+      if (++mt == tiles_m) { mt = 0; ++nt; }
+    } else {
+      nt += dn; mt += dm;
+      if (nt >= tiles_n) { nt -= tiles_n; ++mt; }
+    }
   }
 };
 
@@ -159,9 +185,11 @@ __device__ __forceinline__ float quant_pot(float x) { return fadd(x, RMAGIC); }
 
 // One chunk: 16 accumulator columns of one row -> 16 output codes (4 packed words).  prm = this warp's table + the
 // chunk's column offset.  `resx` = the row's 16 residual codes with the sign bits flipped (code + 128 as u8).
-template <int EPI, bool POT, bool EXACT>
-__device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const int (&acc)[16], const uint4 resx, uint4& out,
-                                           uint32_t& flag) {
+// Columns are processed four at a time; a group in which some column's reciprocal bounds disagree (a quotient within a few
+// ulps of a rounding tie, ~1e-5 of the quotients) is redone on the spot with the IEEE division for those columns - the branch
+// is short and keeps no extra state alive, so a hit costs a few hundred cycles of one warp instead of stalling the tile.
+template <int EPI, bool POT>
+__device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const int (&acc)[16], const uint4 resx, uint4& out) {
   uint32_t ow[4];
   const uint32_t rw[4] = {resx.x, resx.y, resx.z, resx.w};
 #pragma unroll
@@ -179,21 +207,25 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
       const float4 f4 = *reinterpret_cast<const float4*>(prm + PR_ROHI * 64 + j4);
       const float MLv[4] = {a4.x, a4.y, a4.z, a4.w}, MHv[4] = {b4.x, b4.y, b4.z, b4.w}, Mv[4] = {c4.x, c4.y, c4.z, c4.w};
       const float RSv[4] = {d4.x, d4.y, d4.z, d4.w}, OLv[4] = {e4.x, e4.y, e4.z, e4.w}, OHv[4] = {f4.x, f4.y, f4.z, f4.w};
-      float Ov[4] = {1.f, 1.f, 1.f, 1.f};
-      if (EXACT) {
-        const float4 g4 = *reinterpret_cast<const float4*>(prm + PR_RO_ * 64 + j4);
-        Ov[0] = g4.x; Ov[1] = g4.y; Ov[2] = g4.z; Ov[3] = g4.w;
-      }
+      float y[4], r[4];
+      uint32_t flag = 0;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float af = __int2float_rn(acc[j4 + e]);
-        const float y = POT ? __fmaf_rn(af, Sv[e], Bv[e]) : fadd(fmul(af, Sv[e]), Bv[e]);
-        const float k = fsub(quant_iv<EXACT, true>(y, MLv[e], MHv[e], Mv[e], flag), RMAGIC);        // qact after the GEMM (code)
-        const float tt = fmul(k, Mv[e]);
+        y[e] = POT ? __fmaf_rn(af, Sv[e], Bv[e]) : fadd(fmul(af, Sv[e]), Bv[e]);
+        const float k = fsub(quant_iv<false, true>(y[e], MLv[e], MHv[e], Mv[e], flag), RMAGIC);        // qact after the GEMM (code)
         // residual code: byte e of the word (sign already flipped) -> 2^23 + (code + 128) -> code, exactly
-        const float r = fsub(__uint_as_float(__byte_perm(rw[j4 >> 2], 0x4B000000u, 0x7540 + e)), 8388736.f);
-        const float z = fadd(fmul(r, RSv[e]), tt);
-        t[e] = quant_iv<EXACT>(z, OLv[e], OHv[e], Ov[e], flag);
+        r[e] = fmul(fsub(__uint_as_float(__byte_perm(rw[j4 >> 2], 0x4B000000u, 0x7540 + e)), 8388736.f), RSv[e]);
+        t[e] = quant_iv<false>(fadd(r[e], fmul(k, Mv[e])), OLv[e], OHv[e], 1.f, flag);
+      }
+      if (flag) {
+        const float4 g4 = *reinterpret_cast<const float4*>(prm + PR_RO_ * 64 + j4);
+        const float Ov[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float k = fsub(quant_iv<true, true>(y[e], MLv[e], MHv[e], Mv[e], flag), RMAGIC);
+          t[e] = quant_iv<true>(fadd(r[e], fmul(k, Mv[e])), OLv[e], OHv[e], Ov[e], flag);
+        }
       }
     } else if (POT && EPI == P2V_EPI_REQUANT) {
 #pragma unroll
@@ -210,60 +242,23 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
       const float4 a4 = *reinterpret_cast<const float4*>(prm + PR_OLO * 64 + j4);
       const float4 b4 = *reinterpret_cast<const float4*>(prm + PR_OHI * 64 + j4);
       const float OLv[4] = {a4.x, a4.y, a4.z, a4.w}, OHv[4] = {b4.x, b4.y, b4.z, b4.w};
-      float Ov[4] = {1.f, 1.f, 1.f, 1.f};
-      if (EXACT) {
-        const float4 g4 = *reinterpret_cast<const float4*>(prm + PR_O * 64 + j4);
-        Ov[0] = g4.x; Ov[1] = g4.y; Ov[2] = g4.z; Ov[3] = g4.w;
-      }
+      float y[4];
+      uint32_t flag = 0;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float y = fadd(fmul(__int2float_rn(acc[j4 + e]), Sv[e]), Bv[e]);
-        if (EPI == P2V_EPI_GELU) y = gelu_erf(y);
-        t[e] = quant_iv<EXACT>(y, OLv[e], OHv[e], Ov[e], flag);
+        y[e] = fadd(fmul(__int2float_rn(acc[j4 + e]), Sv[e]), Bv[e]);
+        if (EPI == P2V_EPI_GELU) y[e] = gelu_erf(y[e]);
+        t[e] = quant_iv<false>(y[e], OLv[e], OHv[e], 1.f, flag);
+      }
+      if (flag) {
+        const float4 g4 = *reinterpret_cast<const float4*>(prm + PR_O * 64 + j4);
+        const float Ov[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t[e] = quant_iv<true>(y[e], OLv[e], OHv[e], Ov[e], flag);
       }
     }
     ow[j4 >> 2] = pack4_sat(t[0], t[1], t[2], t[3]);
   }
-  out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-}
-
-// The rare second pass of a chunk (some column's reciprocal bounds disagreed): the same arithmetic with the IEEE division
-// where needed, 4 columns at a time in a rolled loop over private copies so that it costs the fast path no registers.
-template <int EPI, bool POT>
-__device__ __noinline__ void pair_chunk_exact_words(const float* __restrict__ prm, const int* __restrict__ acc, const uint32_t* __restrict__ rw,
-                                                    uint32_t* __restrict__ ow) {
-#pragma unroll 1
-  for (int j4 = 0; j4 < 16; j4 += 4) {
-    float t[4];
-    uint32_t flag = 0;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = j4 + e;
-      const float af = __int2float_rn(acc[c]);
-      const float S = prm[PR_S * 64 + c], B = prm[PR_B * 64 + c];
-      if (EPI == P2V_EPI_RESIDUAL) {
-        const float y = POT ? __fmaf_rn(af, S, B) : fadd(fmul(af, S), B);
-        const float M = prm[PR_M * 64 + c];
-        const float k = fsub(quant_iv<true, true>(y, prm[PR_MLO * 64 + c], prm[PR_MHI * 64 + c], M, flag), RMAGIC);
-        const float r = fsub(__uint_as_float(__byte_perm(rw[j4 >> 2], 0x4B000000u, 0x7540 + e)), 8388736.f);
-        const float z = fadd(fmul(r, prm[PR_RS * 64 + c]), fmul(k, M));
-        t[e] = quant_iv<true>(z, prm[PR_ROLO * 64 + c], prm[PR_ROHI * 64 + c], prm[PR_RO_ * 64 + c], flag);
-      } else {
-        float y = fadd(fmul(af, S), B);
-        if (EPI == P2V_EPI_GELU) y = gelu_erf(y);
-        t[e] = quant_iv<true>(y, prm[PR_OLO * 64 + c], prm[PR_OHI * 64 + c], prm[PR_O * 64 + c], flag);
-      }
-    }
-    ow[j4 >> 2] = pack4_sat(t[0], t[1], t[2], t[3]);
-  }
-}
-template <int EPI, bool POT>
-__device__ __forceinline__ void pair_chunk_exact(const float* __restrict__ prm, const int (&acc)[16], const uint4 resx, uint4& out) {
-  int a[16];
-  uint32_t rw[4] = {resx.x, resx.y, resx.z, resx.w}, ow[4];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) a[j] = acc[j];
-  pair_chunk_exact_words<EPI, POT>(prm, a, rw, ow);
   out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
@@ -299,31 +294,32 @@ __device__ __forceinline__ void store_col(float* prm, int c, const RawCol& r) {
   }
 }
 
-template <int STAGES, int EPI, bool POT>
+template <int EPI, bool POT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                  const __grid_constant__ CUtensorMap tmR, EpiParams p, PairGeom g) {
   constexpr bool RESID = EPI == P2V_EPI_RESIDUAL;
-  constexpr int NSLOT = RESID ? 2 : 1;            // staging bytes in units of full-width slots
   constexpr int ROWS = prm_rows<EPI, POT>();
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 12];
+  __shared__ __align__(8) uint64_t bars[2 * P_MAX_STAGES + 13];
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const uint32_t ring = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t stg = ring + STAGES * P_STAGE_BYTES;
-  float* prm_all = reinterpret_cast<float*>(smem_raw + (stg - smem_u32(smem_raw)) + NSLOT * P_SLOT_BYTES);
-  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
-  const uint32_t bar_tfull = smem_u32(&bars[2 * STAGES]), bar_tempty = bar_tfull + 16;
+  const uint32_t bres_base = ring + g.off_bres, stg = ring + g.off_stg;
+  float* prm_all = reinterpret_cast<float*>(smem_raw + (ring - smem_u32(smem_raw)) + g.off_prm);
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[P_MAX_STAGES]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * P_MAX_STAGES]), bar_tempty = bar_tfull + 16;
   const uint32_t bar_rfull = bar_tfull + 32, bar_sempty = bar_tfull + 64;     // up to 4 residual slots each
+  const uint32_t bar_bfull = bar_tfull + 96;                                   // resident W tile loaded
   const uint32_t slot_bytes = uint32_t(P_EPI_WARPS) * 32u * uint32_t(g.W), warp_stg = 32u * uint32_t(g.W);
   const uint32_t slot_mask = (1u << g.nslot_log2) - 1u;
+  const uint32_t nstages = uint32_t(g.nstages), bhalf_bytes = uint32_t(g.BN / 2) * PBK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < P_MAX_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 2 * P_EPI_WARPS);     // every epilogue warp of both CTAs
@@ -332,6 +328,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(bar_rfull + 8 * a, 1);
       mbar_init(bar_sempty + 8 * a, P_EPI_WARPS);
     }
+    mbar_init(bar_bfull, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_pair(smem_u32(&tmem_slot), 512);
@@ -341,72 +338,105 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  // XX = 1 control warp + 4 epilogue warps -> 24 + 4 * 120 registers per lane
+  // Register file: 16 K registers per SM sub-partition hold 1 control warp + 4 epilogue warps.  The kernel starts with 96 per
+  // lane (640 threads); the control warps keep 32 and the epilogue warps grow to 112 out of the CTA's own pool.
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    if (lane == 0) {
-      tma_prefetch_map(&tmA);
-      tma_prefetch_map(&tmB);
-      if (RESID) tma_prefetch_map(&tmR);
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    {     // the whole warp walks the loop; one elected lane issues (see elect_one)
+      if (elect_one()) {
+        tma_prefetch_map(&tmA);
+        tma_prefetch_map(&tmB);
+        if (RESID) tma_prefetch_map(&tmR);
+      }
       const uint32_t full0 = mapa_u32(bar_full, 0);       // the leader's full barriers collect both CTAs' bytes
-      const uint32_t bhalf_bytes = uint32_t(g.BN / 2) * PBK;
+      const uint32_t bfull0 = mapa_u32(bar_bfull, 0);
       uint32_t itk = 0, it = 0;
-      TileIter ti(pair, npairs, g.tiles_n);
-      for (uint32_t t = pair; t < uint32_t(g.tiles); t += npairs, ++it, ti.next()) {
+      int cur_nt = -1;
+      for (TileIter ti(g, pair, npairs); ti.left > 0; ti.next(), ++it) {
         const int mt = ti.mt, nt = ti.nt;
         const int m0 = mt * 256 + int(rank) * PBM, nb0 = nt * g.BN + int(rank) * (g.BN / 2);
         PTRACE(2, it, 0);
+        if (g.bres && nt != cur_nt) {
+          // new column tile: every MMA that reads the old W tile has completed once the stage filled last is free again
+          if (itk > 0) mbar_wait(bar_empty + 8 * ((itk - 1) % nstages), ((itk - 1) / nstages) & 1u);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(bar_bfull, 2u * uint32_t(g.nkb) * bhalf_bytes);
+            for (int kb = 0; kb < g.nkb; ++kb) tma_load_2d_pair(bres_base + kb * bhalf_bytes, &tmB, bfull0, kb * PBK, nb0);
+          }
+          __syncwarp();
+          cur_nt = nt;
+        }
         for (int kb = 0; kb < g.nkb; ++kb, ++itk) {
-          const uint32_t s = itk % STAGES, ph = (itk / STAGES) & 1u;
+          const uint32_t s = itk % nstages, ph = (itk / nstages) & 1u;
           mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-          if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2u * (P_A_BYTES + bhalf_bytes));
-          const uint32_t sa = ring + s * P_STAGE_BYTES;
-          tma_load_2d_pair(sa, &tmA, full0 + 8 * s, kb * PBK, m0);
-          tma_load_2d_pair(sa + P_A_BYTES, &tmB, full0 + 8 * s, kb * PBK, nb0);
+          const uint32_t sa = ring + s * g.stage_bytes;
+          if (elect_one()) {
+            if (g.bres) {
+              if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2u * P_A_BYTES);
+              tma_load_2d_pair(sa, &tmA, full0 + 8 * s, kb * PBK, m0);
+            } else {
+              if (rank == 0) mbar_expect_tx(bar_full + 8 * s, 2u * (P_A_BYTES + bhalf_bytes));
+              tma_load_2d_pair(sa, &tmA, full0 + 8 * s, kb * PBK, m0);
+              tma_load_2d_pair(sa + P_A_BYTES, &tmB, full0 + 8 * s, kb * PBK, nb0);
+            }
+          }
+          __syncwarp();
         }
         PTRACE(2, it, 1);
         if (RESID) {   // residual codes of this tile, straight into the staging slot the epilogue will overwrite
           const uint32_t slot = it & slot_mask, u = it >> g.nslot_log2;
           mbar_wait(bar_sempty + 8 * slot, (u & 1u) ^ 1u);
-          mbar_expect_tx(bar_rfull + 8 * slot, slot_bytes);
-          for (int e = 0; e < P_EPI_WARPS; ++e) {
-            const int q = e & 3, cg = e >> 2;
-            tma_load_2d(stg + slot * slot_bytes + e * warp_stg, &tmR, bar_rfull + 8 * slot, nt * g.BN + cg * g.W, m0 + q * 32);
+          if (elect_one()) {
+            mbar_expect_tx(bar_rfull + 8 * slot, slot_bytes);
+            for (int e = 0; e < P_EPI_WARPS; ++e) {
+              const int q = e & 3, cg = e >> 2;
+              tma_load_2d(stg + slot * slot_bytes + e * warp_stg, &tmR, bar_rfull + 8 * slot, nt * g.BN + cg * g.W, m0 + q * 32);
+            }
           }
+          __syncwarp();
           PTRACE(2, it, 2);
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only) =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    if (lane == 0 && rank == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (rank == 0) {      // warp-uniform loop, one elected lane issues the MMAs and their commits
       const uint32_t idesc = make_i8_idesc(256, g.BN, true, true);
-      uint32_t itk = 0, it = 0;
-      for (uint32_t t = pair; t < uint32_t(g.tiles); t += npairs, ++it) {
+      uint32_t itk = 0, it = 0, reloads = 0;
+      int cur_nt = -1;
+      for (TileIter ti(g, pair, npairs); ti.left > 0; ti.next(), ++it) {
         const uint32_t a = it & 1u, use = it >> 1;
         PTRACE(0, it, 0);
-        mbar_wait(bar_tempty + 8 * a, (use & 1u) ^ 1u);
+        mbar_wait_poll(bar_tempty + 8 * a, (use & 1u) ^ 1u);     // arrivals come from both CTAs: poll, never suspend
+        if (g.bres && ti.nt != cur_nt) {
+          mbar_wait_poll(bar_bfull, reloads & 1u);
+          ++reloads;
+          cur_nt = ti.nt;
+        }
         tc_fence_after();
         PTRACE(0, it, 1);
         const uint32_t d_tmem = tmem_base + a * P_ACC_COLS;
         for (int kb = 0; kb < g.nkb; ++kb, ++itk) {
-          const uint32_t s = itk % STAGES, ph = (itk / STAGES) & 1u;
-          mbar_wait(bar_full + 8 * s, ph);
+          const uint32_t s = itk % nstages, ph = (itk / nstages) & 1u;
+          mbar_wait_poll(bar_full + 8 * s, ph);
           tc_fence_after();
-          const uint32_t sa = ring + s * P_STAGE_BYTES, sb = sa + P_A_BYTES;
+          const uint32_t sa = ring + s * g.stage_bytes, sb = g.bres ? bres_base + kb * bhalf_bytes : sa + P_A_BYTES;
           const int ksteps = min(PBK / 32, (p.K - kb * PBK + 31) / 32);
-          for (int k = 0; k < ksteps; ++k)
-            umma_i8_pair(d_tmem, make_kmajor_sw128_desc(sa + k * 32), make_kmajor_sw128_desc(sb + k * 32), idesc, uint32_t(kb > 0 || k > 0));
-          tc_commit_pair(bar_empty + 8 * s, 3);    // both CTAs' producers may refill the stage
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k)
+              umma_i8_pair(d_tmem, make_kmajor_sw128_desc(sa + k * 32), make_kmajor_sw128_desc(sb + k * 32), idesc, uint32_t(kb > 0 || k > 0));
+            tc_commit_pair(bar_empty + 8 * s, 3);    // both CTAs' producers may refill the stage
+            if (kb == g.nkb - 1) tc_commit_pair(bar_tfull + 8 * a, 3);      // accumulator complete in both CTAs' TMEM
+          }
+          __syncwarp();
         }
-        tc_commit_pair(bar_tfull + 8 * a, 3);      // accumulator complete in both CTAs' TMEM
         PTRACE(0, it, 2);
       }
     }
   } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
   } else {
     // ================= epilogue: 16 warps, warp = 32 rows x W columns =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
@@ -420,38 +450,41 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t row_off = uint32_t(lane) * uint32_t(W);
     const uint32_t xr = g.swz == 2 ? (uint32_t(lane) >> 1) & 3u : (g.swz == 1 ? (uint32_t(lane) >> 2) & 1u : 0u);
     RawCol nx0, nx1;
-    TileIter ti(pair, npairs, g.tiles_n);
+    TileIter ti(g, pair, npairs);
     {
       const int n0 = ti.nt * g.BN + cg * W;
-      nx0 = load_raw_col<EPI>(p, n0 + lane, pair < uint32_t(g.tiles));
-      nx1 = load_raw_col<EPI>(p, n0 + 32 + lane, pair < uint32_t(g.tiles) && 32 + lane < W);
+      nx0 = load_raw_col<EPI>(p, n0 + lane, ti.left > 0);
+      nx1 = load_raw_col<EPI>(p, n0 + 32 + lane, ti.left > 0 && 32 + lane < W);
     }
     uint32_t it = 0;
+    int prm_nt = -1;           // column tile whose constants the warp's table holds
     int pending_slot = -1;     // RESID: staging slot whose store has been issued but not yet released to the producer
-    for (uint32_t t = pair; t < uint32_t(g.tiles); t += npairs, ++it) {
+    for (; ti.left > 0; ++it) {
       const int mt = ti.mt, nt = ti.nt;
       ti.next();
       const int m0 = mt * 256 + int(rank) * PBM + int(quarter) * 32, n0 = nt * g.BN + cg * W;
       const uint32_t a = it & 1u, use = it >> 1;
       const uint32_t slot = RESID ? (it & slot_mask) : 0u, ruse = it >> g.nslot_log2;
       const uint32_t my_stg = stg + slot * slot_bytes + uint32_t(e) * warp_stg;
-      // this tile's column constants (fetched during the previous tile), then fetch the next tile's
-      __syncwarp();
-      store_col<EPI, POT>(prm, lane, nx0);
-      if (32 + lane < W) store_col<EPI, POT>(prm, 32 + lane, nx1);
-      __syncwarp();
-      {
-        const uint32_t tn = t + npairs;
-        const int nn0 = ti.nt * g.BN + cg * W;
-        nx0 = load_raw_col<EPI>(p, nn0 + lane, tn < uint32_t(g.tiles));
-        nx1 = load_raw_col<EPI>(p, nn0 + 32 + lane, tn < uint32_t(g.tiles) && 32 + lane < W);
+      // this tile's column constants (fetched during the previous tile) into the table, then fetch the next tile's
+      if (nt != prm_nt) {
+        __syncwarp();
+        store_col<EPI, POT>(prm, lane, nx0);
+        if (32 + lane < W) store_col<EPI, POT>(prm, 32 + lane, nx1);
+        __syncwarp();
+        prm_nt = nt;
       }
-      if (e == 0 && lane == 0) PTRACE(1, it, 0);
+      if (ti.left > 0 && ti.nt != nt) {
+        const int nn0 = ti.nt * g.BN + cg * W;
+        nx0 = load_raw_col<EPI>(p, nn0 + lane, true);
+        nx1 = load_raw_col<EPI>(p, nn0 + 32 + lane, 32 + lane < W);
+      }
+      if (lane == 0) PTRACE(3 + e, it, 0);
       if (RESID) mbar_wait(bar_rfull + 8 * slot, ruse & 1u);
-      if (e == 0 && lane == 0) PTRACE(1, it, 1);
+      if (lane == 0) PTRACE(3 + e, it, 1);
       mbar_wait(bar_tfull + 8 * a, use & 1u);
       tc_fence_after();
-      if (e == 0 && lane == 0) PTRACE(1, it, 2);
+      if (lane == 0) PTRACE(3 + e, it, 2);
       const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + a * P_ACC_COLS + uint32_t(cg * W);
       int accA[16], accB[16];
       tmem_ld16_async(taddr, accA);
@@ -473,11 +506,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           resx.x ^= 0x80808080u; resx.y ^= 0x80808080u; resx.z ^= 0x80808080u; resx.w ^= 0x80808080u;
         }
         uint4 o;
-        uint32_t flag = 0;
-        pair_chunk<EPI, POT, false>(prm + c * 16, cur, resx, o, flag);
-        if (!(POT && EPI != P2V_EPI_RESIDUAL)) {
-          if (flag) pair_chunk_exact<EPI, POT>(prm + c * 16, cur, resx, o);
-        }
+        pair_chunk<EPI, POT>(prm + c * 16, cur, resx, o);
         if (c == 0) {
           if (!RESID) {                     // the previous tile's store must have finished reading this block
             if (lane == 0) bulk_wait_read0();
@@ -496,17 +525,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {        // always lane 0 of the converged warp: the bulk group and its waits belong to that lane
         tma_store_2d(&tmO, my_stg, n0, m0);
         bulk_commit();
-        if (e == 0) PTRACE(1, it, 3);
+        PTRACE(3 + e, it, 3);
       }
+      __syncwarp();
       if (RESID) pending_slot = int(slot);
     }
-    if (lane == 0) {
-      bulk_wait_all();
-      // no arrive on bar_sempty here: the producer has no further tile to load
-    }
+    if (lane == 0) bulk_wait_all();    // no arrive on bar_sempty: the producer has no further tile to load
   }
   tc_fence_before();
   __syncthreads();
@@ -552,17 +579,40 @@ static int max_pairs() {
   return cached;
 }
 
-template <int STAGES, int EPI, bool POT>
-static int launch_pair(const p2v_gemm_args& a, const PairGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+constexpr size_t P_SMEM_BUDGET = 227 * 1024 - 1024;    // dynamic shared memory per CTA, static part and slack taken off
+
+template <int EPI, bool POT>
+static int launch_pair(const p2v_gemm_args& a, PairGeom g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                        const CUtensorMap& tmR, cudaStream_t stream) {
-  constexpr int NSLOT = EPI == P2V_EPI_RESIDUAL ? 2 : 1;
-  constexpr size_t smem = 1024 + size_t(STAGES) * P_STAGE_BYTES + NSLOT * P_SLOT_BYTES + size_t(P_EPI_WARPS) * prm_rows<EPI, POT>() * 64 * 4;
-  static_assert(smem <= 227 * 1024 - 512, "shared memory budget");
-  auto kern = gemm_pair_kernel<STAGES, EPI, POT>;
+  // shared-memory plan: [operand ring][resident W half-tile][output / residual staging][16 warp-private constant tables]
+  const size_t prm_bytes = size_t(P_EPI_WARPS) * prm_rows<EPI, POT>() * 64 * 4;
+  const size_t bhalf = size_t(g.BN / 2) * PBK;
+  static const int force_bres = getenv("P2V_PAIR_BRES") ? atoi(getenv("P2V_PAIR_BRES")) : -1;    // perf triage only
+  for (;;) {
+    const size_t stg_bytes = (size_t(1) << g.nslot_log2) * P_EPI_WARPS * 32 * g.W;
+    const size_t fixed = 1024 + prm_bytes + stg_bytes;
+    const size_t bres_bytes = size_t(g.nkb) * bhalf;
+    const bool fits = fixed + bres_bytes + 3 * P_A_BYTES <= P_SMEM_BUDGET;
+    if (!fits && EPI == P2V_EPI_RESIDUAL && g.nslot_log2 == 2 && fixed - stg_bytes / 2 + bres_bytes + 3 * P_A_BYTES <= P_SMEM_BUDGET) {
+      g.nslot_log2 = 1;        // a resident W tile is worth more than the two extra residual slots
+      continue;
+    }
+    g.bres = (fits && force_bres != 0) ? 1 : 0;
+    g.stage_bytes = uint32_t(P_A_BYTES + (g.bres ? 0 : P_B_BYTES));
+    const size_t ring_room = P_SMEM_BUDGET - fixed - (g.bres ? bres_bytes : 0);
+    g.nstages = int(std::min<size_t>(P_MAX_STAGES, ring_room / g.stage_bytes));
+    P2V_REQUIRE(g.nstages >= 2, "gemm_pair: no room for the operand ring (K=%d N=%d)", a.K, a.N);
+    g.off_bres = uint32_t(g.nstages) * g.stage_bytes;
+    g.off_stg = g.off_bres + uint32_t(g.bres ? bres_bytes : 0);
+    g.off_prm = g.off_stg + uint32_t(stg_bytes);
+    break;
+  }
+  const size_t smem = 1024 + g.off_prm + prm_bytes;
+  auto kern = gemm_pair_kernel<EPI, POT>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    P2V_REQUIRE(e == cudaSuccess, "gemm_pair: cannot set %zu bytes of dynamic shared memory: %s", smem, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P_SMEM_BUDGET));
+    P2V_REQUIRE(e == cudaSuccess, "gemm_pair: cannot set %zu bytes of dynamic shared memory: %s", P_SMEM_BUDGET, cudaGetErrorString(e));
     attr = true;
   }
   const int grid = 2 * std::min(g.tiles, max_pairs());
@@ -587,6 +637,7 @@ int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
   PairGeom g;
   g.BN = best_bn;
   g.W = best_bn / 4;
+  g.tiles_m = tiles_m;
   g.tiles_n = (a.N + best_bn - 1) / best_bn;
   g.tiles = tiles_m * g.tiles_n;
   g.nkb = (a.K + PBK - 1) / PBK;
@@ -603,14 +654,14 @@ int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
   const bool pot = a.pot_scales != 0;
   switch (a.epilogue) {
     case P2V_EPI_REQUANT:
-      return pot ? launch_pair<5, P2V_EPI_REQUANT, true>(a, g, tmA, tmB, tmO, tmR, stream)
-                 : launch_pair<5, P2V_EPI_REQUANT, false>(a, g, tmA, tmB, tmO, tmR, stream);
+      return pot ? launch_pair<P2V_EPI_REQUANT, true>(a, g, tmA, tmB, tmO, tmR, stream)
+                 : launch_pair<P2V_EPI_REQUANT, false>(a, g, tmA, tmB, tmO, tmR, stream);
     case P2V_EPI_GELU:
-      return pot ? launch_pair<5, P2V_EPI_GELU, true>(a, g, tmA, tmB, tmO, tmR, stream)
-                 : launch_pair<5, P2V_EPI_GELU, false>(a, g, tmA, tmB, tmO, tmR, stream);
+      return pot ? launch_pair<P2V_EPI_GELU, true>(a, g, tmA, tmB, tmO, tmR, stream)
+                 : launch_pair<P2V_EPI_GELU, false>(a, g, tmA, tmB, tmO, tmR, stream);
     default:
-      return pot ? launch_pair<3, P2V_EPI_RESIDUAL, true>(a, g, tmA, tmB, tmO, tmR, stream)
-                 : launch_pair<3, P2V_EPI_RESIDUAL, false>(a, g, tmA, tmB, tmO, tmR, stream);
+      return pot ? launch_pair<P2V_EPI_RESIDUAL, true>(a, g, tmA, tmB, tmO, tmR, stream)
+                 : launch_pair<P2V_EPI_RESIDUAL, false>(a, g, tmA, tmB, tmO, tmR, stream);
   }
 }
 

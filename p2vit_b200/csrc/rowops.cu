@@ -1,6 +1,7 @@
 // HBM-bound element / row kernels: QAct quantize & fake-quant, patch gather, integer LayerNorm,
 // stand-alone integer log2-softmax, calibration reductions.  Reference call sites are cited in
 // include/p2vit_b200.h next to each entry point.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace p2v {
@@ -240,6 +241,33 @@ __device__ __forceinline__ uint32_t ln_pot_word(float t, float mos, const float 
   return pack4_s8(q[0], q[1], q[2], q[3]);
 }
 
+// one lane's words of a row through ln_pot_word<true>, every constant re-derived from global memory as the kernel prologue does
+__device__ __noinline__ void ln_pot_row_slow(const p2v_layernorm_args& a, const uint32_t* __restrict__ xr, uint32_t* __restrict__ orow, int sub,
+                                             int lpr, int wpln, float t, float mos, float clamp_hi) {
+  const float rnext = fdiv(1.f, a.next_scale);
+  for (int i = 0; i < wpln; ++i) {
+    const int w = sub + lpr * i;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma) + w), b4 = __ldg(reinterpret_cast<const float4*>(a.beta) + w);
+    const float4 o4 = __ldg(reinterpret_cast<const float4*>(a.out_scale) + w), p4 = __ldg(reinterpret_cast<const float4*>(a.post_div) + w);
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.in_mult) + w);
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, oo[4] = {o4.x, o4.y, o4.z, o4.w};
+    const float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+    const uint32_t u = __ldg(xr + w);
+    const int cx[4] = {int(int8_t(u & 0xff)), int(int8_t((u >> 8) & 0xff)), int(int8_t((u >> 16) & 0xff)), int(int8_t(u >> 24))};
+    float g[4], bt[4], f[4];
+    int xv[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ros = fdiv(1.f, oo[e]);
+      g[e] = fmul(gg[e], ros);
+      bt[e] = fmul(bb[e], ros);
+      f[e] = fmul(fmul(oo[e], fdiv(1.f, pp[e])), rnext);
+      xv[e] = cx[e] * int(mm[e]);
+    }
+    orow[w] = ln_pot_word<true>(t, mos, g, bt, f, xv, clamp_hi);
+  }
+}
+
 // The same arithmetic for the common case 2^-24 <= |A| < 2^8 with integer / magic-constant tricks (results identical):
 //   N = 7 - (E - 127) with E the biased exponent of A, so 2^N and 2^-N are exponent-field subtractions;
 //   M = floor(|A| * 2^N) = the top 8 bits of A's significand, and sign(A) * M as a float is A with its low 16 mantissa bits
@@ -347,11 +375,11 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
       for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_fast_word(t, mos, g[i], bt[i], f[i], xv[i], a.clamp_mid != 0, mant_max);
     }
     if (!in_range || mant_max >= 0x007ffff0u) {
+      ln_pot_row_slow(a, xr, orow, sub, LPR, WPLN, t, mos, clamp_hi);     // rare: out of line, constants re-read from memory
+    } else {
 #pragma unroll
-      for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_word<true>(t, mos, g[i], bt[i], f[i], xv[i], clamp_hi);
+      for (int i = 0; i < WPLN; ++i) orow[sub + LPR * i] = qw[i];
     }
-#pragma unroll
-    for (int i = 0; i < WPLN; ++i) orow[sub + LPR * i] = qw[i];
   }
 }
 
@@ -359,8 +387,12 @@ template <int LPR, int WPLN>
 static void launch_ln_pot(const p2v_layernorm_args& a, cudaStream_t stream) {
   constexpr int GPW = 32 / LPR;
   const int rows_per_block = 4 * GPW;
-  // persistent: several rows per lane group so the register-resident channel constants are amortised
-  const int blocks = std::max(1, std::min((a.rows + rows_per_block - 1) / rows_per_block, num_sms() * 3));
+  // persistent: several rows per lane group so the register-resident channel constants are amortised; one wave of resident blocks
+  static int occ = 0;
+  if (!occ) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_pot_kernel<LPR, WPLN>, 128, 0) != cudaSuccess || occ < 1) occ = 3;
+  }
+  const int blocks = std::max(1, std::min((a.rows + rows_per_block - 1) / rows_per_block, num_sms() * occ));
   layernorm_pot_kernel<LPR, WPLN><<<blocks, 128, 0, stream>>>(a);
 }
 
@@ -368,31 +400,18 @@ int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
   const int nwords = a.C / 4;
   if (a.pot_scales && a.out_i8 && !a.out_f32) {
     bool done = true;
-    if (nwords % 8 == 0 && nwords / 8 <= 6 && nwords / 8 >= 3 && a.rows >= 4) {
-      switch (nwords / 8) {
-        case 3: launch_ln_pot<8, 3>(a, stream); break;
-        case 4: launch_ln_pot<8, 4>(a, stream); break;
-        case 5: launch_ln_pot<8, 5>(a, stream); break;
-        default: launch_ln_pot<8, 6>(a, stream); break;
-      }
-    } else if (nwords % 16 == 0 && nwords / 16 <= 6 && nwords / 16 >= 3 && a.rows >= 2) {
-      switch (nwords / 16) {
-        case 3: launch_ln_pot<16, 3>(a, stream); break;
-        case 4: launch_ln_pot<16, 4>(a, stream); break;
-        case 5: launch_ln_pot<16, 5>(a, stream); break;
-        default: launch_ln_pot<16, 6>(a, stream); break;
-      }
-    } else if (nwords % 32 == 0 && nwords / 32 <= 8) {
-      switch (nwords / 32) {
-        case 1: launch_ln_pot<32, 1>(a, stream); break;
-        case 2: launch_ln_pot<32, 2>(a, stream); break;
-        case 3: launch_ln_pot<32, 3>(a, stream); break;
-        case 4: launch_ln_pot<32, 4>(a, stream); break;
-        case 5: launch_ln_pot<32, 5>(a, stream); break;
-        case 6: launch_ln_pot<32, 6>(a, stream); break;
-        case 7: launch_ln_pot<32, 7>(a, stream); break;
-        default: launch_ln_pot<32, 8>(a, stream); break;
-      }
+    // lanes per row: as many as leave a lane >= 12 channels (3 words) - more rows in flight per SM beat the amortisation of
+    // the per-row scalar work (C = 384: 32 lanes x 3 words 26.8 us vs 16 x 6 32.9 us for 50 k rows, tools/ln_bench.py)
+#define P2V_LN_POT(LPR_, N_) case N_: launch_ln_pot<LPR_, N_>(a, stream); break;
+    if (nwords % 32 == 0 && nwords / 32 >= 3 && nwords / 32 <= 8) {
+      switch (nwords / 32) { P2V_LN_POT(32, 3) P2V_LN_POT(32, 4) P2V_LN_POT(32, 5) P2V_LN_POT(32, 6) P2V_LN_POT(32, 7) P2V_LN_POT(32, 8) }
+    } else if (nwords % 16 == 0 && nwords / 16 >= 3 && nwords / 16 <= 6 && a.rows >= 2) {
+      switch (nwords / 16) { P2V_LN_POT(16, 3) P2V_LN_POT(16, 4) P2V_LN_POT(16, 5) P2V_LN_POT(16, 6) }
+    } else if (nwords % 8 == 0 && nwords / 8 >= 3 && nwords / 8 <= 6 && a.rows >= 4) {
+      switch (nwords / 8) { P2V_LN_POT(8, 3) P2V_LN_POT(8, 4) P2V_LN_POT(8, 5) P2V_LN_POT(8, 6) }
+    } else if (nwords % 32 == 0 && nwords / 32 <= 2) {
+      switch (nwords / 32) { P2V_LN_POT(32, 1) P2V_LN_POT(32, 2) }
+#undef P2V_LN_POT
     } else {
       done = false;
     }

@@ -10,6 +10,21 @@ namespace p2v {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
+// One leader lane of a converged warp (the lowest, deterministically for the full mask).  Control code runs warp-uniform and
+// wraps only the TMA / tcgen05 / expect-tx instructions in `if (elect_one())`: their operands then stay in uniform registers.
+// Under `if (lane == 0)` instead the compiler has to assume divergence and feeds every UTCIMMA / UTMALDG through an
+// ELECT + R2UR.BROADCAST waterfall loop - about 300 cycles per MMA instruction issued, measured (tools/pair_trace.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -30,17 +45,43 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // try_wait suspends in hardware for a bounded time per call; a wait that lasts longer than 2 s of wall clock is a protocol
-// bug and becomes a trap (reported as a launch error by the next API call) instead of a hung GPU.
+// bug and becomes a trap (reported as a launch error by the next API call) instead of a hung GPU.  No nanosleep in the loop:
+// its granularity (~1 us) would add a microsecond to every wait that is not satisfied on the first try.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);       // keep the issue slots for the warps that have work
-    if ((++spins & 63u) == 0u) {
+    if ((++spins & 1023u) == 0u) {
       uint64_t t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      if (t1 - t0 > 2000000000ull) __trap();
+    }
+  }
+}
+// Polling wait (test_wait never suspends).  For barriers whose last arrival can come from the peer CTA of a cluster
+// (mbarrier.arrive.shared::cluster / a peer's TMA complete_tx): a thread suspended inside try_wait was observed to sleep
+// on for thousands of cycles after such a remote arrival completed the phase (tools/pair_trace.py, proj GEMM).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 4095u) == 0u) {
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
       if (t1 - t0 > 2000000000ull) __trap();
     }
   }

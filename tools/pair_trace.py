@@ -20,7 +20,7 @@ if epi == ops.EPI_RESIDUAL:
               res=torch.randint(-128, 128, (M, N), generator=g, dtype=torch.int32).to(torch.int8).to(dev))
 else:
     kw["out_scale"] = torch.full((N,), 2.0 ** -5, device=dev)
-trace = torch.zeros(2 * 3 * 64 * 4, dtype=torch.int64, device=dev)
+trace = torch.zeros(2 * 19 * 64 * 4, dtype=torch.int64, device=dev)
 ops.set_gemm_variant(2)
 args = ops.gemm_args(A, W, epi, torch.full((N,), 2.0 ** -13, device=dev), **kw)
 for _ in range(3):
@@ -29,13 +29,14 @@ torch.cuda.synchronize()
 args.out_f32 = trace.data_ptr()
 ops.gemm(args)
 torch.cuda.synchronize()
-t = trace.cpu().reshape(2, 3, 64, 4)
+t = trace.cpu().reshape(2, 19, 64, 4)
 for rank in (0, 1):
     t0 = int(t[rank][t[rank] > 0].min())
     print("== CTA rank", rank, "(clock64 relative to first stamp)")
     for it in range(64):
-        if t[rank, 1, it, 0] == 0:
+        if t[rank, 3, it, 0] == 0:
             break
         r = lambda role, k: int(t[rank, role, it, k]) - t0 if t[rank, role, it, k] > 0 else -1
-        print("tile %2d  prod: start %7d kblocks-issued %7d res-issued %7d | mma: wait-tempty %7d got %7d committed %7d | epi: start %7d rfull %7d tfull %7d stored %7d" % (
-            it, r(2, 0), r(2, 1), r(2, 2), r(0, 0), r(0, 1), r(0, 2), r(1, 0), r(1, 1), r(1, 2), r(1, 3)))
+        print("tile %2d  prod: start %7d kblocks-issued %7d res-issued %7d | mma: wait-tempty %7d got %7d committed %7d | epi warp 0: start %7d rfull %7d tfull %7d stored %7d" % (
+            it, r(2, 0), r(2, 1), r(2, 2), r(0, 0), r(0, 1), r(0, 2), r(3, 0), r(3, 1), r(3, 2), r(3, 3)))
+        print("         epilogue warps tfull->stored: " + " ".join("%d:%d-%d" % (e, r(3 + e, 2), r(3 + e, 3)) for e in range(16)))
