@@ -157,7 +157,8 @@ int p2v_layernorm_int(const p2v_layernorm_args* args_host, void* stream);
  * reference's fp32 formulas (p2vit_b200/engine.py: build_softmax_lut), drives both the stand-alone
  * kernel and the fused attention.  exp_int = hi*2^32 + lo exactly; exp_f32 = the same value in fp32.
  * code = clamp(log_round(RNE(fl(sum)/exp_f32)), 0, 15); probability 2^-code, 0 when log_round >= 16
- * (code 255 on the wire).
+ * (code 255 on the wire).  Every entry must be below 2^55 (the fused attention kernel sums up to 256 of them in 64 bits);
+ * p2vit_b200/intmath.py: build_softmax_lut refuses scales that would exceed it (below ~2^-10).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   uint32_t hi[256];

@@ -11,9 +11,13 @@
 //                       O = 256*acc_hi + acc_lo (exact int32)
 //   out = sat(RNE(O*m2))  qact2 codes, 64 contiguous bytes per row.
 //
-// One CTA = 4 softmax warps + 1 control warp (one lane issues TMA and MMA), two CTAs per SM (256 TMEM columns and
-// ~112 KB shared memory each) so one CTA's MMA / TMA latency hides under the other's integer work.  A CTA walks
-// heads blockIdx.x, blockIdx.x + gridDim.x, ...; each head is 1 or 2 query tiles of 128 rows.
+// One CTA = 8 softmax warps + 1 control warp, two CTAs per SM (256 TMEM columns and ~112 KB shared memory each) so one CTA's
+// MMA / TMA latency hides under the other's integer work.  Two softmax warps share each TMEM lane quarter (32 query rows) and
+// split the key axis in 16-column units; their partial row max / row sum meet through spare TMEM columns (tcgen05.st, a
+// 64-thread named barrier, tcgen05.ld) - the kernel is bound by the softmax warps' instruction issue, so 16 of them per SM
+// instead of 8 is what hides the TMEM / shared-memory latencies.  Pass 2 writes d = max - code back over S in TMEM so
+// pass 3 does not requantise again.  A CTA walks heads blockIdx.x, blockIdx.x + gridDim.x, ...; each head is 1 or 2 query
+// tiles of 128 rows.
 #include <climits>
 #include <type_traits>
 #include "tc_common.cuh"
@@ -22,7 +26,9 @@ namespace p2v {
 
 constexpr int AT_KV_ROWS = 224;                 // key / value rows staged per head (TMA box, >= T)
 constexpr int AT_DH = 64;
-constexpr int AT_THREADS = 160;
+constexpr int AT_SM_WARPS = 8;                  // softmax warps: lane quarter = warp & 3, key half = warp >> 2
+constexpr int AT_THREADS = AT_SM_WARPS * 32 + 32;
+constexpr uint32_t AT_XMAX = 224, AT_XSUM = 228;   // spare TMEM columns: partial row max (1 per half), partial row sum (2 per half)
 constexpr uint32_t AT_TMEM_COLS = 256;
 constexpr uint32_t AT_OFF_Q = 0;                                  // 2 x [128 x 64]
 constexpr uint32_t AT_OFF_K = 2 * 128 * AT_DH;                    // [224 x 64]
@@ -55,15 +61,39 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n) {   // PTX
   asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
   return r;
 }
-__device__ __forceinline__ uint32_t prob_bits_fast(float tot, float rcp, bool& near) {
+// `near_min` / `y2_min` collect the guard-band distances of a unit's elements: the unit is redone exactly when
+// near_min < 32 (some w within 16 ulps of a power of two >= 2; w + 16 ulps below 2 is mapped to a huge value by the xor)
+// or y2_min < 1e-5.
+__device__ __forceinline__ uint32_t prob_bits_fast(float tot, float rcp, uint32_t& near_min, float& y2_min) {
   const float y = fadd(fmul(tot, rcp), 0.5f);
   // 2/3 rounded up twice: y >= 1.5 - 1 ulp always (e <= tot), so w >= 1 and the exponent field needs no clamp; the
   // 1-ulp shift of the thresholds is inside the guard band
   const float w = fmul(y, 0.66666674613952636718750f);
   const uint32_t wb = __float_as_uint(w);
-  const uint32_t nb = wb + 16u;
-  near = ((nb & 0x007fffffu) < 32u && nb >= 0x40000000u) || fabsf(fsub(y, 2.0f)) < 1e-5f;
+  near_min = min(near_min, ((wb + 16u) & 0x407fffffu) ^ 0x40000000u);
+  y2_min = fminf(y2_min, fabsf(fsub(y, 2.0f)));
   return shr_clamp(y >= 2.0f ? 0x4000u : 0x8000u, (wb >> 23) - 127u);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const int (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a), "+r"(b) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// partner exchange: both warps of a lane quarter have stored their words to TMEM; returns once each can load the other's
+__device__ __forceinline__ void quarter_exchange_sync(uint32_t quarter) {
+  tmem_wait_st();
+  tc_fence_before();
+  named_barrier(1 + quarter, 64);
+  tc_fence_after();
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 2)
@@ -82,10 +112,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (threadIdx.x == 0) {
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
-    mbar_init(bar_p, 4); mbar_init(bar_free, 4);
+    mbar_init(bar_p, AT_SM_WARPS); mbar_init(bar_free, AT_SM_WARPS);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc<AT_TMEM_COLS>(smem_u32(&tmem_slot));
+  if (warp == AT_SM_WARPS) tmem_alloc<AT_TMEM_COLS>(smem_u32(&tmem_slot));
   for (int i = threadIdx.x; i < 256; i += AT_THREADS) {
     s_lut[i] = make_uint2(p.lut->hi[i], p.lut->lo[i]);
     s_rcp[i] = fdiv(1.0f, p.lut->exp_f32[i]);
@@ -95,11 +125,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp == 4) {
-    // ================= control lane: TMA producer + MMA issuer =================
-    if (lane == 0) {
-      tma_prefetch_map(&tmQ);
-      tma_prefetch_map(&tmKV);
+  if (warp == AT_SM_WARPS) {
+    // ================= control warp: TMA producer + MMA issuer =================
+    // The whole warp walks the loop (warp-uniform, so addresses and descriptors stay in uniform registers); one elected lane
+    // issues each TMA / MMA / commit (tc_common.cuh: elect_one).
+    {
+      if (elect_one()) {
+        tma_prefetch_map(&tmQ);
+        tma_prefetch_map(&tmKV);
+      }
       const int row_bytes_h = AT_DH;  // column offsets inside a token row: q at h*64, k at (H+h)*64, v at (2H+h)*64
       auto load_qk = [&](int hd) {
         const int b = hd / H, h = hd % H;
@@ -114,7 +148,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       };
       const uint32_t idesc_qk = make_i8_idesc(128, p.n_pad, true, true);
       const uint32_t idesc_pv = make_i8_idesc(128, AT_DH, false, true, false, true);   // P u8 K-major, V s8 MN-major
-      if (int(blockIdx.x) < p.total_heads) { load_qk(blockIdx.x); load_v(blockIdx.x); }
+      if (int(blockIdx.x) < p.total_heads) {
+        if (elect_one()) { load_qk(blockIdx.x); load_v(blockIdx.x); }
+        __syncwarp();
+      }
       uint32_t n = 0, hcount = 0;
       for (int hd = blockIdx.x; hd < p.total_heads; hd += gridDim.x, ++hcount) {
         const int next = hd + gridDim.x;
@@ -122,158 +159,189 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int mt = 0; mt < p.mtiles; ++mt, ++n) {
           mbar_wait(bar_free, (n & 1u) ^ 1u);          // previous tile's O has left TMEM
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < AT_DH / 32; ++k)
-            umma_i8(tmem_base, make_smem_desc(base + AT_OFF_Q + mt * 128 * AT_DH + k * 32, 16, 512, UMMA_LAYOUT_SW64),
-                    make_smem_desc(base + AT_OFF_K + k * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_qk, uint32_t(k > 0));
-          tc_commit(bar_s);
+            for (int k = 0; k < AT_DH / 32; ++k)
+              umma_i8(tmem_base, make_smem_desc(base + AT_OFF_Q + mt * 128 * AT_DH + k * 32, 16, 512, UMMA_LAYOUT_SW64),
+                      make_smem_desc(base + AT_OFF_K + k * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_qk, uint32_t(k > 0));
+            tc_commit(bar_s);
+          }
+          __syncwarp();
           if (mt == p.mtiles - 1 && next < p.total_heads) {
             mbar_wait(bar_s, n & 1u);                  // q / k tiles have been read: refill them for the next head
-            load_qk(next);
+            if (elect_one()) load_qk(next);
+            __syncwarp();
           }
           mbar_wait(bar_p, n & 1u);                    // P planes written, S consumed
           if (mt == 0) mbar_wait(bar_v, hcount & 1u);
           tc_fence_after();
-          for (int plane = 0; plane < 2; ++plane)
-            for (int ks = 0; ks < p.ksteps; ++ks)
-              umma_i8(tmem_base + plane * AT_DH,
-                      make_kmajor_sw128_desc(base + AT_OFF_P + plane * AT_P_PLANE + (ks >> 2) * AT_P_CHUNK + (ks & 3) * 32),
-                      make_smem_desc(base + AT_OFF_V + ks * 32 * AT_DH, AT_KV_ROWS * AT_DH, 512, UMMA_LAYOUT_SW64), idesc_pv,
-                      uint32_t(ks > 0));
-          tc_commit(bar_o);
+          if (elect_one()) {
+            for (int plane = 0; plane < 2; ++plane)
+              for (int ks = 0; ks < p.ksteps; ++ks)
+                umma_i8(tmem_base + plane * AT_DH,
+                        make_kmajor_sw128_desc(base + AT_OFF_P + plane * AT_P_PLANE + (ks >> 2) * AT_P_CHUNK + (ks & 3) * 32),
+                        make_smem_desc(base + AT_OFF_V + ks * 32 * AT_DH, AT_KV_ROWS * AT_DH, 512, UMMA_LAYOUT_SW64), idesc_pv,
+                        uint32_t(ks > 0));
+            tc_commit(bar_o);
+          }
+          __syncwarp();
           if (mt == p.mtiles - 1 && next < p.total_heads) {
             mbar_wait(bar_o, n & 1u);                  // v tile has been read
-            load_v(next);
+            if (elect_one()) load_v(next);
+            __syncwarp();
           }
         }
       }
     }
   } else {
-    // ================= softmax warps: one thread per query row of the tile =================
-    const int rloc = warp * 32 + lane;
-    const uint32_t tlane = tmem_base + (uint32_t(warp * 32) << 16);
+    // ================= softmax warps: thread = one query row (TMEM lane) x one half of the key axis =================
+    const uint32_t quarter = uint32_t(warp) & 3u, half = uint32_t(warp) >> 2;
+    const int rloc = int(quarter) * 32 + lane;
+    const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
     const float mult = p.score_mult;
+    const uint32_t lut32 = base + AT_OFF_LUT, rcp32 = base + AT_OFF_LUT + 256 * 8;    // 32-bit shared addresses of the tables
+    // key axis in 16-column units: units with a column < T hold scores, the P operand needs 2 * ksteps units (zero padded)
+    const int units_p = 2 * p.ksteps, units_s = (T + 15) >> 4, u_mid = (units_p + 1) >> 1;
+    const int u_begin = half ? u_mid : 0, u_end = half ? units_p : u_mid;
+    const int u_send = min(u_end, units_s);               // my units that hold scores: [u_begin, u_send)
     uint32_t n = 0;
     for (int hd = blockIdx.x; hd < p.total_heads; hd += gridDim.x) {
       const int b = hd / H, h = hd % H;
       for (int mt = 0; mt < p.mtiles; ++mt, ++n) {
         const int row = mt * 128 + rloc;
-        const bool warp_live = mt * 128 + warp * 32 < T;
+        const bool warp_live = mt * 128 + int(quarter) * 32 < T;     // the same for both warps of a quarter
         mbar_wait(bar_s, n & 1u);
         tc_fence_after();
         if (warp_live) {
-          // S stays in TMEM and is re-read by every pass (TMEM reads are cheap; a rolled loop keeps the kernel in
-          // the instruction cache, which a register-resident row of codes - a fully unrolled body - does not).
-          const int nchunks = p.ksteps;                 // 32 key columns per chunk
+          // S stays in TMEM and is re-read by every pass (a rolled loop over units keeps the kernel in the instruction cache).
+          // Only the unit that straddles column T needs per-element masking: [u_begin, u_full) run the unmasked bodies.
+          const int u_full = min(u_send, T >> 4);
           // ---- pass 1: row max of the raw scores; the requantisation is monotone, so max code = code(max S)
           int smax = INT_MIN;
-#pragma unroll 1
-          for (int c = 0; c < nchunks; ++c) {
-            int acc[32];
-            tmem_ld32(tlane + c * 32, acc);
-            const int nv = T - c * 32;
+          auto max_unit = [&](auto masked, int u) {
+            int acc[16];
+            tmem_ld16(tlane + u * 16, acc);
+            const int nv = T - u * 16;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) smax = max(smax, e < nv ? acc[e] : INT_MIN);
+            for (int e = 0; e < 16; ++e) smax = max(smax, (!decltype(masked)::value || e < nv) ? acc[e] : INT_MIN);
+          };
+#pragma unroll 1
+          for (int u = u_begin; u < u_full; ++u) max_unit(std::false_type{}, u);
+          if (u_full < u_send) max_unit(std::true_type{}, u_full);
+          {
+            uint32_t o0, o1;
+            tmem_st2(tlane + AT_XMAX + 2 * half, uint32_t(smax), 0u);
+            quarter_exchange_sync(quarter);
+            tmem_ld2(tlane + AT_XMAX + 2 * (half ^ 1u), o0, o1);
+            smax = max(smax, int(o0));
           }
           const int mx = sat_s8(fmul(float(smax), mult));
-          // ---- pass 2: exact row sum of exp_int(max - code); only the last chunk can hold columns >= T
-          const int nfull = T >> 5;
-          unsigned long long shi = 0, slo = 0;
-          auto sum_chunk = [&](auto masked, int c) {
-            int acc[32];
-            tmem_ld32(tlane + c * 32, acc);
-            const int nv = T - c * 32;
+          // ---- pass 2: exact row sum of exp_int(max - code) over my units; d = max - code goes back to TMEM over S
+          //      code = sat(RNE(fl(S * mult))): RNE through the magic constant (no F2I), the saturation is a clamp of d
+          const int mxb = 0x4B400000 + mx, dmax = mx + 128;
+          unsigned long long sum = 0;
+          auto sum_unit = [&](auto masked, int u) {
+            int acc[16];
+            tmem_ld16(tlane + u * 16, acc);
+            const int nv = T - u * 16;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int d = mx - sat_s8(fmul(float(acc[e]), mult));
-              const uint2 v = s_lut[d];
-              if (!decltype(masked)::value || e < nv) { shi += v.x; slo += v.y; }
+            for (int e = 0; e < 16; ++e) {
+              const int d = min(max(mxb - __float_as_int(fadd(fmul(__int2float_rn(acc[e]), mult), RMAGIC)), 0), dmax);
+              acc[e] = d;
+              uint32_t vx, vy;
+              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "r"(lut32 + uint32_t(d) * 8u));
+              if (!decltype(masked)::value || e < nv) sum += (static_cast<unsigned long long>(vx) << 32) | vy;
             }
+            tmem_st16(tlane + u * 16, acc);
           };
 #pragma unroll 1
-          for (int c = 0; c < nfull; ++c) sum_chunk(std::false_type{}, c);
-          if (nfull < nchunks) sum_chunk(std::true_type{}, nfull);
-          const float tot = u96_to_f32(shi, slo);
+          for (int u = u_begin; u < u_full; ++u) sum_unit(std::false_type{}, u);
+          if (u_full < u_send) sum_unit(std::true_type{}, u_full);
+          {
+            uint32_t o0, o1;
+            tmem_st2(tlane + AT_XSUM + 2 * half, uint32_t(sum), uint32_t(sum >> 32));
+            quarter_exchange_sync(quarter);           // also orders the d write-back before pass 3's loads
+            tmem_ld2(tlane + AT_XSUM + 2 * (half ^ 1u), o0, o1);
+            sum += (static_cast<unsigned long long>(o1) << 32) | o0;
+          }
+          const float tot = __ull2float_rn(sum);      // the exact integer sum (< 2^64: intmath.build_softmax_lut bounds the table), rounded once
           // ---- pass 3: probabilities 2^(15-code) as hi / lo byte planes in the UMMA K-major SW128 layout
-          uint8_t* prow = gbase + AT_OFF_P + rloc * 128;
+          const uint32_t prow = base + AT_OFF_P + uint32_t(rloc) * 128u;
           const uint32_t sw = uint32_t(rloc & 7);
-          auto prob_chunk = [&](auto masked, int c) {
-            int acc[32];
-            tmem_ld32(tlane + c * 32, acc);
-            const int nv = T - c * 32;
+          auto store_unit = [&](int u, const uint32_t (&hi)[4], const uint32_t (&lo)[4]) {
+            const uint32_t dst = prow + uint32_t(u >> 3) * AT_P_CHUNK + ((uint32_t(u & 7) ^ sw) << 4);    // unit = 16 bytes along the key axis
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + AT_P_PLANE), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+          };
+          auto prob_unit = [&](auto masked, int u) {
+            int dd[16];
+            tmem_ld16(tlane + u * 16, dd);
+            const int nv = T - u * 16;
+            uint32_t pv[16];
+            uint32_t near_min = 0xffffffffu;
+            float y2_min = 1.0f;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t pv[16];
-              bool any_near = false;
+            for (int e = 0; e < 16; ++e) {
+              float rcp;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rcp) : "r"(rcp32 + uint32_t(dd[e]) * 4u));
+              pv[e] = prob_bits_fast(tot, rcp, near_min, y2_min);
+            }
+            if (near_min < 32u || y2_min < 1e-5f) {   // some element sits next to a rounding / log2 boundary: redo the unit with the IEEE division
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                const int d = mx - sat_s8(fmul(float(acc[half * 16 + e]), mult));
-                acc[half * 16 + e] = d;
-                bool near;
-                pv[e] = prob_bits_fast(tot, s_rcp[d], near);
-                any_near |= near;
+                const uint2 v = s_lut[dd[e]];
+                const uint32_t big = log2_code(tot, __ull2float_rn((static_cast<unsigned long long>(v.x) << 32) | v.y));
+                pv[e] = shr_clamp(0x8000u, big);
               }
-              if (any_near) {   // some element sits next to a rounding / log2 boundary: redo the unit with the IEEE division
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const uint2 v = s_lut[acc[half * 16 + e]];
-                  const uint32_t big = log2_code(tot, __ull2float_rn((static_cast<unsigned long long>(v.x) << 32) | v.y));
-                  pv[e] = shr_clamp(0x8000u, big);
-                }
-              }
-              uint32_t lo[4], hi[4];
-#pragma unroll
-              for (int e4 = 0; e4 < 4; ++e4) {
-                if (decltype(masked)::value) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e)
-                    if (half * 16 + e4 * 4 + e >= nv) pv[e4 * 4 + e] = 0u;
-                }
-                const uint32_t p01 = pv[e4 * 4] | (pv[e4 * 4 + 1] << 16), p23 = pv[e4 * 4 + 2] | (pv[e4 * 4 + 3] << 16);
-                lo[e4] = __byte_perm(p01, p23, 0x6420);
-                hi[e4] = __byte_perm(p01, p23, 0x7531);
-              }
-              const int g = c * 2 + half;                       // 16-byte unit along the key axis
-              uint8_t* dst = prow + (g >> 3) * AT_P_CHUNK + ((uint32_t(g & 7) ^ sw) << 4);
-              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(dst + AT_P_PLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              if (decltype(masked)::value) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (e4 * 4 + e >= nv) pv[e4 * 4 + e] = 0u;
+              }
+              const uint32_t p01 = pv[e4 * 4] | (pv[e4 * 4 + 1] << 16), p23 = pv[e4 * 4 + 2] | (pv[e4 * 4 + 3] << 16);
+              lo[e4] = __byte_perm(p01, p23, 0x6420);
+              hi[e4] = __byte_perm(p01, p23, 0x7531);
+            }
+            store_unit(u, hi, lo);
           };
 #pragma unroll 1
-          for (int c = 0; c < nfull; ++c) prob_chunk(std::false_type{}, c);
-          if (nfull < nchunks) prob_chunk(std::true_type{}, nfull);
+          for (int u = u_begin; u < u_full; ++u) prob_unit(std::false_type{}, u);
+          if (u_full < u_send) prob_unit(std::true_type{}, u_full);
+          {
+            const uint32_t zero[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+            for (int u = max(u_begin, units_s); u < u_end; ++u) store_unit(u, zero, zero);    // zero padding of the P operand
+          }
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_p);
-        // ---- O = 256*hi + lo -> qact2 codes
+        // ---- O = 256*hi + lo -> qact2 codes; this warp's half of the 64 head channels
         mbar_wait(bar_o, n & 1u);
         tc_fence_after();
         if (warp_live) {
-          int8_t* orow = p.out + (int64_t(b) * T + row) * (int64_t(H) * AT_DH) + h * AT_DH;
+          int8_t* orow = p.out + (int64_t(b) * T + row) * (int64_t(H) * AT_DH) + h * AT_DH + half * 32;
+          int ah[32], al[32];
+          tmem_ld32_async(tlane + half * 32, ah);
+          tmem_ld32_async(tlane + AT_DH + half * 32, al);
+          tmem_wait_ld();
+          if (row < T) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            int ah[32], al[32];
-            tmem_ld32_async(tlane + half * 32, ah);
-            tmem_ld32_async(tlane + AT_DH + half * 32, al);
-            tmem_wait_ld();
-            if (row < T) {
+            for (int j = 0; j < 32; j += 16) {
+              uint32_t w[4];
 #pragma unroll
-              for (int j = 0; j < 32; j += 16) {
-                uint32_t w[4];
+              for (int e4 = 0; e4 < 4; ++e4) {
+                float r[4];
 #pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
-                  int q[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int O = ah[j + e4 * 4 + e] * 256 + al[j + e4 * 4 + e];
-                    q[e] = sat_s8(fmul(float(O), p.out_mult));
-                  }
-                  w[e4] = pack4_s8(q[0], q[1], q[2], q[3]);
-                }
-                *reinterpret_cast<uint4*>(orow + half * 32 + j) = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int e = 0; e < 4; ++e) r[e] = fadd(fmul(__int2float_rn(ah[j + e4 * 4 + e] * 256 + al[j + e4 * 4 + e]), p.out_mult), RMAGIC);
+                w[e4] = pack4_sat(r[0], r[1], r[2], r[3]);
               }
+              *reinterpret_cast<uint4*>(orow + j) = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
         }
@@ -285,7 +353,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == AT_SM_WARPS) {
     tc_fence_after();
     tmem_dealloc<AT_TMEM_COLS>(tmem_base);
   }

@@ -69,45 +69,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
+    // ================= TMA producer: warp-uniform loop, one elected lane issues (tc_common.cuh: elect_one) =================
+    if (elect_one()) {
       tma_prefetch_map(&tmA);
       tma_prefetch_map(&tmB);
-      uint32_t it = 0;
-      for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int m0 = int(t / tiles_n) * BM, n0 = int(t % tiles_n) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
-          mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+    }
+    uint32_t it = 0;
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int m0 = int(t / tiles_n) * BM, n0 = int(t % tiles_n) * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+        if (elect_one()) {
           mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
           const uint32_t sa = stage0 + s * STAGE_BYTES;
           tma_load_2d(sa, &tmA, bar_full + 8 * s, kb * BK, m0);
           tma_load_2d(sa + A_BYTES, &tmB, bar_full + 8 * s, kb * BK, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_i8_idesc(BM, BN, true, true);
-      uint32_t it = 0, local = 0;
-      for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
-        const uint32_t g = local % TC_GROUPS, use = local / TC_GROUPS;
-        mbar_wait(bar_tempty + 8 * g, (use & 1u) ^ 1u);
+    constexpr uint32_t idesc = make_i8_idesc(BM, BN, true, true);
+    uint32_t it = 0, local = 0;
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x, ++local) {
+      const uint32_t g = local % TC_GROUPS, use = local / TC_GROUPS;
+      mbar_wait(bar_tempty + 8 * g, (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + g * BN;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
+        mbar_wait(bar_full + 8 * s, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + g * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
-          mbar_wait(bar_full + 8 * s, ph);
-          tc_fence_after();
-          const uint32_t sa = stage0 + s * STAGE_BYTES, sb = sa + A_BYTES;
+        const uint32_t sa = stage0 + s * STAGE_BYTES, sb = sa + A_BYTES;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             umma_i8(d_tmem, make_kmajor_sw128_desc(sa + k * UMMA_K), make_kmajor_sw128_desc(sb + k * UMMA_K), idesc,
                     uint32_t(kb > 0 || k > 0));
           tc_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs have read it
+          if (kb == nkb - 1) tc_commit(bar_tfull + 8 * g);    // accumulator complete
         }
-        tc_commit(bar_tfull + 8 * g);    // accumulator complete
+        __syncwarp();
       }
     }
   } else {

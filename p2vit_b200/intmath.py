@@ -36,8 +36,10 @@ def build_softmax_lut(scale, max_row_len=1024):
     e = softmax_exp_table(scale)
     lut = np.zeros((), dtype=LUT_DTYPE)
     vals = [int(v) for v in e.double().tolist()]  # fp32 -> python int is exact (integer valued)
-    if max(vals) * max_row_len >= 1 << 95:
-        raise NotImplementedError("attention score scale %g is too small for the exact 96-bit row sum" % float(scale))
+    if max(vals) * max_row_len >= 1 << 95 or max(vals) >= 1 << 55:
+        # the tcgen05 attention kernel sums a row (<= 256 keys) exactly in 64 bits; 2^55 is reached only below scale ~2^-10,
+        # far finer than an int8 score grid ever needs (include/p2vit_b200.h: p2v_softmax_lut)
+        raise NotImplementedError("attention score scale %g is too small for the exact integer row sum" % float(scale))
     lut["hi"] = np.array([v >> 32 for v in vals], dtype=np.uint64).astype(np.uint32)
     lut["lo"] = np.array([v & 0xFFFFFFFF for v in vals], dtype=np.uint64).astype(np.uint32)
     lut["exp_f32"] = e.numpy()

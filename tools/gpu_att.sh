@@ -1,5 +1,11 @@
 #!/bin/bash
+export PYTHONPATH=$PWD
 mkdir -p gpurun_out
-run() { name=$1; shift; echo "=== $name" ; timeout ${TMO:-600} "$@" > gpurun_out/$name.log 2>&1; echo "exit $?"; tail -n ${TAILN:-15} gpurun_out/$name.log; }
-run att python -m pytest tests/test_gpu_ops.py -q -m gpu -p no:cacheprovider -k attention -x
-TAILN=3 run bench python bench.py --steps 20 --warmup 3 --golden-state --no-cpu-baseline
+echo "=== attention tests"
+timeout 300 python -m pytest tests/test_gpu_ops.py -x -q -k "attention" > gpurun_out/att_tests.log 2>&1
+rc=$?; echo "exit $rc"; tail -n 4 gpurun_out/att_tests.log
+[ $rc -ne 0 ] && exit 0
+timeout 100 python tools/att_bench.py 6 256 2>&1 | tee gpurun_out/att_bench.log
+timeout 100 python tools/att_bench.py 12 256 2>&1 | tee -a gpurun_out/att_bench.log
+echo "--- previous library (control lane under if (lane == 0))"
+P2V_LIB=$PWD/p2vit_b200/csrc/libp2vit_b200_prev.so timeout 100 python tools/att_bench.py 6 256 2>&1 | tee -a gpurun_out/att_bench.log
