@@ -105,9 +105,14 @@ typedef struct {
  * (and for the rare segments flagged non-monotone), so its result is identical to the direct evaluation.
  * Layout: header {float y0, inv_w; int32 n, reserved} then n entries {float threshold; uint32 below | above<<8 | slow<<31}. */
 #define P2V_GELU_TABLE_MAX_ENTRIES 4096
-#define P2V_GELU_TABLE_BYTES (16 + 8 * P2V_GELU_TABLE_MAX_ENTRIES)
-/* returns 0 and fills `table_dev` (P2V_GELU_TABLE_BYTES bytes), or 3 if out_scale needs more than the maximum number of
- * entries / is not a power of two (the caller then passes gelu_table = NULL) */
+/* A second form of the same function follows the first in the buffer (used by the CTA-pair GEMM, csrc/common.cuh:
+ * GeluStepsHeader): a linear map per y-segment that pins the code down to two candidates, and one exact threshold per code
+ * boundary on each side of GELU's minimum, laid out so that the epilogue's lookups are free of bank conflicts.  The builder
+ * checks it against the direct evaluation on ~2.3 M arguments (every threshold +-256 ulps, a dense grid, 200 binades). */
+#define P2V_GELU_TABLE_BYTES (16 + 8 * P2V_GELU_TABLE_MAX_ENTRIES + 64 + 8 * 64 + 4 * 512)
+/* returns 0 and fills `table_dev` (P2V_GELU_TABLE_BYTES bytes, 16-byte aligned), or 3 if out_scale is not a power of two in
+ * the tabulated range 2^-7 .. 2^-2 or a form failed its self-check (the caller then passes gelu_table = NULL and the kernels
+ * evaluate erf per element).  Synchronises `stream` once (the verdict of the self-check is read back). */
 int p2v_build_gelu_table(float out_scale, void* table_dev, void* stream);
 
 int p2v_gemm_i8(const p2v_gemm_args* args_host, void* stream);

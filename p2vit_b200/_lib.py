@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("P2V_LIB") or os.path.join(_HERE, "csrc", "libp2vit_b200.so")   # P2V_LIB: experiment builds (tools/)
 
 EPI_REQUANT, EPI_GELU, EPI_RESIDUAL, EPI_EMBED, EPI_DEQUANT, EPI_F32 = range(6)
-GELU_TABLE_BYTES = 16 + 8 * 4096
+GELU_TABLE_BYTES = 16 + 8 * 4096 + 64 + 8 * 64 + 4 * 512
 
 
 class GemmArgs(C.Structure):

@@ -86,6 +86,78 @@ __device__ __forceinline__ int gelu_code_table(float y, uint2 e, bool& slow) {
   return int(__byte_perm(e.y, 0u, sel));
 }
 
+// ---- GELU step tables, second form (CTA-pair GEMM epilogue; include/p2vit_b200.h: p2v_build_gelu_table)
+// code(y) = sat(RNE(gelu_erf(y) / so)) is a step function: non-increasing for y < y* (the minimum of GELU) and non-decreasing
+// above.  A per-segment linear map P(y) ~ gelu(y)/so (error < 0.4) gives f = RNE(P - 1/2), so the code is f or f + 1, and ONE
+// exact threshold decides: code = f + [code(y) >= f + 1], where [code(y) >= c] is  y >= thrR[c]  right of y* and  y < thrL[c]
+// left of it.  Thresholds are exact fp32 values found by bisection on the kernels' own gelu_erf; y within 8 ulps of the
+// threshold consulted is sent to the direct evaluation (erff is not monotone at the ulp level).  Both tables sit in shared
+// memory replicated per lane (entry i of lane l at i * stride + 4 l), so the two data-dependent lookups are free of bank
+// conflicts - the reason the first form (one 8-byte entry per y-segment, ~5-way conflicts) gained almost nothing.
+struct GeluStepsHeader {   // 64 bytes, then float2 seg[P2V_GELU_STEPS_MAX_SEG], float thr[P2V_GELU_STEPS_MAX_THR]
+  float ymin, ymax, inv_w, soff, ystar;
+  int nseg, nr, nl, k1, rep_log2, ok;
+  int pad[5];
+};
+constexpr int P2V_GELU_STEPS_MAX_SEG = 64, P2V_GELU_STEPS_MAX_THR = 512;
+constexpr int P2V_GELU_STEPS_OFFSET = 16 + 8 * P2V_GELU_TABLE_MAX_ENTRIES;                 // byte offset inside a p2v gelu table buffer
+constexpr int P2V_GELU_STEPS_SMEM_MAX = 256 * P2V_GELU_STEPS_MAX_SEG + 26 * 1024;          // replicated tables: segments + thresholds
+struct GeluSteps {         // per-lane view of the replicated tables (32-bit shared addresses, pre-biased by the magic constant)
+  uint32_t seg_addr, thr_addr, nr_off, thr_shift;
+  float ymin, ymax, inv_w, soff, ystar;
+};
+__host__ __device__ inline uint32_t gelu_steps_smem_bytes(const GeluStepsHeader& h) {
+  return uint32_t(h.nseg) * 256u + (uint32_t(h.nr + h.nl) << (2 + h.rep_log2));
+}
+// every thread of the block copies its share of the global table into the replicated shared-memory layout at `smem`
+__device__ __forceinline__ void gelu_steps_fill_smem(const void* table, uint32_t smem, int tid, int nthreads) {
+  const char* base = reinterpret_cast<const char*>(table) + P2V_GELU_STEPS_OFFSET;
+  const GeluStepsHeader h = *reinterpret_cast<const GeluStepsHeader*>(base);
+  const float2* seg = reinterpret_cast<const float2*>(base + sizeof(GeluStepsHeader));
+  const float* thr = reinterpret_cast<const float*>(base + sizeof(GeluStepsHeader) + 8 * P2V_GELU_STEPS_MAX_SEG);
+  for (int i = tid; i < h.nseg * 32; i += nthreads) {
+    const float2 v = __ldg(seg + (i >> 5));
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(smem + uint32_t(i) * 8u), "f"(v.x), "f"(v.y) : "memory");
+  }
+  const uint32_t thr0 = smem + uint32_t(h.nseg) * 256u;
+  const int n = (h.nr + h.nl) << h.rep_log2;
+  for (int i = tid; i < n; i += nthreads) {
+    const float v = __ldg(thr + (i >> h.rep_log2));
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(thr0 + uint32_t(i) * 4u), "f"(v) : "memory");
+  }
+}
+__device__ __forceinline__ GeluSteps gelu_steps_view(const void* table, uint32_t smem, int lane) {
+  const GeluStepsHeader h = *reinterpret_cast<const GeluStepsHeader*>(reinterpret_cast<const char*>(table) + P2V_GELU_STEPS_OFFSET);
+  GeluSteps t;
+  t.thr_shift = uint32_t(2 + h.rep_log2);
+  t.seg_addr = smem + uint32_t(lane) * 8u - (0x4B400000u << 8);
+  t.thr_addr = smem + uint32_t(h.nseg) * 256u + (uint32_t(lane) & ((1u << h.rep_log2) - 1u)) * 4u + ((uint32_t(h.k1) - 0x4B400000u) << t.thr_shift);
+  t.nr_off = uint32_t(h.nr) << t.thr_shift;
+  t.ymin = h.ymin; t.ymax = h.ymax; t.inv_w = h.inv_w; t.soff = h.soff; t.ystar = h.ystar;
+  return t;
+}
+// the code of y, NOT saturated (pack4_sat_int saturates); near_min collects min(bits(y) - bits(threshold) + 8) as unsigned:
+// a value <= 16 means some y was within 8 ulps of the threshold consulted and the caller must evaluate erf directly
+__device__ __forceinline__ int gelu_steps_code(float y, const GeluSteps& t, uint32_t& near_min) {
+  const float yc = fminf(fmaxf(y, t.ymin), t.ymax);
+  const uint32_t sb = __float_as_uint(fadd(__fmaf_rn(yc, t.inv_w, t.soff), RMAGIC));          // 0x4B400000 + segment
+  float A, B;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(A), "=f"(B) : "r"(t.seg_addr + (sb << 8)));
+  const uint32_t fb = __float_as_uint(fadd(__fmaf_rn(A, yc, B), RMAGIC));                       // 0x4B400000 + f
+  const bool left = yc < t.ystar;
+  float thr;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(thr) : "r"(t.thr_addr + (fb << t.thr_shift) + (left ? t.nr_off : 0u)));
+  near_min = min(near_min, __float_as_uint(yc) - __float_as_uint(thr) + 8u);
+  return int(fb - 0x4B400000u) + (((yc >= thr) != left) ? 1 : 0);
+}
+// four int32 codes -> four saturated int8 codes in one word (see pack4_sat)
+__device__ __forceinline__ uint32_t pack4_sat_int(int a, int b, int c, int d) {
+  uint32_t hi, out;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(out) : "r"(b), "r"(a), "r"(hi));
+  return out;
+}
+
 // floor(log2(|a|)) for finite non-zero a (normal or subnormal)
 __device__ __forceinline__ int ilog2f(float a) {
   uint32_t u = __float_as_uint(a) & 0x7fffffffu;

@@ -4,6 +4,7 @@
 // neighbourhood of the threshold is probed so that a segment whose code is not a clean step is flagged `slow`
 // (the epilogue then evaluates erf directly for every y that lands in it).
 #include <cmath>
+#include <vector>
 #include "common.cuh"
 
 namespace p2v {
@@ -66,6 +67,159 @@ __global__ void __launch_bounds__(128) build_gelu_table_kernel(GeluTabHeader hd,
   entries[i] = make_uint2(thr_bits, (uint32_t(below) & 0xffu) | ((uint32_t(above) & 0xffu) << 8) | (slow ? 0x80000000u : 0u));
 }
 
+// ------------------------------------------------------------------------------------------------
+// second form (common.cuh: GeluStepsHeader): exact per-code thresholds on both branches + a segment-wise linear map
+// ------------------------------------------------------------------------------------------------
+// thread i: threshold of code boundary c = cr0 + i (right of y*: smallest y with code >= c) or, for i >= nr, c = cr0 + i - nr
+// (left of y*: smallest y with code < c, the code being non-increasing in y there); +-inf when the boundary is never / always
+// crossed on that branch.  A threshold whose neighbourhood is not a clean step outside the +-8 ulp band clears *ok.
+__global__ void __launch_bounds__(128) build_gelu_steps_kernel(GeluStepsHeader h, float ro, int cr0, float* __restrict__ thr, int* __restrict__ ok) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h.nr + h.nl) return;
+  const bool left = i >= h.nr;
+  const int c = cr0 + (left ? i - h.nr : i);
+  auto F = [&](uint32_t k) { return gelu_code_direct(key2f(k), ro); };
+  const uint32_t k_star = f2key(h.ystar), k_lo = left ? f2key(h.ymin) : k_star, k_hi = left ? k_star : f2key(h.ymax);
+  // on [k_lo, k_hi] the predicate Q(k) = (code >= c) on the right branch, (code < c) on the left one, goes from false to true
+  auto Q = [&](uint32_t k) { return left ? F(k) < c : F(k) >= c; };
+  const float inf = __int_as_float(0x7f800000);
+  float out;
+  bool bad = false;
+  if (Q(k_lo)) {
+    out = left ? -inf : -inf;           // true on the whole branch: right "y >= -inf", left "code < c everywhere" i.e. never code >= c
+  } else if (!Q(k_hi)) {
+    out = inf;                          // false on the whole branch
+  } else {
+    uint32_t lo = k_lo, hi = k_hi;
+    while (hi - lo > 1u) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (Q(mid)) hi = mid; else lo = mid;
+    }
+    out = key2f(hi);
+    for (uint32_t d = 9; d <= 64; ++d) {
+      if (hi - k_lo >= d) bad |= Q(hi - d);
+      if (k_hi - hi >= d) bad |= !Q(hi + d);
+    }
+    const uint32_t span = k_hi - k_lo;
+    for (int s = 1; s < 32; ++s) {
+      const uint32_t k = k_lo + uint32_t((uint64_t(span) * s) >> 5);
+      if (k + 8u < hi) bad |= Q(k);
+      if (k > hi + 8u) bad |= !Q(k);
+    }
+    bad |= fabsf(out) < 1e-30f;         // the ulp-distance test needs a threshold away from +-0
+  }
+  thr[i] = out;
+  if (bad) atomicExch(ok, 0);
+}
+
+// Self-check with the epilogue's own code path (replicated shared-memory tables, gelu_steps_code): +-256 ulps around every
+// threshold, a uniform grid over the active range and beyond, and a sweep of magnitudes; any y that is not sent to the direct
+// evaluation (near_min > 16) must get exactly the direct code.  A mismatch clears *ok.
+__global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __restrict__ table, float ro, int* __restrict__ ok) {
+  extern __shared__ uint8_t vsm[];
+  const uint32_t base = (uint32_t(__cvta_generic_to_shared(vsm)) + 255u) & ~255u;
+  gelu_steps_fill_smem(table, base, int(threadIdx.x), int(blockDim.x));
+  __syncthreads();
+  const GeluSteps t = gelu_steps_view(table, base, int(threadIdx.x) & 31);
+  const GeluStepsHeader h = *reinterpret_cast<const GeluStepsHeader*>(reinterpret_cast<const char*>(table) + P2V_GELU_STEPS_OFFSET);
+  const float* thr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(table) + P2V_GELU_STEPS_OFFSET + sizeof(GeluStepsHeader) +
+                                                    8 * P2V_GELU_STEPS_MAX_SEG);
+  bool bad = false;
+  auto check = [&](float y) {
+    uint32_t nm = 0xffffffffu;
+    const int c = min(max(gelu_steps_code(y, t, nm), -128), 127);
+    if (nm > 16u && c != gelu_code_direct(y, ro)) bad = true;
+  };
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  const long long n1 = (long long)(h.nr + h.nl) * 513;
+  for (long long j = gid; j < n1; j += gsz) {
+    const float v = thr[j / 513];
+    if (fabsf(v) < 1e30f) check(key2f(f2key(v) + uint32_t(int(j % 513) - 256)));
+  }
+  const long long n2 = 1ll << 21;
+  const float a = h.ymin - 1.5f, w = (h.ymax - h.ymin + 3.0f) / float(n2);
+  for (long long j = gid; j < n2; j += gsz) check(a + w * float(j));
+  for (long long j = gid; j < 8192; j += gsz) {
+    const float m = exp2f(-100.0f + 200.0f * float(j >> 1) / 4096.0f);
+    check((j & 1) ? -m : m);
+  }
+  if (gid == 0) { check(0.0f); check(-0.0f); check(h.ymin); check(h.ymax); check(h.ystar); }
+  if (bad) atomicExch(ok, 0);
+}
+
+static double gelu_f64(double y) { return 0.5 * y * (1.0 + erf(y * 0.70710678118654752440)); }
+
+// host side of the second form: active range, segment map, table dimensions.  false = this scale is not tabulated.
+static bool plan_gelu_steps(float out_scale, GeluStepsHeader& h, std::vector<float2>& seg, int& cr0) {
+  const double so = out_scale, ro = 1.0 / so;
+  const float ystar = -0.7517916f;
+  const double gmin = gelu_f64(ystar);
+  if (-gmin * ro <= 0.45 || so > 0.25) return false;          // (almost) no negative codes: not worth a table
+  double lo = 0.0, hi = 300.0 * so + 10.0;                     // ymax: gelu = 128.2 * so (every y above saturates to 127)
+  for (int it = 0; it < 200; ++it) { const double mid = 0.5 * (lo + hi); if (gelu_f64(mid) < 128.2 * so) lo = mid; else hi = mid; }
+  const double ymax = hi;
+  lo = -40.0; hi = ystar;                                      // ymin: gelu = -0.4 * so left of the minimum (every y below has code 0)
+  for (int it = 0; it < 200; ++it) { const double mid = 0.5 * (lo + hi); if (gelu_f64(mid) > -0.4 * so) lo = mid; else hi = mid; }
+  const double ymin = lo;
+  cr0 = int(floor(gmin * ro + 0.5)) - 2;
+  h.ymin = float(ymin); h.ymax = float(ymax); h.ystar = ystar;
+  h.nr = 131 - cr0; h.nl = 3 - cr0; h.k1 = 1 - cr0; h.ok = 1;
+  for (int k = 0; k < 5; ++k) h.pad[k] = 0;
+  const int entries = h.nr + h.nl;
+  if (entries > P2V_GELU_STEPS_MAX_THR) return false;
+  if (entries * 128 <= 26 * 1024) h.rep_log2 = 5;
+  else if (entries * 64 <= 26 * 1024) h.rep_log2 = 4;
+  else return false;
+  for (int nseg = 16; nseg <= P2V_GELU_STEPS_MAX_SEG; nseg *= 2) {
+    const double inv_w = double(nseg) / (double(h.ymax) - double(h.ymin)) * (1.0 - 1e-4);
+    h.nseg = nseg; h.inv_w = float(inv_w); h.soff = float(-double(h.ymin) * double(h.inv_w) - 0.5 + 5e-4);
+    seg.assign(nseg, make_float2(0.f, 0.f));
+    double worst = 0.0;
+    for (int s = 0; s < nseg; ++s) {      // y with RNE(y * inv_w + soff) == s, widened by 2 % of a segment, clipped to the active range
+      double a = (double(s) - 0.52 - double(h.soff)) / double(h.inv_w), b = (double(s) + 0.52 - double(h.soff)) / double(h.inv_w);
+      a = std::max(a, double(h.ymin)); b = std::min(b, double(h.ymax));
+      if (!(b > a)) { seg[s] = make_float2(0.f, float(gelu_f64(std::min(std::max(a, double(h.ymin)), double(h.ymax))) * ro - 0.5)); continue; }
+      const double A = (gelu_f64(b) - gelu_f64(a)) * ro / (b - a);
+      double dmin = 1e300, dmax = -1e300;
+      for (int j = 0; j <= 128; ++j) {
+        const double y = a + (b - a) * j / 128.0, d = gelu_f64(y) * ro - A * y;
+        dmin = std::min(dmin, d); dmax = std::max(dmax, d);
+      }
+      worst = std::max(worst, 0.5 * (dmax - dmin));
+      seg[s] = make_float2(float(A), float(0.5 * (dmax + dmin) - 0.5));
+    }
+    if (worst <= 0.30) return true;
+  }
+  return false;
+}
+
+// builds the second form behind the first in `table_dev`; synchronises `stream` to read the verdict back
+static int build_gelu_steps(float out_scale, void* table_dev, cudaStream_t stream) {
+  GeluStepsHeader h;
+  std::vector<float2> seg;
+  int cr0 = 0;
+  char* base = reinterpret_cast<char*>(table_dev) + P2V_GELU_STEPS_OFFSET;
+  if (!plan_gelu_steps(out_scale, h, seg, cr0)) return 3;
+  cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, stream);
+  cudaMemcpyAsync(base + sizeof(h), seg.data(), seg.size() * sizeof(float2), cudaMemcpyHostToDevice, stream);
+  int* ok_dev = &reinterpret_cast<GeluStepsHeader*>(base)->ok;
+  float* thr_dev = reinterpret_cast<float*>(base + sizeof(h) + 8 * P2V_GELU_STEPS_MAX_SEG);
+  build_gelu_steps_kernel<<<(h.nr + h.nl + 127) / 128, 128, 0, stream>>>(h, 1.0f / out_scale, cr0, thr_dev, ok_dev);
+  const size_t smem = gelu_steps_smem_bytes(h) + 256;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(verify_gelu_steps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P2V_GELU_STEPS_SMEM_MAX + 256));
+    attr = true;
+  }
+  verify_gelu_steps_kernel<<<64, 256, smem, stream>>>(table_dev, 1.0f / out_scale, ok_dev);
+  count_launch(2);
+  if (int r = check_launch("build_gelu_steps")) return r;
+  int ok = 0;
+  cudaMemcpyAsync(&ok, ok_dev, sizeof(int), cudaMemcpyDeviceToHost, stream);
+  if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("build_gelu_steps: %s", cudaGetErrorString(cudaGetLastError())); return 2; }
+  return ok ? 0 : 3;
+}
+
 int launch_build_gelu_table(float out_scale, void* table_dev, cudaStream_t stream) {
   int ex = 0;
   const float m = frexpf(out_scale, &ex);
@@ -82,7 +236,8 @@ int launch_build_gelu_table(float out_scale, void* table_dev, cudaStream_t strea
   build_gelu_table_kernel<<<(hd.n + 127) / 128, 128, 0, stream>>>(hd, 1.0f / out_scale,
                                                                    reinterpret_cast<uint2*>(reinterpret_cast<char*>(table_dev) + sizeof(hd)));
   count_launch();
-  return check_launch("build_gelu_table");
+  if (int r = check_launch("build_gelu_table")) return r;
+  return build_gelu_steps(out_scale, table_dev, stream);             // both forms or none: the caller passes one pointer to every kernel
 }
 
 }  // namespace p2v

@@ -48,7 +48,7 @@ struct PairGeom {
   int bres;         // 1: this CTA's half of the W column tile (all of K) stays resident in shared memory, only A streams;
                     //    tiles are then walked row-block fastest in one contiguous range per CTA pair, so W is reloaded only
                     //    when the range crosses into the next column tile.  0: A and W stream together, tiles column fastest.
-  uint32_t stage_bytes, off_bres, off_stg, off_prm;   // shared-memory layout relative to the 1024-aligned base
+  uint32_t stage_bytes, off_bres, off_stg, off_prm, off_gst;   // shared-memory layout relative to the 1024-aligned base
 };
 constexpr int P_MAX_STAGES = 8;
 
@@ -188,10 +188,11 @@ __device__ __forceinline__ float quant_pot(float x) { return fadd(x, RMAGIC); }
 // Columns are processed four at a time; a group in which some column's reciprocal bounds disagree (a quotient within a few
 // ulps of a rounding tie, ~1e-5 of the quotients) is redone on the spot with the IEEE division for those columns - the branch
 // is short and keeps no extra state alive, so a hit costs a few hundred cycles of one warp instead of stalling the tile.
-template <int EPI, bool POT>
-__device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const int (&acc)[16], const uint4 resx, uint4& out) {
+template <int EPI, bool POT, bool GST>
+__device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const int (&acc)[16], const uint4 resx, uint4& out, const GeluSteps& gst) {
   uint32_t ow[4];
   const uint32_t rw[4] = {resx.x, resx.y, resx.z, resx.w};
+  uint32_t gst_near = 0xffffffffu;
 #pragma unroll
   for (int j4 = 0; j4 < 16; j4 += 4) {
     const float4 S4 = *reinterpret_cast<const float4*>(prm + PR_S * 64 + j4);
@@ -230,6 +231,15 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
     } else if (POT && EPI == P2V_EPI_REQUANT) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) t[e] = quant_pot(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]));   // S, B pre-divided by out_scale
+    } else if (POT && EPI == P2V_EPI_GELU && GST) {
+      // step tables (common.cuh: gelu_steps_code): ~22 instructions per column instead of ~40 for erff.  No branch inside the
+      // chunk, so the 16 columns' lookup chains (two dependent shared-memory loads each) overlap; the near-threshold test is
+      // taken once per chunk, after the loop.
+      int q[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) q[e] = gelu_steps_code(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]), gst, gst_near);
+      ow[j4 >> 2] = pack4_sat_int(q[0], q[1], q[2], q[3]);
+      continue;
     } else if (POT && EPI == P2V_EPI_GELU) {
       const float4 R4 = *reinterpret_cast<const float4*>(prm + PR_RO * 64 + j4);
       const float Rv[4] = {R4.x, R4.y, R4.z, R4.w};
@@ -258,6 +268,25 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
       }
     }
     ow[j4 >> 2] = pack4_sat(t[0], t[1], t[2], t[3]);
+  }
+  if (POT && EPI == P2V_EPI_GELU && GST) {
+    if (gst_near <= 16u) {     // some y within 8 ulps of the threshold it consulted: the chunk takes the direct evaluation
+#pragma unroll 1
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        const float4 S4 = *reinterpret_cast<const float4*>(prm + PR_S * 64 + j4);
+        const float4 B4 = *reinterpret_cast<const float4*>(prm + PR_B * 64 + j4);
+        const float4 R4 = *reinterpret_cast<const float4*>(prm + PR_RO * 64 + j4);
+        const int a0 = j4 == 0 ? acc[0] : j4 == 4 ? acc[4] : j4 == 8 ? acc[8] : acc[12];
+        const int a1 = j4 == 0 ? acc[1] : j4 == 4 ? acc[5] : j4 == 8 ? acc[9] : acc[13];
+        const int a2 = j4 == 0 ? acc[2] : j4 == 4 ? acc[6] : j4 == 8 ? acc[10] : acc[14];
+        const int a3 = j4 == 0 ? acc[3] : j4 == 4 ? acc[7] : j4 == 8 ? acc[11] : acc[15];
+        const uint32_t w = pack4_sat_int(gelu_code_direct(__fmaf_rn(__int2float_rn(a0), S4.x, B4.x), R4.x),
+                                         gelu_code_direct(__fmaf_rn(__int2float_rn(a1), S4.y, B4.y), R4.y),
+                                         gelu_code_direct(__fmaf_rn(__int2float_rn(a2), S4.z, B4.z), R4.z),
+                                         gelu_code_direct(__fmaf_rn(__int2float_rn(a3), S4.w, B4.w), R4.w));
+        if (j4 == 0) ow[0] = w; else if (j4 == 4) ow[1] = w; else if (j4 == 8) ow[2] = w; else ow[3] = w;
+      }
+    }
   }
   out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
@@ -294,7 +323,7 @@ __device__ __forceinline__ void store_col(float* prm, int c, const RawCol& r) {
   }
 }
 
-template <int EPI, bool POT>
+template <int EPI, bool POT, bool GST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                  const __grid_constant__ CUtensorMap tmR, EpiParams p, PairGeom g) {
@@ -332,6 +361,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_pair(smem_u32(&tmem_slot), 512);
+  if (GST) gelu_steps_fill_smem(p.gelu_table, ring + g.off_gst, int(threadIdx.x), P_THREADS);   // replicated GELU step tables
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA signal
@@ -449,6 +479,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // byte offset of this lane's 16-byte chunk c inside the warp's staging block (row pitch W bytes)
     const uint32_t row_off = uint32_t(lane) * uint32_t(W);
     const uint32_t xr = g.swz == 2 ? (uint32_t(lane) >> 1) & 3u : (g.swz == 1 ? (uint32_t(lane) >> 2) & 1u : 0u);
+    GeluSteps gst = {};
+    if (GST) gst = gelu_steps_view(p.gelu_table, ring + g.off_gst, lane);
     RawCol nx0, nx1;
     TileIter ti(g, pair, npairs);
     {
@@ -506,7 +538,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           resx.x ^= 0x80808080u; resx.y ^= 0x80808080u; resx.z ^= 0x80808080u; resx.w ^= 0x80808080u;
         }
         uint4 o;
-        pair_chunk<EPI, POT>(prm + c * 16, cur, resx, o);
+        pair_chunk<EPI, POT, GST>(prm + c * 16, cur, resx, o, gst);
         if (c == 0) {
           if (!RESID) {                     // the previous tile's store must have finished reading this block
             if (lane == 0) bulk_wait_read0();
@@ -581,11 +613,11 @@ static int max_pairs() {
 
 constexpr size_t P_SMEM_BUDGET = 227 * 1024 - 1024;    // dynamic shared memory per CTA, static part and slack taken off
 
-template <int EPI, bool POT>
+template <int EPI, bool POT, bool GST = false>
 static int launch_pair(const p2v_gemm_args& a, PairGeom g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                        const CUtensorMap& tmR, cudaStream_t stream) {
   // shared-memory plan: [operand ring][resident W half-tile][output / residual staging][16 warp-private constant tables]
-  const size_t prm_bytes = size_t(P_EPI_WARPS) * prm_rows<EPI, POT>() * 64 * 4;
+  const size_t prm_bytes = size_t(P_EPI_WARPS) * prm_rows<EPI, POT>() * 64 * 4 + (GST ? P2V_GELU_STEPS_SMEM_MAX : 0);   // + GELU step tables
   const size_t bhalf = size_t(g.BN / 2) * PBK;
   static const int force_bres = getenv("P2V_PAIR_BRES") ? atoi(getenv("P2V_PAIR_BRES")) : -1;    // perf triage only
   for (;;) {
@@ -605,10 +637,11 @@ static int launch_pair(const p2v_gemm_args& a, PairGeom g, const CUtensorMap& tm
     g.off_bres = uint32_t(g.nstages) * g.stage_bytes;
     g.off_stg = g.off_bres + uint32_t(g.bres ? bres_bytes : 0);
     g.off_prm = g.off_stg + uint32_t(stg_bytes);
+    g.off_gst = g.off_prm + uint32_t(P_EPI_WARPS) * prm_rows<EPI, POT>() * 64 * 4;
     break;
   }
   const size_t smem = 1024 + g.off_prm + prm_bytes;
-  auto kern = gemm_pair_kernel<EPI, POT>;
+  auto kern = gemm_pair_kernel<EPI, POT, GST>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P_SMEM_BUDGET));
@@ -657,6 +690,7 @@ int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
       return pot ? launch_pair<P2V_EPI_REQUANT, true>(a, g, tmA, tmB, tmO, tmR, stream)
                  : launch_pair<P2V_EPI_REQUANT, false>(a, g, tmA, tmB, tmO, tmR, stream);
     case P2V_EPI_GELU:
+      if (pot && a.gelu_table) return launch_pair<P2V_EPI_GELU, true, true>(a, g, tmA, tmB, tmO, tmR, stream);
       return pot ? launch_pair<P2V_EPI_GELU, true>(a, g, tmA, tmB, tmO, tmR, stream)
                  : launch_pair<P2V_EPI_GELU, false>(a, g, tmA, tmB, tmO, tmR, stream);
     default:

@@ -158,6 +158,36 @@ def test_gemm_gelu_step_table_equals_direct_erf(log2so):
         assert int(res[0].float().abs().sum()) > 0
 
 
+@pytest.mark.parametrize("log2so", [-2, -3, -4, -5, -6, -7])
+def test_gemm_pair_gelu_step_tables_equal_direct_erf(log2so):
+    """CTA-pair kernel: the second form of the GELU table (segment map + exact per-code thresholds, conflict-free shared-memory
+    lookups) must reproduce the direct erf epilogue bit for bit - random pre-activations, fine sweeps that land many y within
+    ulps of thresholds on both sides of GELU's minimum, and saturating / far-negative arguments"""
+    so = 2.0 ** log2so
+    tab = ops.gelu_table(so, DEV)
+    assert tab is not None
+    M, N, K = 2048 + 77, 256, 64
+    A, W, _ = _gemm_inputs(M, N, K, 170 + log2so)
+    Ad, Wd = A.to(DEV), W.to(DEV)
+    outs = torch.full((N,), so, device=DEV)
+    cases = ((2.0 ** -12, torch.randn(N) * 0.5), (2.0 ** -16, torch.linspace(-9.0, 5.0, N)), (2.0 ** -20, torch.linspace(-1.5, 0.5, N)),
+             (2.0 ** -18, torch.linspace(-0.9, -0.6, N)), (2.0 ** -8, torch.randn(N) * 3), (2.0 ** -22, torch.linspace(-4.0, 130.0 * so, N)))
+    try:
+        ops.set_gemm_variant(2)
+        for acc_scale, bias in cases:
+            s = torch.full((N,), acc_scale, device=DEV)
+            res = []
+            for table in (None, tab):
+                o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
+                ops.gemm(ops.gemm_args(Ad, Wd, ops.EPI_GELU, s, bias=bias.to(DEV), out_scale=outs, out_i8=o8, pot=True, gelu_table=table))
+                res.append(o8)
+            torch.cuda.synchronize()
+            assert torch.equal(res[0], res[1]), "acc_scale 2^%d: %d codes differ between step tables and direct erf" % (
+                int(np.log2(acc_scale)), int((res[0] != res[1]).sum()))
+    finally:
+        ops.set_gemm_variant(0)
+
+
 def test_gelu_table_rejects_unsupported_scales():
     assert ops.gelu_table(0.3, DEV) is None and ops.gelu_table(2.0 ** -9, DEV) is None
 

@@ -33,7 +33,7 @@ def main():
             kw = dict(bias=bias, out_scale=out_scale, out_i8=o8, pot=True)
             if epi == ops.EPI_RESIDUAL:
                 kw.update(mid_scale=mid, res_scale=rs, res=res)
-            if epi == ops.EPI_GELU and v == 1:
+            if epi == ops.EPI_GELU:
                 kw.update(gelu_table=ops.gelu_table(2.0 ** -5, dev))
             args = ops.gemm_args(A, W, epi, acc_scale, **kw)
             for _ in range(3 if not os.environ.get("GEMM_BENCH_ONCE") else 2):

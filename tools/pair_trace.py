@@ -7,7 +7,7 @@ from p2vit_b200 import ops
 kind = sys.argv[1] if len(sys.argv) > 1 else "proj"
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 384
 M = 256 * 197
-K, N, epi = {"proj": (D, D, ops.EPI_RESIDUAL), "fc2": (4 * D, D, ops.EPI_RESIDUAL), "qkv": (D, 3 * D, ops.EPI_REQUANT)}[kind]
+K, N, epi = {"proj": (D, D, ops.EPI_RESIDUAL), "fc2": (4 * D, D, ops.EPI_RESIDUAL), "qkv": (D, 3 * D, ops.EPI_REQUANT), "fc1": (D, 4 * D, ops.EPI_GELU)}[kind]
 dev = "cuda"
 g = torch.Generator().manual_seed(0)
 A = torch.randint(-128, 128, (M, K), generator=g, dtype=torch.int32).to(torch.int8).to(dev)
@@ -20,6 +20,8 @@ if epi == ops.EPI_RESIDUAL:
               res=torch.randint(-128, 128, (M, N), generator=g, dtype=torch.int32).to(torch.int8).to(dev))
 else:
     kw["out_scale"] = torch.full((N,), 2.0 ** -5, device=dev)
+    if epi == ops.EPI_GELU:
+        kw["gelu_table"] = ops.gelu_table(2.0 ** -5, dev)
 trace = torch.zeros(2 * 19 * 64 * 4, dtype=torch.int64, device=dev)
 ops.set_gemm_variant(2)
 args = ops.gemm_args(A, W, epi, torch.full((N,), 2.0 ** -13, device=dev), **kw)
