@@ -224,7 +224,7 @@ static int g_gemm_variant = 0;   // 0 auto, 1 one-tile-per-group kernel (this fi
 void set_gemm_variant(int v) { g_gemm_variant = v; }
 
 int launch_gemm_tc(const p2v_gemm_args& a, cudaStream_t stream) {
-  if (g_gemm_variant != 1 && gemm_pair_supported(a) && (g_gemm_variant == 2 || a.M >= 1024)) return launch_gemm_pair(a, stream);
+  if (g_gemm_variant != 1 && gemm_pair_supported(a) && (g_gemm_variant == 2 || a.M >= 256)) return launch_gemm_pair(a, stream);
   // BN = 128: 32 KB / smem stage, 4 x 128 TMEM columns; 5 stages, or 4 stages + the 32 KB GELU step table
   if (a.epilogue == P2V_EPI_GELU && a.pot_scales && a.gelu_table) return launch_tc_bn<128, 4, true>(a, stream);
   return launch_tc_bn<128, 5, false>(a, stream);
