@@ -15,10 +15,17 @@
 // MMA / TMA latency hides under the other's integer work.  Two softmax warps share each TMEM lane quarter (32 query rows) and
 // split the key axis in 16-column units; their partial row max / row sum meet through spare TMEM columns (tcgen05.st, a
 // 64-thread named barrier, tcgen05.ld) - the kernel is bound by the softmax warps' instruction issue, so 16 of them per SM
-// instead of 8 is what hides the TMEM / shared-memory latencies.  Pass 2 writes d = max - code back over S in TMEM so
-// pass 3 does not requantise again.  A CTA walks heads blockIdx.x, blockIdx.x + gridDim.x, ...; each head is 1 or 2 query
-// tiles of 128 rows.
+// instead of 8 is what hides the TMEM / shared-memory latencies.  Pass 2 writes the shared-memory address of the table
+// entry of d = max - code back over S in TMEM so pass 3 does not requantise again.  A CTA walks heads blockIdx.x,
+// blockIdx.x + gridDim.x, ...; each head is 1 or 2 query tiles of 128 rows.
+//
+// Both element loops are written for the pipe split of the SM sub-partition (ALU pipe: integer add / logic / min-max /
+// shifts, FMA pipe: FFMA / FMUL / FADD, each one warp instruction per two cycles): the clamps of pass 2 are an FFMA.SAT,
+// table indices leave an FFMA already scaled to byte offsets, pass 3 gets 2^(15-code) and its guard band from the
+// exponent field with float multiplies - 4 ALU + 3 FMA (pass 2) and 4.5 ALU + 5 FMA (pass 3) instructions per score
+// instead of 6 + 2 and 10 + 4.
 #include <climits>
+#include <cmath>
 #include <type_traits>
 #include "tc_common.cuh"
 
@@ -35,9 +42,15 @@ constexpr uint32_t AT_OFF_K = 2 * 128 * AT_DH;                    // [224 x 64]
 constexpr uint32_t AT_OFF_V = AT_OFF_K + AT_KV_ROWS * AT_DH;      // [224 x 64]
 constexpr uint32_t AT_OFF_P = AT_OFF_V + AT_KV_ROWS * AT_DH;      // 2 planes x 2 chunks x [128 x 128]
 constexpr uint32_t AT_P_CHUNK = 128 * 128, AT_P_PLANE = 2 * AT_P_CHUNK;
-constexpr uint32_t AT_OFF_LUT = AT_OFF_P + 2 * AT_P_PLANE;        // uint2 [256] (hi, lo) + float [256] reciprocals
-constexpr uint32_t AT_SMEM = AT_OFF_LUT + 256 * 8 + 256 * 4;
-constexpr size_t AT_SMEM_ALLOC = AT_SMEM + 1024;                  // alignment slack
+// exp_int table: entries -1..255 of 8 bytes (hi, lo); entry -1 repeats entry 0 (a code above 127 saturates, and then the row
+// max is 127).  Reciprocal table: the same 8-byte stride AT_RCP_OFF further on, so one address serves both lookups.
+constexpr uint32_t AT_OFF_LUT = AT_OFF_P + 2 * AT_P_PLANE;
+constexpr uint32_t AT_RCP_OFF = 2064;
+constexpr uint32_t AT_OFF_BARS = AT_OFF_LUT + AT_RCP_OFF + 2064;  // 6 mbarriers + the TMEM slot
+constexpr uint32_t AT_SMEM = AT_OFF_BARS + 64;
+// The kernel has no static shared memory, so its dynamic window starts at the 1 KB the system reserves per CTA and is
+// 1024-aligned already; 128 bytes of slack, checked at run time (two CTAs of 112 KB + tables have to fit one SM).
+constexpr size_t AT_SMEM_ALLOC = AT_SMEM + 128;
 static_assert(AT_OFF_K % 1024 == 0 && AT_OFF_V % 1024 == 0 && AT_OFF_P % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 struct AttTcParams {
@@ -50,29 +63,30 @@ struct AttTcParams {
   int8_t* out;
 };
 
-// log_round(RNE(fl(tot / e))) of layers.py:376-381,422-427 without the division.
-//   x = RNE(q), q = fl(tot/e) >= 1;  big(x) = #{t in {2, 3, 6, 12, 24, ...} : x >= t}, and x >= t <=> q + 1/2 >= t up to
-//   the tie rule.  With y = tot*rcp + 1/2 and w = y*(2/3):  big = [y >= 2] + max(0, floor(log2 w)).  tot*rcp, y and w
-//   are each within a few ulps of the exact values, so the result can only differ from the reference when w is
-//   within 16 ulps of a power of two >= 2 or y within 1e-5 of 2 (`near`): those take the exact path (log2_code).
-// Returns 2^(15-big) (0 when big >= 16).
+// log_round(RNE(fl(tot / e))) of layers.py:376-381,422-427 without the division, as 2^(15-big) (0 when big >= 16).
+//   x = RNE(q), q = fl(tot/e) >= 1;  big(x) = #{t in {2, 3, 6, 12, 24, ...} : x >= t}, and x >= t <=> q + 1/2 >= t up to the
+//   tie rule.  g(q) = min(2q - 1, (4q + 2)/3) is increasing, equals 2 at q + 1/2 = 2 and 2^(j+2) at q + 1/2 = 3 * 2^j, so
+//   big = floor(log2 g) = the exponent field of g.  g is computed from the table's reciprocal with two FFMAs (a few ulps off
+//   the exact value), so the result can only differ from the reference when g is within 16 ulps of a power of two: with
+//   pf = 2^(15-E) (E = exponent of g, an integer subtraction on the exponent field), g * pf lies in [2^15, 2^16) and the
+//   guard is |g*pf - 1.5*2^15| >= 2^14 - 16 ulps; `gmax` collects it over a unit, which is then redone with the IEEE
+//   division (log2_code).  pf + 2^23 leaves the integer 2^(15-E) (0 from E = 16 on: 0.5 rounds to even) in the low mantissa bits.
 __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n) {   // PTX shr: amounts > 31 give 0
   uint32_t r;
   asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
   return r;
 }
-// `near_min` / `y2_min` collect the guard-band distances of a unit's elements: the unit is redone exactly when
-// near_min < 32 (some w within 16 ulps of a power of two >= 2; w + 16 ulps below 2 is mapped to a huge value by the xor)
-// or y2_min < 1e-5.
-__device__ __forceinline__ uint32_t prob_bits_fast(float tot, float rcp, uint32_t& near_min, float& y2_min) {
-  const float y = fadd(fmul(tot, rcp), 0.5f);
-  // 2/3 rounded up twice: y >= 1.5 - 1 ulp always (e <= tot), so w >= 1 and the exponent field needs no clamp; the
-  // 1-ulp shift of the thresholds is inside the guard band
-  const float w = fmul(y, 0.66666674613952636718750f);
-  const uint32_t wb = __float_as_uint(w);
-  near_min = min(near_min, ((wb + 16u) & 0x407fffffu) ^ 0x40000000u);
-  y2_min = fminf(y2_min, fabsf(fsub(y, 2.0f)));
-  return shr_clamp(y >= 2.0f ? 0x4000u : 0x8000u, (wb >> 23) - 127u);
+constexpr float AT_GUARD = 16384.f - 0.0625f;     // 16 ulps of [2^15, 2^16)
+__device__ __forceinline__ uint32_t prob_bits_fast(float tot2, float tot43, float rcp, float& gmax) {
+  const float g = fminf(__fmaf_rn(tot2, rcp, -1.0f), __fmaf_rn(tot43, rcp, 0.666666686534881591796875f));
+  const float pf = __uint_as_float(0x86800000u - (__float_as_uint(g) & 0x7F800000u));     // 2^(15 - E), E = floor(log2 g)
+  gmax = fmaxf(gmax, fabsf(fadd(fmul(g, pf), -49152.f)));
+  return __float_as_uint(fadd(pf, 8388608.f));      // low 16 bits: 2^(15-E)
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const int (&r)[16]) {
   asm volatile(
@@ -96,29 +110,33 @@ __device__ __forceinline__ void quarter_exchange_sync(uint32_t quarter) {
   tc_fence_after();
 }
 
+// POTM: score_mult is a power of two (minmax observers), so S * mult is exact and one FFMA on the magic-biased integer does
+// the conversion, the scaling and the RNE together; otherwise the reference's separately rounded product is kept.
+template <bool POTM>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[6];
-  __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (base - smem_u32(smem_raw) + AT_SMEM > uint32_t(AT_SMEM_ALLOC)) __trap();     // dynamic window not aligned as assumed
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_qk = smem_u32(&bars[0]), bar_v = smem_u32(&bars[1]), bar_s = smem_u32(&bars[2]);
-  const uint32_t bar_p = smem_u32(&bars[3]), bar_o = smem_u32(&bars[4]), bar_free = smem_u32(&bars[5]);
+  const uint32_t bars = base + AT_OFF_BARS;
+  const uint32_t bar_qk = bars, bar_v = bars + 8, bar_s = bars + 16, bar_p = bars + 24, bar_o = bars + 32, bar_free = bars + 40;
+  volatile uint32_t& tmem_slot = *reinterpret_cast<volatile uint32_t*>(gbase + AT_OFF_BARS + 48);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T, H = p.H;
-  uint2* s_lut = reinterpret_cast<uint2*>(gbase + AT_OFF_LUT);
-  float* s_rcp = reinterpret_cast<float*>(gbase + AT_OFF_LUT + 256 * 8);
+  uint2* s_lut = reinterpret_cast<uint2*>(gbase + AT_OFF_LUT);                       // s_lut[1 + d]
+  float2* s_rcp = reinterpret_cast<float2*>(gbase + AT_OFF_LUT + AT_RCP_OFF);        // s_rcp[1 + d].x
 
   if (threadIdx.x == 0) {
     mbar_init(bar_qk, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
     mbar_init(bar_p, AT_SM_WARPS); mbar_init(bar_free, AT_SM_WARPS);
     fence_mbar_init();
   }
-  if (warp == AT_SM_WARPS) tmem_alloc<AT_TMEM_COLS>(smem_u32(&tmem_slot));
-  for (int i = threadIdx.x; i < 256; i += AT_THREADS) {
-    s_lut[i] = make_uint2(p.lut->hi[i], p.lut->lo[i]);
-    s_rcp[i] = fdiv(1.0f, p.lut->exp_f32[i]);
+  if (warp == AT_SM_WARPS) tmem_alloc<AT_TMEM_COLS>(base + AT_OFF_BARS + 48);
+  for (int i = threadIdx.x; i < 257; i += AT_THREADS) {
+    const int d = max(i - 1, 0);
+    s_lut[i] = make_uint2(p.lut->hi[d], p.lut->lo[d]);
+    s_rcp[i] = make_float2(fdiv(1.0f, p.lut->exp_f32[d]), 0.f);
   }
   tc_fence_before();
   __syncthreads();
@@ -199,7 +217,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int rloc = int(quarter) * 32 + lane;
     const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
     const float mult = p.score_mult;
-    const uint32_t lut32 = base + AT_OFF_LUT, rcp32 = base + AT_OFF_LUT + 256 * 8;    // 32-bit shared addresses of the tables
+    const uint32_t lut32 = base + AT_OFF_LUT + 8u;        // shared address of exp_int[0]
+    // RMAGIC + S*mult in one rounding from t = RMAGIC + S (exact for |S| < 2^22; |S| <= 64 * 2^14 here)
+    const float potm_c = fsub(RMAGIC, fmul(RMAGIC, mult));
     // key axis in 16-column units: units with a column < T hold scores, the P operand needs 2 * ksteps units (zero padded)
     const int units_p = 2 * p.ksteps, units_s = (T + 15) >> 4, u_mid = (units_p + 1) >> 1;
     const int u_begin = half ? u_mid : 0, u_end = half ? units_p : u_mid;
@@ -236,9 +256,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             smax = max(smax, int(o0));
           }
           const int mx = sat_s8(fmul(float(smax), mult));
-          // ---- pass 2: exact row sum of exp_int(max - code) over my units; d = max - code goes back to TMEM over S
-          //      code = sat(RNE(fl(S * mult))): RNE through the magic constant (no F2I), the saturation is a clamp of d
-          const int mxb = 0x4B400000 + mx, dmax = mx + 128;
+          // ---- pass 2: exact row sum of exp_int(max - code) over my units; the table address of d = max - code goes back to
+          //      TMEM over S.  u = RMAGIC + RNE(S * mult); v = sat((code + 128) / 256) clamps the code to [-128, 128] (FFMA.SAT,
+          //      exact); RMAGIC + 2048 v has 8 (code_sat + 128) in its low mantissa bits, so one subtraction from
+          //      rowk = &exp_int[mx + 128] + bits(RMAGIC) gives &exp_int[mx - code_sat].  code_sat = 128 only when mx = 127: entry -1.
+          const uint32_t rowk = lut32 + uint32_t(mx + 128) * 8u + 0x4B400000u;
           unsigned long long sum = 0;
           auto sum_unit = [&](auto masked, int u) {
             int acc[16];
@@ -246,10 +268,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int nv = T - u * 16;
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              const int d = min(max(mxb - __float_as_int(fadd(fmul(__int2float_rn(acc[e]), mult), RMAGIC)), 0), dmax);
-              acc[e] = d;
+              const float uq = POTM ? __fmaf_rn(__int_as_float(acc[e] + 0x4B400000), mult, potm_c)
+                                    : fadd(fmul(__int2float_rn(acc[e]), mult), RMAGIC);
+              const float v = fma_sat(uq, 0.00390625f, -49151.5f);
+              const uint32_t addr = rowk - __float_as_uint(__fmaf_rn(v, 2048.f, RMAGIC));
+              acc[e] = int(addr);
               uint32_t vx, vy;
-              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "r"(lut32 + uint32_t(d) * 8u));
+              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "r"(addr));
               if (!decltype(masked)::value || e < nv) sum += (static_cast<unsigned long long>(vx) << 32) | vy;
             }
             tmem_st16(tlane + u * 16, acc);
@@ -260,11 +285,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           {
             uint32_t o0, o1;
             tmem_st2(tlane + AT_XSUM + 2 * half, uint32_t(sum), uint32_t(sum >> 32));
-            quarter_exchange_sync(quarter);           // also orders the d write-back before pass 3's loads
+            quarter_exchange_sync(quarter);           // also orders the address write-back before pass 3's loads
             tmem_ld2(tlane + AT_XSUM + 2 * (half ^ 1u), o0, o1);
             sum += (static_cast<unsigned long long>(o1) << 32) | o0;
           }
           const float tot = __ull2float_rn(sum);      // the exact integer sum (< 2^64: intmath.build_softmax_lut bounds the table), rounded once
+          const float tot2 = fmul(tot, 2.0f), tot43 = fmul(tot, 1.33333337306976318359375f);
           // ---- pass 3: probabilities 2^(15-code) as hi / lo byte planes in the UMMA K-major SW128 layout
           const uint32_t prow = base + AT_OFF_P + uint32_t(rloc) * 128u;
           const uint32_t sw = uint32_t(rloc & 7);
@@ -274,23 +300,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + AT_P_PLANE), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
           };
           auto prob_unit = [&](auto masked, int u) {
-            int dd[16];
-            tmem_ld16(tlane + u * 16, dd);
+            int aa[16];
+            tmem_ld16(tlane + u * 16, aa);
             const int nv = T - u * 16;
             uint32_t pv[16];
-            uint32_t near_min = 0xffffffffu;
-            float y2_min = 1.0f;
+            float gmax = 0.f;
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               float rcp;
-              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rcp) : "r"(rcp32 + uint32_t(dd[e]) * 4u));
-              pv[e] = prob_bits_fast(tot, rcp, near_min, y2_min);
+              asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(rcp) : "r"(uint32_t(aa[e])), "n"(AT_RCP_OFF));
+              pv[e] = prob_bits_fast(tot2, tot43, rcp, gmax);
             }
-            if (near_min < 32u || y2_min < 1e-5f) {   // some element sits next to a rounding / log2 boundary: redo the unit with the IEEE division
+            if (!(gmax < AT_GUARD)) {   // some element sits next to a rounding / log2 boundary (or is not finite): redo the unit with the IEEE division
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                const uint2 v = s_lut[dd[e]];
-                const uint32_t big = log2_code(tot, __ull2float_rn((static_cast<unsigned long long>(v.x) << 32) | v.y));
+                uint32_t vx, vy;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "r"(uint32_t(aa[e])));
+                const uint32_t big = log2_code(tot, __ull2float_rn((static_cast<unsigned long long>(vx) << 32) | vy));
                 pv[e] = shr_clamp(0x8000u, big);
               }
             }
@@ -302,7 +328,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 for (int e = 0; e < 4; ++e)
                   if (e4 * 4 + e >= nv) pv[e4 * 4 + e] = 0u;
               }
-              const uint32_t p01 = pv[e4 * 4] | (pv[e4 * 4 + 1] << 16), p23 = pv[e4 * 4 + 2] | (pv[e4 * 4 + 3] << 16);
+              const uint32_t p01 = __byte_perm(pv[e4 * 4], pv[e4 * 4 + 1], 0x5410), p23 = __byte_perm(pv[e4 * 4 + 2], pv[e4 * 4 + 3], 0x5410);
               lo[e4] = __byte_perm(p01, p23, 0x6420);
               hi[e4] = __byte_perm(p01, p23, 0x7531);
             }
@@ -397,11 +423,16 @@ int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC));
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC));
     P2V_REQUIRE(e == cudaSuccess, "attention_tc: cannot set %zu bytes of dynamic shared memory: %s", AT_SMEM_ALLOC, cudaGetErrorString(e));
   }
   const int grid = std::min(p.total_heads, 2 * sms);
-  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_ALLOC, stream>>>(tmQ, tmKV, p);
+  // power-of-two score multiplier in [2^-20, 2^8]: RMAGIC * (1 - mult) is then exact and so is the fused scaling
+  int mexp = 0;
+  const bool potm = std::frexp(a.score_mult, &mexp) == 0.5f && mexp >= -19 && mexp <= 9;
+  if (potm) attention_tc_kernel<true><<<grid, AT_THREADS, AT_SMEM_ALLOC, stream>>>(tmQ, tmKV, p);
+  else attention_tc_kernel<false><<<grid, AT_THREADS, AT_SMEM_ALLOC, stream>>>(tmQ, tmKV, p);
   count_launch();
   return check_launch("attention_tc");
 }

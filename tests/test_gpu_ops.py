@@ -484,6 +484,39 @@ def test_attention_tcgen05_vs_simt_many_heads(s_as, spread):
     assert int((a != 0).sum()) > a.numel() // 4   # not a degenerate case
 
 
+@pytest.mark.parametrize("s_as,spread,mult_fudge", [(2.0 ** -3, 41, 1.0), (2.0 ** -6, 128, 1.0), (2.0 ** -1, 20, 1.0), (2.0 ** -8, 128, 1.0),
+                                                    (2.0 ** -4, 60, 1.0), (2.0 ** -3, 41, 0.8731), (2.0 ** -5, 90, 1.377)])
+def test_attention_tcgen05_every_probability_code(s_as, spread, mult_fudge):
+    """Reads every softmax probability of the tcgen05 kernel back through P.V: with v = one key block's identity matrix the
+    output column c of row r is P[r, blk*64 + c] = 2^(15-code), and two output multipliers (2^-8: codes 0..7, 1: codes 9..15
+    and zero) resolve all of them.  Expected values come from the dp4a kernel's probability dump (itself pinned to the oracle
+    by test_attention_vs_oracle).  mult_fudge != 1 makes the score multiplier a non-power-of-two (ema / percentile observers:
+    separately rounded product path)."""
+    B, T, H = 24, 197, 6
+    qkv, (m1, _, lut), _ = _attention_case(B, T, H, seed=11, s_as=s_as, spread=spread)
+    m1 = float(torch.tensor(m1 * mult_fudge, dtype=torch.float32))
+    q5 = qkv.reshape(B, T, 3, H, 64)
+    probs = torch.empty(B, H, T, T, dtype=torch.uint8, device=DEV)
+    scratch = torch.empty((B * T, H * 64), dtype=torch.int8, device=DEV)
+    ops.attention(ops.attention_args(qkv, scratch, B, T, H, 64, m1, 2.0 ** -20, lut, probs, None), simt=True)
+    pc = probs.int()
+    P = torch.where(pc == 255, torch.zeros_like(pc), torch.bitwise_left_shift(torch.ones_like(pc), (15 - pc).clamp(min=0)))   # [B,H,T,T]
+    assert int((pc != 255).sum()) > pc.numel() // 8 and len(torch.unique(pc)) >= 2      # not a degenerate case
+    out = torch.empty((B * T, H * 64), dtype=torch.int8, device=DEV)
+    bad = 0
+    for blk in range(4):
+        nk = min(64, T - blk * 64)
+        q5[:, :, 2] = 0
+        idx = torch.arange(nk, device=DEV)
+        q5[:, blk * 64 + idx, 2, :, idx] = 1
+        for m2 in (2.0 ** -8, 1.0):
+            ops.attention(ops.attention_args(qkv, out, B, T, H, 64, m1, m2, lut))
+            got = out.reshape(B, T, H, 64).permute(0, 2, 1, 3)[..., :nk].int()                    # [B,H,T,nk]
+            want = (P[..., blk * 64: blk * 64 + nk].float() * m2).round().clamp(max=127).int()
+            bad += int((got != want).sum())
+    assert bad == 0, "%d probability read-backs differ between tcgen05 and dp4a attention" % bad
+
+
 # ------------------------------------------------------------------------------------------------ observers' kernels
 def test_minmax_and_mse_scores():
     torch.manual_seed(9)
