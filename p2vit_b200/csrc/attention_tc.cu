@@ -83,11 +83,6 @@ __device__ __forceinline__ uint32_t prob_bits_fast(float tot2, float tot43, floa
   gmax = fmaxf(gmax, fabsf(fadd(fmul(g, pf), -49152.f)));
   return __float_as_uint(fadd(pf, 8388608.f));      // low 16 bits: 2^(15-E)
 }
-__device__ __forceinline__ float fma_sat(float a, float b, float c) {
-  float r;
-  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const int (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"

@@ -97,14 +97,16 @@ __device__ __forceinline__ int gelu_code_table(float y, uint2 e, bool& slow) {
 struct GeluStepsHeader {   // 64 bytes, then float2 seg[P2V_GELU_STEPS_MAX_SEG], float thr[P2V_GELU_STEPS_MAX_THR]
   float ymin, ymax, inv_w, soff, ystar;
   int nseg, nr, nl, k1, rep_log2, ok;
-  int pad[5];
+  float seg_scale;         // nseg - 1 + 0.49: segment = RNE(sat((y * inv_w + soff) / seg_scale) * seg_scale)
+  float f_scale;           // 126 - f0 + 0.49 (f0 = -k1): f = f0 + RNE(sat(A' y + B') * f_scale), seg = (A', B') = (A, B - f0) / f_scale
+  int pad[3];
 };
 constexpr int P2V_GELU_STEPS_MAX_SEG = 64, P2V_GELU_STEPS_MAX_THR = 512;
 constexpr int P2V_GELU_STEPS_OFFSET = 16 + 8 * P2V_GELU_TABLE_MAX_ENTRIES;                 // byte offset inside a p2v gelu table buffer
 constexpr int P2V_GELU_STEPS_SMEM_MAX = 256 * P2V_GELU_STEPS_MAX_SEG + 26 * 1024;          // replicated tables: segments + thresholds
 struct GeluSteps {         // per-lane view of the replicated tables (32-bit shared addresses, pre-biased by the magic constant)
-  uint32_t seg_addr, thr_addr, nr_off, thr_shift;
-  float ymin, ymax, inv_w, soff, ystar;
+  uint32_t seg_addr, thr_r, thr_l, thr_mul;
+  float ymin, sa, sb, seg_scale, f_scale, f_magic, ystar;
 };
 __host__ __device__ inline uint32_t gelu_steps_smem_bytes(const GeluStepsHeader& h) {
   return uint32_t(h.nseg) * 256u + (uint32_t(h.nr + h.nl) << (2 + h.rep_log2));
@@ -126,29 +128,47 @@ __device__ __forceinline__ void gelu_steps_fill_smem(const void* table, uint32_t
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(thr0 + uint32_t(i) * 4u), "f"(v) : "memory");
   }
 }
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {     // clamp(fl(a*b + c), 0, 1) in one FMA-pipe instruction
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ GeluSteps gelu_steps_view(const void* table, uint32_t smem, int lane) {
   const GeluStepsHeader h = *reinterpret_cast<const GeluStepsHeader*>(reinterpret_cast<const char*>(table) + P2V_GELU_STEPS_OFFSET);
   GeluSteps t;
-  t.thr_shift = uint32_t(2 + h.rep_log2);
+  const uint32_t shift = uint32_t(2 + h.rep_log2);
+  t.thr_mul = 1u << shift;
   t.seg_addr = smem + uint32_t(lane) * 8u - (0x4B400000u << 8);
-  t.thr_addr = smem + uint32_t(h.nseg) * 256u + (uint32_t(lane) & ((1u << h.rep_log2) - 1u)) * 4u + ((uint32_t(h.k1) - 0x4B400000u) << t.thr_shift);
-  t.nr_off = uint32_t(h.nr) << t.thr_shift;
-  t.ymin = h.ymin; t.ymax = h.ymax; t.inv_w = h.inv_w; t.soff = h.soff; t.ystar = h.ystar;
+  t.thr_r = smem + uint32_t(h.nseg) * 256u + (uint32_t(lane) & ((1u << h.rep_log2) - 1u)) * 4u + ((uint32_t(h.k1) - 0x4B400000u) << shift);
+  t.thr_l = t.thr_r + (uint32_t(h.nr) << shift);
+  // the biased addresses stay opaque to the compiler: it would otherwise split the bias off and add it back per column
+  asm volatile("" : "+r"(t.seg_addr), "+r"(t.thr_r), "+r"(t.thr_l), "+r"(t.thr_mul));
+  t.ymin = h.ymin; t.ystar = h.ystar;
+  t.seg_scale = h.seg_scale; t.sa = h.inv_w / h.seg_scale; t.sb = h.soff / h.seg_scale;
+  t.f_scale = h.f_scale; t.f_magic = RMAGIC - float(h.k1);             // RMAGIC + f0, f0 = cr0 - 1 = -k1
   return t;
 }
-// the code of y, NOT saturated (pack4_sat_int saturates); near_min collects min(bits(y) - bits(threshold) + 8) as unsigned:
-// a value <= 16 means some y was within 8 ulps of the threshold consulted and the caller must evaluate erf directly
-__device__ __forceinline__ int gelu_steps_code(float y, const GeluSteps& t, uint32_t& near_min) {
-  const float yc = fminf(fmaxf(y, t.ymin), t.ymax);
-  const uint32_t sb = __float_as_uint(fadd(__fmaf_rn(yc, t.inv_w, t.soff), RMAGIC));          // 0x4B400000 + segment
+// RMAGIC-biased code of y: the low byte of the result is the int8 code (0x4B400000 has a zero low byte and the code lies in
+// [-128, 127] by construction: f is capped at 126 by the FFMA.SAT, the threshold of code 127 adds the last step).
+// Written for the ALU / FMA pipe split: both clamps of the table indices are FFMA.SATs (the segment entry holds A / f_scale and
+// (B - f0) / f_scale), the indices leave an FFMA already biased and become addresses with one IMAD each.
+// near_min collects min(bits(y) - bits(threshold) + 8) as unsigned: a value <= 16 means some y was within 8 ulps of the
+// threshold consulted and the caller must evaluate erf directly.
+__device__ __forceinline__ uint32_t gelu_steps_code(float y, const GeluSteps& t, uint32_t& near_min) {
+  const float yc = fmaxf(y, t.ymin);                     // left of ymin the code is constant; right of ymax the SATs hold the indices
+  const uint32_t sb = __float_as_uint(__fmaf_rn(fma_sat(yc, t.sa, t.sb), t.seg_scale, RMAGIC));      // 0x4B400000 + segment
   float A, B;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(A), "=f"(B) : "r"(t.seg_addr + (sb << 8)));
-  const uint32_t fb = __float_as_uint(fadd(__fmaf_rn(A, yc, B), RMAGIC));                       // 0x4B400000 + f
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(A), "=f"(B) : "r"(sb * 256u + t.seg_addr));
+  const uint32_t fb = __float_as_uint(__fmaf_rn(fma_sat(A, yc, B), t.f_scale, t.f_magic));            // 0x4B400000 + f
   const bool left = yc < t.ystar;
   float thr;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(thr) : "r"(t.thr_addr + (fb << t.thr_shift) + (left ? t.nr_off : 0u)));
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(thr) : "r"(fb * t.thr_mul + (left ? t.thr_l : t.thr_r)));
   near_min = min(near_min, __float_as_uint(yc) - __float_as_uint(thr) + 8u);
-  return int(fb - 0x4B400000u) + (((yc >= thr) != left) ? 1 : 0);
+  return fb + (((yc >= thr) != left) ? 1u : 0u);
+}
+// low bytes of four words -> one word
+__device__ __forceinline__ uint32_t pack4_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 // four int32 codes -> four saturated int8 codes in one word (see pack4_sat)
 __device__ __forceinline__ uint32_t pack4_sat_int(int a, int b, int c, int d) {

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __re
   bool bad = false;
   auto check = [&](float y) {
     uint32_t nm = 0xffffffffu;
-    const int c = min(max(gelu_steps_code(y, t, nm), -128), 127);
+    const int c = int(int8_t(gelu_steps_code(y, t, nm) & 0xffu));
     if (nm > 16u && c != gelu_code_direct(y, ro)) bad = true;
   };
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
@@ -164,7 +164,9 @@ static bool plan_gelu_steps(float out_scale, GeluStepsHeader& h, std::vector<flo
   cr0 = int(floor(gmin * ro + 0.5)) - 2;
   h.ymin = float(ymin); h.ymax = float(ymax); h.ystar = ystar;
   h.nr = 131 - cr0; h.nl = 3 - cr0; h.k1 = 1 - cr0; h.ok = 1;
-  for (int k = 0; k < 5; ++k) h.pad[k] = 0;
+  for (int k = 0; k < 3; ++k) h.pad[k] = 0;
+  const double f0 = double(cr0 - 1);
+  h.f_scale = float(126.0 - f0 + 0.49);
   const int entries = h.nr + h.nl;
   if (entries > P2V_GELU_STEPS_MAX_THR) return false;
   if (entries * 128 <= 26 * 1024) h.rep_log2 = 5;
@@ -173,12 +175,16 @@ static bool plan_gelu_steps(float out_scale, GeluStepsHeader& h, std::vector<flo
   for (int nseg = 16; nseg <= P2V_GELU_STEPS_MAX_SEG; nseg *= 2) {
     const double inv_w = double(nseg) / (double(h.ymax) - double(h.ymin)) * (1.0 - 1e-4);
     h.nseg = nseg; h.inv_w = float(inv_w); h.soff = float(-double(h.ymin) * double(h.inv_w) - 0.5 + 5e-4);
+    h.seg_scale = float(double(nseg) - 1.0 + 0.49);
     seg.assign(nseg, make_float2(0.f, 0.f));
     double worst = 0.0;
     for (int s = 0; s < nseg; ++s) {      // y with RNE(y * inv_w + soff) == s, widened by 2 % of a segment, clipped to the active range
       double a = (double(s) - 0.52 - double(h.soff)) / double(h.inv_w), b = (double(s) + 0.52 - double(h.soff)) / double(h.inv_w);
       a = std::max(a, double(h.ymin)); b = std::min(b, double(h.ymax));
-      if (!(b > a)) { seg[s] = make_float2(0.f, float(gelu_f64(std::min(std::max(a, double(h.ymin)), double(h.ymax))) * ro - 0.5)); continue; }
+      if (!(b > a)) {
+        seg[s] = make_float2(0.f, float((gelu_f64(std::min(std::max(a, double(h.ymin)), double(h.ymax))) * ro - 0.5 - f0) / double(h.f_scale)));
+        continue;
+      }
       const double A = (gelu_f64(b) - gelu_f64(a)) * ro / (b - a);
       double dmin = 1e300, dmax = -1e300;
       for (int j = 0; j <= 128; ++j) {
@@ -186,7 +192,7 @@ static bool plan_gelu_steps(float out_scale, GeluStepsHeader& h, std::vector<flo
         dmin = std::min(dmin, d); dmax = std::max(dmax, d);
       }
       worst = std::max(worst, 0.5 * (dmax - dmin));
-      seg[s] = make_float2(float(A), float(0.5 * (dmax + dmin) - 0.5));
+      seg[s] = make_float2(float(A / double(h.f_scale)), float((0.5 * (dmax + dmin) - 0.5 - f0) / double(h.f_scale)));
     }
     if (worst <= 0.30) return true;
   }

@@ -232,13 +232,13 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
 #pragma unroll
       for (int e = 0; e < 4; ++e) t[e] = quant_pot(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]));   // S, B pre-divided by out_scale
     } else if (POT && EPI == P2V_EPI_GELU && GST) {
-      // step tables (common.cuh: gelu_steps_code): ~22 instructions per column instead of ~40 for erff.  No branch inside the
+      // step tables (common.cuh: gelu_steps_code): ~19 instructions per column (9 ALU-pipe, 8 FMA-pipe) instead of ~40 for erff.  No branch inside the
       // chunk, so the 16 columns' lookup chains (two dependent shared-memory loads each) overlap; the near-threshold test is
       // taken once per chunk, after the loop.
-      int q[4];
+      uint32_t q[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) q[e] = gelu_steps_code(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]), gst, gst_near);
-      ow[j4 >> 2] = pack4_sat_int(q[0], q[1], q[2], q[3]);
+      ow[j4 >> 2] = pack4_low_bytes(q[0], q[1], q[2], q[3]);
       continue;
     } else if (POT && EPI == P2V_EPI_GELU) {
       const float4 R4 = *reinterpret_cast<const float4*>(prm + PR_RO * 64 + j4);
