@@ -1,7 +1,7 @@
 #!/bin/bash
 export PYTHONPATH=$PWD
 mkdir -p gpurun_out
-for m in "$@"; do
-timeout 200 python tools/gemm_bench.py $m 256 > gpurun_out/gemm_bench_$m.log 2>&1
-echo "exit $?"; tail -n 20 gpurun_out/gemm_bench_$m.log
-done
+timeout 300 python -m pytest tests/test_gpu_ops.py -x -q -k "gemm" > gpurun_out/gemm_tests.log 2>&1
+echo "exit $?"; tail -n 3 gpurun_out/gemm_tests.log
+timeout 200 python tools/gemm_bench.py deit_small 256 2 2>&1 | tee gpurun_out/gemm_bench_deit_small.log
+timeout 200 python tools/gemm_bench.py vit_base 256 2 2>&1 | tee gpurun_out/gemm_bench_vit_base.log
