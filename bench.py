@@ -362,6 +362,17 @@ def main():
         ach = by / (fam_ms[top] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "%s (all %d launches of a step)" % (top, fam_n[top]), "achieved": ach, "peak": hbm_gbs, "unit": "GB/s",
                 "frac": ach / hbm_gbs, "traffic": None, "note": "algorithmic int8 bytes in+out; peak = %s copy bandwidth" % peak_src}
+    # measured DRAM traffic per launch of the kernel family above (ncu capture of the same workload, profiles/ncu_traffic.json)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("%s_b%d" % (args.model, B)) if args.bits == "8" else None
+    except OSError:
+        tr = None
+    if tr:
+        kinds = [k for k in tr if k.startswith("gemm_")] if top == "gemm" else [top]
+        if all(k in tr for k in kinds) and kinds:
+            roof["traffic"] = sum(tr[k] for k in kinds) / len(kinds)
+            roof["traffic_note"] = "bytes per launch, mean over %s; %s" % ("/".join(kinds), tr["source"])
+    roof["per_launch"] = {"launches_per_step": fam_n[top], "avg_us": round(fam_ms[top] * 1e3 / fam_n[top], 2)}
     roof["device_ms_per_step_by_family"] = {k: round(v, 4) for k, v in fam_ms.items()}
     roof["share_of_step"] = share
     roof["gemm_ms_by_kind"] = {k: v for k, v in fine_ms.items() if k.startswith("gemm")}

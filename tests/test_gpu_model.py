@@ -340,3 +340,29 @@ def test_input_quant_false_engine_vs_oracle():
     assert not bad, "integer steps differ from the oracle: %s" % bad
     got = m(x.cuda(), bits)[0]
     assert torch.equal(m.forward_eager(x.cuda(), bits)[0], got)
+
+
+def test_mixed_precision_search_flow():
+    """test_quant.py:316-463 end to end on the GPU: calibrate vit_micro, take FLOPs / global_distance from the calibration
+    forward, rank sampled {4,8} configurations and run a short evolutionary search whose fitness is top-1 agreement with the
+    all-8-bit model (synthetic labels).  Checks the plumbing: per-layer bit_config switching through the engine, budget,
+    ordering, memoised evaluations."""
+    from p2vit_b200 import runner, search
+    m = build_model("vit_micro", Config(), seed=0, device="cuda")
+    calib = synth.synth_images(16, seed=3).cuda()
+    (_, flops, gdist), _ = runner.calibrate_model(m, calib)
+    n = 4 * m.depth + 2
+    assert len(flops) == n and len(gdist) == n - 1
+    imgs = [synth.synth_images(16, seed=10 + i).cuda() for i in range(2)]
+    batches = [(x, m(x, [8] * n)[0].argmax(1)) for x in imgs]          # labels = the W8A8 model's own top-1
+    assert runner.validate(m, batches, [8] * n)[1] == 100.0
+    res = search.mixed_precision_search(m, flops, gdist, batches, seed=0, top_validate=2, ratio=1.6, pop_size=6, evo_iter=2,
+                                        mutate_size=3, crossover_size=3)
+    lim = search.budget(res["flops"], 1.6)
+    assert len(res["ranked"]) >= 6 and [o for _, o in res["ranked"]] == sorted(o for _, o in res["ranked"])
+    assert len(res["validated"]) == 2 and all(0.0 <= a <= 100.0 for _, _, a in res["validated"])
+    popu = res["population"]
+    assert len(popu) == 6 and [s for _, s in popu] == sorted((s for _, s in popu), reverse=True)
+    for cfg, acc in popu:
+        assert len(cfg) == n and set(cfg) <= {4, 8} and search.model_cost(res["flops"], cfg) <= lim
+        assert runner.validate(m, batches, cfg)[1] == acc            # deterministic: the memoised score is reproducible

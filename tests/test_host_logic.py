@@ -139,3 +139,60 @@ def test_statistics_allreduce_world2_gloo(tmp_path):
                         "--master-port", "29641", str(script)], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+# ------------------------------------------------------------------------------------------------ mixed-precision search
+def _vit_flops(depth=12, D=192, T=197):
+    f = [196 * 768 * D]
+    for _ in range(depth):
+        f += [T * D * 3 * D, T * D * D, T * D * 4 * D, T * 4 * D * D]
+    return f + [D * 1000]
+
+
+def test_search_candidates_follow_reference_sampling_rule():
+    """test_quant.py:323-341: first layer 8 bit, consecutive layers share a width pairwise, budget 1.1 x the 4-bit cost, no repeats"""
+    import random
+    from p2vit_b200 import search
+    flops = _vit_flops()
+    cands = search.sample_candidates(flops, random.Random(0))
+    assert len(cands) == 51 and len({tuple(c) for c in cands}) == 51
+    lim = 1.1 * sum(f * 4 for f in flops)
+    for c in cands:
+        assert len(c) == 50 and c[0] == 8 and set(c) <= {4, 8}
+        assert all(c[1 + 2 * k] == c[2 + 2 * k] for k in range(24))
+        assert search.model_cost(flops, c) <= lim
+
+
+def test_search_ranking_and_distance_columns():
+    from p2vit_b200 import search
+    gd = [[9.0, 8.0, 4.0, 1.0]] * 3                       # uint3, uint4, int4, int8 per layer
+    assert search.distance_columns(gd) == [[4.0, 1.0]] * 3                                   # fixed mapping: int4 / int8 entries
+    assert search.distance_columns(gd, replicate_reference=True) == [[9.0, 8.0]] * 3         # test_quant.py:351-354 as written
+    ranked = search.rank_by_sensitivity([[8, 4, 4, 8], [8, 8, 8, 4], [8, 4, 4, 4]], search.distance_columns(gd), [1.0, 2.0, 0.5])
+    assert [r[0] for r in ranked] == [[8, 8, 8, 4], [8, 4, 4, 8], [8, 4, 4, 4]]
+    assert ranked[0][1] == 1.0 * 1 + 2.0 * 1 + 0.5 * 4 and ranked[2][1] == 4 + 8 + 2
+
+
+def test_evolutionary_search_improves_and_respects_budget():
+    """toy objective: accuracy = weighted count of 8-bit layers; the population's best must not get worse, every survivor fits
+    the budget, and no configuration is evaluated twice"""
+    import random
+    from p2vit_b200 import search
+    flops = _vit_flops()
+    w = [((7 * i) % 11 + 1) / 10.0 for i in range(50)]
+    calls = []
+
+    def evaluate(cfg):
+        calls.append(tuple(cfg))
+        return sum(wi for wi, b in zip(w, cfg) if b == 8)
+
+    rng = random.Random(1)
+    seeds = search.sample_candidates(flops, rng)
+    first_best = max(evaluate(c) for c in seeds[:25])
+    calls.clear()
+    popu, n_eval = search.evolutionary_search(evaluate, seeds, flops, rng, evo_iter=4)
+    assert len(popu) == 25 and popu[0][1] >= first_best
+    assert [s for _, s in popu] == sorted((s for _, s in popu), reverse=True)
+    lim = search.budget(flops)
+    assert all(search.model_cost(flops, c) <= lim for c, _ in popu)
+    assert len(calls) == len(set(calls)) == n_eval
