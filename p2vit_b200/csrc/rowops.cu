@@ -286,7 +286,7 @@ __device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const f
     const float rtwoN = __uint_as_float(Ef - 0x03800000u);           // 2^(E - 134)
     const float sM = __uint_as_float((Ab & 0x807f0000u) | 0x43000000u);
     const float Bv = rintf(fmul(fsub(bt[e], fmul(mos, g[e])), twoN));
-    const float sum = fadd(fmul(sM, __int2float_rn(xv[e])), Bv);
+    const float sum = __fmaf_rn(sM, __int2float_rn(xv[e]), Bv);     // sM * x is exact (8 x 11 bits): one rounding, as fadd(fmul(..), Bv)
     float yq = fsub(__fmaf_rn(sum, rtwoN, RMAGIC), RMAGIC);          // RNE(sum / 2^N)
     if (clamp_mid) yq = fminf(fmaxf(yq, -128.f), 127.f);
     r[e] = __fmaf_rn(yq, f[e], RMAGIC);                              // RNE(yq * f) + RMAGIC, saturated below
