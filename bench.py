@@ -58,6 +58,21 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        try:      # NVML in-process: a sample costs ~0.1 ms, so even a 100 ms timed region gets tens of them
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [0x8, 0x40, 0x20, 0x4]      # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+            while not self.stop_flag:
+                r = get_reasons(h)
+                self.rows.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx), str(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)] +
+                                 ["Active" if r & b else "Not Active" for b in bits])
+                time.sleep(0.004)
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
