@@ -196,3 +196,38 @@ def test_evolutionary_search_improves_and_respects_budget():
     lim = search.budget(flops)
     assert all(search.model_cost(flops, c) <= lim for c, _ in popu)
     assert len(calls) == len(set(calls)) == n_eval
+
+
+# ------------------------------------------------------------------------------------------------ real-data plumbing
+def test_build_transform_and_sharded_imagefolder(tmp_path):
+    """test_quant.py:112-157, 565-597 on a tiny synthetic ImageFolder tree: transform geometry / normalisation per model family,
+    ordered validation batches, disjoint per-rank shards that cover the set"""
+    import numpy as np
+    from PIL import Image
+    from p2vit_b200 import data
+    rng = np.random.RandomState(0)
+    for split, per_class in (("train", 3), ("val", 5)):
+        for c in ("n01", "n02"):
+            d = tmp_path / split / c
+            d.mkdir(parents=True)
+            for i in range(per_class):
+                Image.fromarray(rng.randint(0, 256, (300 + 10 * i, 280, 3), dtype=np.uint8)).save(d / ("%d.png" % i))
+    assert data.preprocess_for("deit_small")["crop_pct"] == 0.875 and data.preprocess_for("vit_base")["mean"] == (0.5, 0.5, 0.5)
+    assert data.preprocess_for("swin_tiny")["crop_pct"] == 0.9
+    with pytest.raises(NotImplementedError):
+        data.preprocess_for("resnet50")
+    tf = data.build_transform(**data.preprocess_for("vit_base"))
+    assert [type(t).__name__ for t in tf.transforms] == ["Resize", "CenterCrop", "ToTensor", "Normalize"]
+    assert tf.transforms[0].size == 248            # floor(224 / 0.9)
+    x = tf(Image.fromarray(np.full((300, 280, 3), 255, dtype=np.uint8)))
+    assert x.shape == (3, 224, 224) and torch.allclose(x, torch.ones_like(x))      # (1 - 0.5) / 0.5
+    train, val = data.build_loaders(str(tmp_path), "deit_tiny", calib_batchsize=4, val_batchsize=4, num_workers=0)
+    xb, yb = next(iter(train))
+    assert xb.shape == (4, 3, 224, 224) and len(train) == 1          # 6 images, drop_last
+    labels = torch.cat([y for _, y in val])
+    assert labels.tolist() == [0] * 5 + [1] * 5
+    seen = []
+    for r in range(3):
+        _, v = data.build_loaders(str(tmp_path), "deit_tiny", 4, 4, 0, rank=r, world_size=3)
+        seen += torch.cat([y for _, y in v]).tolist()
+    assert seen == labels.tolist()
