@@ -49,6 +49,7 @@ struct PairGeom {
                     //    tiles are then walked row-block fastest in one contiguous range per CTA pair, so W is reloaded only
                     //    when the range crosses into the next column tile.  0: A and W stream together, tiles column fastest.
   uint32_t stage_bytes, off_bres, off_stg, off_prm, off_gst;   // shared-memory layout relative to the 1024-aligned base
+  uint32_t smem_bytes;   // dynamic shared memory of the launch
 };
 constexpr int P_MAX_STAGES = 8;
 
@@ -613,34 +614,71 @@ static int max_pairs() {
 
 constexpr size_t P_SMEM_BUDGET = 227 * 1024 - 1024;    // dynamic shared memory per CTA, static part and slack taken off
 
-template <int EPI, bool POT, bool GST = false>
-static int launch_pair(const p2v_gemm_args& a, PairGeom g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
-                       const CUtensorMap& tmR, cudaStream_t stream) {
-  // shared-memory plan: [operand ring][resident W half-tile][output / residual staging][16 warp-private constant tables]
-  const size_t prm_bytes = size_t(P_EPI_WARPS) * prm_rows<EPI, POT>() * 64 * 4 + (GST ? P2V_GELU_STEPS_SMEM_MAX : 0);   // + GELU step tables
-  const size_t bhalf = size_t(g.BN / 2) * PBK;
+// Shared-memory plan of one candidate geometry: [operand ring][resident W half-tile][output / residual staging][16 warp-private
+// constant tables (+ GELU step tables)].  rows = prm_rows<EPI, POT>().  false = no room for a two-stage ring.
+static bool plan_pair(const p2v_gemm_args& a, int bn, int rows, bool gst, PairGeom& g) {
   static const int force_bres = getenv("P2V_PAIR_BRES") ? atoi(getenv("P2V_PAIR_BRES")) : -1;    // perf triage only
+  g.BN = bn;
+  g.W = bn / 4;
+  g.tiles_m = (a.M + 255) / 256;
+  g.tiles_n = (a.N + bn - 1) / bn;
+  g.tiles = g.tiles_m * g.tiles_n;
+  g.nkb = (a.K + PBK - 1) / PBK;
+  g.swz = g.W == 64 ? 2 : (g.W == 32 ? 1 : 0);
+  g.nslot_log2 = a.epilogue == P2V_EPI_RESIDUAL ? (g.W == 32 ? 2 : 1) : 0;
+  const size_t prm_bytes = size_t(P_EPI_WARPS) * rows * 64 * 4 + (gst ? P2V_GELU_STEPS_SMEM_MAX : 0);
+  const size_t bhalf = size_t(g.BN / 2) * PBK;
   for (;;) {
     const size_t stg_bytes = (size_t(1) << g.nslot_log2) * P_EPI_WARPS * 32 * g.W;
     const size_t fixed = 1024 + prm_bytes + stg_bytes;
     const size_t bres_bytes = size_t(g.nkb) * bhalf;
     const bool fits = fixed + bres_bytes + 3 * P_A_BYTES <= P_SMEM_BUDGET;
-    if (!fits && EPI == P2V_EPI_RESIDUAL && g.nslot_log2 == 2 && fixed - stg_bytes / 2 + bres_bytes + 3 * P_A_BYTES <= P_SMEM_BUDGET) {
+    if (!fits && a.epilogue == P2V_EPI_RESIDUAL && g.nslot_log2 == 2 && fixed - stg_bytes / 2 + bres_bytes + 3 * P_A_BYTES <= P_SMEM_BUDGET) {
       g.nslot_log2 = 1;        // a resident W tile is worth more than the two extra residual slots
       continue;
     }
     g.bres = (fits && force_bres != 0) ? 1 : 0;
     g.stage_bytes = uint32_t(P_A_BYTES + (g.bres ? 0 : P_B_BYTES));
+    if (fixed + (g.bres ? bres_bytes : 0) + 2 * g.stage_bytes > P_SMEM_BUDGET) return false;
     const size_t ring_room = P_SMEM_BUDGET - fixed - (g.bres ? bres_bytes : 0);
     g.nstages = int(std::min<size_t>(P_MAX_STAGES, ring_room / g.stage_bytes));
-    P2V_REQUIRE(g.nstages >= 2, "gemm_pair: no room for the operand ring (K=%d N=%d)", a.K, a.N);
     g.off_bres = uint32_t(g.nstages) * g.stage_bytes;
     g.off_stg = g.off_bres + uint32_t(g.bres ? bres_bytes : 0);
     g.off_prm = g.off_stg + uint32_t(stg_bytes);
-    g.off_gst = g.off_prm + uint32_t(P_EPI_WARPS) * prm_rows<EPI, POT>() * 64 * 4;
-    break;
+    g.off_gst = g.off_prm + uint32_t(P_EPI_WARPS) * rows * 64 * 4;
+    g.smem_bytes = uint32_t(1024 + g.off_prm + prm_bytes);
+    return true;
   }
-  const size_t smem = 1024 + g.off_prm + prm_bytes;
+}
+
+// Estimated cycles of the slowest CTA pair for a planned geometry (r1m measurements of 12 shapes x 3 tile widths, tools/gpu_exp.sh;
+// DESIGN.md 3.1): per tile max(operand load, MMA, epilogue) + ~1500 cycles of hand-offs, times the tile waves over the pairs.
+//   operand load: bytes per CTA at <= 28 B/clk (what L2 delivers per SM with every SM streaming) and at most the ring's bytes in
+//                 flight per loaded round trip (2200 cycles while A fits L2, 2800 from DRAM): a resident W tile that leaves a
+//                 3-stage ring is latency-bound (DeiT-S fc2 at BN = 128);
+//   MMA:          2.46 cycles per column and k-block (256 x BN x 128 int8 MACs at 6.6 k MAC/clk/SM);
+//   epilogue:     all BN columns of a tile cost (the warps of padded columns idle, the others are not faster), cycles per column
+//                 by epilogue kind;
+//   a narrower tile has to win by 8 % per step (per-tile costs the model does not see).
+// With these constants the model picks the measured-fastest width on all 12 shapes.  The old rule (least waves x BN) ignored the
+// fixed cost per tile and took 128-column tiles for short row counts: ViT-B qkv at batch 128 65 -> 42 us, ViT-L fc1 / fc2
+// 163 -> 114 / 144 -> 97 us, DeiT-S fc2 55 -> 45 us.
+static double pair_cost(const p2v_gemm_args& a, const PairGeom& g, bool gst) {
+  const double waves = double((g.tiles + max_pairs() - 1) / max_pairs());
+  const double bytes = (128.0 + (g.bres ? 0.0 : g.BN / 2.0)) * a.K;
+  const double round_trip = double(a.M) * a.K <= 48e6 ? 2200.0 : 2800.0;
+  const double rate = std::min(28.0, double(g.nstages) * g.stage_bytes / round_trip);
+  const double load = bytes / rate;
+  const double mma = double(g.nkb) * g.BN * 2.46;
+  const bool pot = a.pot_scales != 0;
+  const double per_col = a.epilogue == P2V_EPI_RESIDUAL ? 33.0 : a.epilogue == P2V_EPI_GELU ? (gst ? 31.0 : 50.0) : (pot ? 15.0 : 22.0);
+  const double handicap = 1.0 + 0.08 * (g.BN == 256 ? 0 : g.BN == 192 ? 1 : 2);
+  return waves * (std::max(load, std::max(mma, g.BN * per_col)) + 1500.0) * handicap;
+}
+
+template <int EPI, bool POT, bool GST = false>
+static int launch_pair(const p2v_gemm_args& a, const PairGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                       const CUtensorMap& tmR, cudaStream_t stream) {
   auto kern = gemm_pair_kernel<EPI, POT, GST>;
   static bool attr = false;
   if (!attr) {
@@ -650,32 +688,29 @@ static int launch_pair(const p2v_gemm_args& a, PairGeom g, const CUtensorMap& tm
   }
   const int grid = 2 * std::min(g.tiles, max_pairs());
   EpiParams p = make_epi_params(a);
-  kern<<<grid, P_THREADS, smem, stream>>>(tmA, tmB, tmO, tmR, p, g);
+  kern<<<grid, P_THREADS, g.smem_bytes, stream>>>(tmA, tmB, tmO, tmR, p, g);
   count_launch();
   return check_launch("gemm_pair");
 }
 
 int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
   P2V_REQUIRE(gemm_pair_supported(a), "gemm_pair: unsupported arguments");
-  // column tile: least makespan in column units over the CTA pairs, ties to the wider tile (less operand traffic)
-  const int tiles_m = (a.M + 255) / 256, pairs = max_pairs();
-  int best_bn = 128;
-  long best_cost = -1;
-  for (int bn : {256, 192, 128}) {
-    const long tn = (a.N + bn - 1) / bn;
-    const long waves = (long(tiles_m) * tn + pairs - 1) / pairs;
-    const long cost = waves * bn;
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
-  }
+  const bool pot = a.pot_scales != 0;
+  const bool gst = a.epilogue == P2V_EPI_GELU && pot && a.gelu_table;
+  const int rows = a.epilogue == P2V_EPI_RESIDUAL ? prm_rows<P2V_EPI_RESIDUAL, true>()
+                   : a.epilogue == P2V_EPI_GELU   ? (pot ? prm_rows<P2V_EPI_GELU, true>() : prm_rows<P2V_EPI_GELU, false>())
+                                                  : (pot ? prm_rows<P2V_EPI_REQUANT, true>() : prm_rows<P2V_EPI_REQUANT, false>());
+  static const int force_bn = getenv("P2V_PAIR_BN") ? atoi(getenv("P2V_PAIR_BN")) : 0;    // perf triage only
   PairGeom g;
-  g.BN = best_bn;
-  g.W = best_bn / 4;
-  g.tiles_m = tiles_m;
-  g.tiles_n = (a.N + best_bn - 1) / best_bn;
-  g.tiles = tiles_m * g.tiles_n;
-  g.nkb = (a.K + PBK - 1) / PBK;
-  g.swz = g.W == 64 ? 2 : (g.W == 32 ? 1 : 0);
-  g.nslot_log2 = a.epilogue == P2V_EPI_RESIDUAL ? (g.W == 32 ? 2 : 1) : 0;
+  double best = -1.0;
+  for (int bn : {256, 192, 128}) {
+    if (force_bn && bn != force_bn) continue;
+    PairGeom c;
+    if (!plan_pair(a, bn, rows, gst, c)) continue;
+    const double cost = pair_cost(a, c, gst);
+    if (best < 0.0 || cost < best) { best = cost; g = c; }
+  }
+  P2V_REQUIRE(best >= 0.0, "gemm_pair: no room for the operand ring (K=%d N=%d)", a.K, a.N);
   const CUtensorMapSwizzle oswz = g.W == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (g.W == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE);
   CUtensorMap tmA, tmB, tmO, tmR;
   if (int r = make_tmap_rows(&tmA, a.A, a.M, a.K, PBK, PBM, CU_TENSOR_MAP_SWIZZLE_128B)) return r;
@@ -684,13 +719,12 @@ int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
   tmR = tmO;
   if (a.epilogue == P2V_EPI_RESIDUAL)
     if (int r = make_tmap_rows(&tmR, a.res, a.M, a.N, g.W, 32, oswz)) return r;
-  const bool pot = a.pot_scales != 0;
   switch (a.epilogue) {
     case P2V_EPI_REQUANT:
       return pot ? launch_pair<P2V_EPI_REQUANT, true>(a, g, tmA, tmB, tmO, tmR, stream)
                  : launch_pair<P2V_EPI_REQUANT, false>(a, g, tmA, tmB, tmO, tmR, stream);
     case P2V_EPI_GELU:
-      if (pot && a.gelu_table) return launch_pair<P2V_EPI_GELU, true, true>(a, g, tmA, tmB, tmO, tmR, stream);
+      if (gst) return launch_pair<P2V_EPI_GELU, true, true>(a, g, tmA, tmB, tmO, tmR, stream);
       return pot ? launch_pair<P2V_EPI_GELU, true>(a, g, tmA, tmB, tmO, tmR, stream)
                  : launch_pair<P2V_EPI_GELU, false>(a, g, tmA, tmB, tmO, tmR, stream);
     default:
