@@ -210,6 +210,26 @@ __device__ __forceinline__ uint32_t log2_code(float sum_f, float exp_f) {
   return big >= 16 ? 255u : uint32_t(big);
 }
 
+// log_round(RNE(fl(tot / e))) of layers.py:376-381,422-427 without the division, as 2^(15-big) (0 when big >= 16).
+//   x = RNE(q), q = fl(tot/e) >= 1;  big(x) = #{t in {2, 3, 6, 12, 24, ...} : x >= t}, and x >= t <=> q + 1/2 >= t up to the
+//   tie rule.  g(q) = min(2q - 1, (4q + 2)/3) is increasing, equals 2 at q + 1/2 = 2 and 2^(j+2) at q + 1/2 = 3 * 2^j, so
+//   big = floor(log2 g) = the exponent field of g.  g is computed from the table's reciprocal with two FFMAs (a few ulps off
+//   the exact value), so the result can only differ from the reference when g is within 16 ulps of a power of two: with
+//   pf = 2^(15-E) (E = exponent of g, an integer subtraction on the exponent field), g * pf lies in [2^15, 2^16) and the
+//   guard is |g*pf - 1.5*2^15| >= 2^14 - 16 ulps; `gmax` collects it over a unit, which is then redone with the IEEE
+//   division (log2_code).  pf + 2^23 leaves the integer 2^(15-E) (0 from E = 16 on: 0.5 rounds to even) in the low mantissa bits.
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n) {   // PTX shr: amounts > 31 give 0
+  uint32_t r;
+  asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+  return r;
+}
+constexpr float PROB_GUARD = 16384.f - 0.0625f;     // 16 ulps of [2^15, 2^16)
+__device__ __forceinline__ uint32_t prob_bits_fast(float tot2, float tot43, float rcp, float& gmax) {
+  const float g = fminf(__fmaf_rn(tot2, rcp, -1.0f), __fmaf_rn(tot43, rcp, 0.666666686534881591796875f));
+  const float pf = __uint_as_float(0x86800000u - (__float_as_uint(g) & 0x7F800000u));     // 2^(15 - E), E = floor(log2 g)
+  gmax = fmaxf(gmax, fabsf(fadd(fmul(g, pf), -49152.f)));
+  return __float_as_uint(fadd(pf, 8388608.f));      // low 16 bits: 2^(15-E)
+}
 // exactly rounded (RNE) fp32 of the 128-bit integer hi*2^32 + lo  (hi, lo < 2^63)
 __device__ __forceinline__ float u96_to_f32(unsigned long long hi, unsigned long long lo) {
   unsigned __int128 v = ((unsigned __int128)hi << 32) + lo;

@@ -3,6 +3,7 @@
 // (p2v_gemm_args.row_map).  Here: the per-window attention (quantized relative-position bias and SW-MSA mask inside),
 // the 2x2 patch-merging gather, and the token average pool + QAct of the classifier tail.
 #include <climits>
+#include <cmath>
 #include <algorithm>
 #include "common.cuh"
 
@@ -17,120 +18,159 @@ __device__ __forceinline__ int dp4a_us_w(uint32_t a_u8x4, uint32_t b_s8x4, int c
 constexpr int WA_WARPS = 4;
 constexpr int WA_MAXT = 64;
 
-// One CTA per (window, head): T = ws*ws <= 64 tokens, one warp per query row, a lane owns keys lane and lane + 32.
-// Windows are tiny (49 x 32 per head), so this is an integer-ALU / latency kernel; dp4a for both matmuls.
-template <int DH>
-__global__ void __launch_bounds__(WA_WARPS * 32) window_attention_kernel(p2v_window_attention_args a, uint32_t e_mask) {
+// Persistent CTAs over (window, head) units: T = ws*ws <= 64 tokens, one warp per query row, a lane owns keys lane and lane + 32.
+// Windows are tiny (49 x 32 per head), so this is an integer-ALU / latency kernel; dp4a for both matmuls.  What the first version
+// paid per unit and this one does not: the 3 KB softmax table reloaded by every CTA (233 k CTAs at batch 256), three XU-pipe
+// conversions, one IEEE division for qact2 and one for log_round per score, and twenty 64-bit shuffles per row for the exact sum:
+//   * the table {exp_int hi, lo, fp32, reciprocal} is loaded once per CTA, one LDS.128 per score;
+//   * roundings / saturations go through the 1.5 * 2^23 constant (exact, common.cuh), the division by a power-of-two s_attn2 is
+//     a multiplication (POT2; other observers keep __fdiv_rn);
+//   * the row sum is three REDUX.ADDs: the hi words and the two 16-bit halves of the lo words each stay below 2^32;
+//   * 2^(15-code) from prob_bits_fast (exponent-field shortcut with its guard band; log2_code when the guard trips).
+template <int DH, bool POT2>
+__global__ void __launch_bounds__(WA_WARPS * 32) window_attention_kernel(p2v_window_attention_args a, uint32_t e_mask, int units) {
   constexpr int DW = DH / 4, KSTR = DW + 1, TW = WA_MAXT / 4, VSTR = TW + 1;
   __shared__ uint32_t sQ[WA_MAXT * DW], sK[WA_MAXT * KSTR], sVt[DH * VSTR], sP[WA_WARPS * 2 * TW];
-  __shared__ uint32_t sLh[256], sLl[256];
-  __shared__ float sLe[256];
+  __shared__ uint4 sLut[256];          // hi, lo, bits(exp_f32), bits(1 / exp_f32)
   __shared__ int8_t sLab[WA_MAXT];
   const int T = a.T, H = a.H;
-  const int win = blockIdx.x / H, h = blockIdx.x % H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row_bytes = int64_t(3) * H * DH;
-  const int8_t* base = a.qkv + int64_t(win) * T * row_bytes + h * DH;
-  for (int i = tid; i < 256; i += blockDim.x) { sLh[i] = a.lut_dev->hi[i]; sLl[i] = a.lut_dev->lo[i]; sLe[i] = a.lut_dev->exp_f32[i]; }
-  for (int i = tid; i < DH * VSTR; i += blockDim.x) sVt[i] = 0u;
-  for (int i = tid; i < WA_WARPS * 2 * TW; i += blockDim.x) sP[i] = 0u;
-  if (tid < WA_MAXT) sLab[tid] = (a.labels && tid < T) ? a.labels[(win % a.windows_per_image) * T + tid] : int8_t(0);
-  __syncthreads();
-  constexpr int CH = DH / 16;
-  for (int idx = tid; idx < T * CH; idx += blockDim.x) {
-    const int r = idx / CH, ch = idx % CH;
-    const int8_t* p = base + int64_t(r) * row_bytes + ch * 16;
-    const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(p));
-    const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(p + int64_t(H) * DH));
-    const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(p + int64_t(2) * H * DH));
-    uint32_t* dq = sQ + r * DW + ch * 4;
-    dq[0] = q4.x; dq[1] = q4.y; dq[2] = q4.z; dq[3] = q4.w;
-    uint32_t* dk = sK + r * KSTR + ch * 4;
-    dk[0] = k4.x; dk[1] = k4.y; dk[2] = k4.z; dk[3] = k4.w;
-    const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
-    uint8_t* vt = reinterpret_cast<uint8_t*>(sVt);
-#pragma unroll
-    for (int e = 0; e < 16; ++e) vt[size_t(ch * 16 + e) * VSTR * 4 + r] = uint8_t(vv[e >> 2] >> ((e & 3) * 8));
+  for (int i = tid; i < 256; i += blockDim.x) {
+    const float e = a.lut_dev->exp_f32[i];
+    sLut[i] = make_uint4(a.lut_dev->hi[i], a.lut_dev->lo[i], __float_as_uint(e), __float_as_uint(fdiv(1.0f, e)));
   }
-  __syncthreads();
-
+  for (int i = tid; i < DH * VSTR; i += blockDim.x) sVt[i] = 0u;       // rows >= T of V and keys >= T of P stay zero for every unit
+  for (int i = tid; i < WA_WARPS * 2 * TW; i += blockDim.x) sP[i] = 0u;
+  const float e_mask_f = float(e_mask), r_mask = fdiv(1.0f, e_mask_f);
+  const float r2 = fdiv(1.0f, a.s_attn2);
+  constexpr float LO = RMAGIC - 128.f, HI = RMAGIC + 127.f;
   uint32_t* pHi = sP + warp * 2 * TW;
   uint32_t* pLo = pHi + TW;
-  const float* bias_h = a.bias + size_t(h) * T * T;
-  for (int i = warp; i < T; i += WA_WARPS) {
-    int x[2];
-    bool masked[2];
-    int mx = INT_MIN;
-    const uint32_t* qi = sQ + i * DW;
+  uint8_t* bHi = reinterpret_cast<uint8_t*>(pHi);
+  uint8_t* bLo = reinterpret_cast<uint8_t*>(pLo);
+  constexpr int CH = DH / 16;
+
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int win = unit / H, h = unit % H;
+    const int8_t* base = a.qkv + int64_t(win) * T * row_bytes + h * DH;
+    __syncthreads();                    // the previous unit's rows are done with sQ / sK / sVt (first pass: the tables are written)
+    if (tid < WA_MAXT) sLab[tid] = (a.labels && tid < T) ? a.labels[(win % a.windows_per_image) * T + tid] : int8_t(0);
+    for (int idx = tid; idx < T * CH; idx += blockDim.x) {
+      const int r = idx / CH, ch = idx % CH;
+      const int8_t* p = base + int64_t(r) * row_bytes + ch * 16;
+      const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(p));
+      const uint4 k4 = __ldg(reinterpret_cast<const uint4*>(p + int64_t(H) * DH));
+      const uint4 v4 = __ldg(reinterpret_cast<const uint4*>(p + int64_t(2) * H * DH));
+      uint32_t* dq = sQ + r * DW + ch * 4;
+      dq[0] = q4.x; dq[1] = q4.y; dq[2] = q4.z; dq[3] = q4.w;
+      uint32_t* dk = sK + r * KSTR + ch * 4;
+      dk[0] = k4.x; dk[1] = k4.y; dk[2] = k4.z; dk[3] = k4.w;
+      const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      uint8_t* vt = reinterpret_cast<uint8_t*>(sVt);
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const int j = lane + 32 * jj;
-      x[jj] = INT_MIN;
-      masked[jj] = false;
-      if (j < T) {
-        const uint32_t* kj = sK + j * KSTR;
-        int s = 0;
-#pragma unroll
-        for (int w = 0; w < DW; ++w) s = __dp4a(int(qi[w]), int(kj[w]), s);
-        const int c1 = sat_s8(fmul(float(s), a.score_mult));                                   // qact_attn1
-        const float v = fadd(fmul(float(c1), a.s_attn1), __ldg(bias_h + i * T + j));            // + relative position bias
-        const int c2 = sat_s8(fdiv(v, a.s_attn2));                                              // qact2
-        masked[jj] = sLab[i] != sLab[j];
-        x[jj] = c2 + (masked[jj] ? a.mask_code : 0);                                            // + mask (after the quantizer)
-        mx = max(mx, x[jj]);
-      }
+      for (int e = 0; e < 16; ++e) vt[size_t(ch * 16 + e) * VSTR * 4 + r] = uint8_t(vv[e >> 2] >> ((e & 3) * 8));
     }
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    unsigned long long hi = 0, lo = 0;
-    float ef[2] = {0.f, 0.f};
+    __syncthreads();
+
+    const float* bias_h = a.bias + size_t(h) * T * T;
+    for (int i = warp; i < T; i += WA_WARPS) {
+      int x[2];
+      bool masked[2];
+      int mx = INT_MIN;
+      const uint32_t* qi = sQ + i * DW;
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj)
-      if (lane + 32 * jj < T) {
-        if (masked[jj] && mx - x[jj] > 255) {   // beyond the table: the clamped tail (host guarantees mask_code reaches it)
-          lo += e_mask;
-          ef[jj] = float(e_mask);
-        } else {
-          const int d = mx - x[jj];
-          hi += sLh[d]; lo += sLl[d];
-          ef[jj] = sLe[d];
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = lane + 32 * jj;
+        x[jj] = INT_MIN;
+        masked[jj] = false;
+        if (j < T) {
+          const uint32_t* kj = sK + j * KSTR;
+          int s = 0;
+#pragma unroll
+          for (int w = 0; w < DW; ++w) s = __dp4a(int(qi[w]), int(kj[w]), s);
+          // qact_attn1: float(sat_s8(s * m)) without leaving fp32 (the biased sum is monotone in its argument)
+          const float c1 = fsub(fminf(fmaxf(fadd(fmul(__int2float_rn(s), a.score_mult), RMAGIC), LO), HI), RMAGIC);
+          const float v = fadd(fmul(c1, a.s_attn1), __ldg(bias_h + i * T + j));                 // + relative position bias
+          const float q2 = POT2 ? fmul(v, r2) : fdiv(v, a.s_attn2);                             // qact2
+          const int c2 = __float_as_int(fminf(fmaxf(fadd(q2, RMAGIC), LO), HI)) - 0x4B400000;
+          masked[jj] = sLab[i] != sLab[j];
+          x[jj] = c2 + (masked[jj] ? a.mask_code : 0);                                          // + mask (after the quantizer)
+          mx = max(mx, x[jj]);
         }
       }
+      mx = __reduce_max_sync(0xffffffffu, mx);
+      uint32_t hi = 0, lo0 = 0, lo1 = 0;
+      float ef[2] = {1.f, 1.f}, rc[2] = {1.f, 1.f};
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { hi += __shfl_xor_sync(0xffffffffu, hi, o); lo += __shfl_xor_sync(0xffffffffu, lo, o); }
-    const float tot = u96_to_f32(hi, lo);
-    uint8_t* bHi = reinterpret_cast<uint8_t*>(pHi);
-    uint8_t* bLo = reinterpret_cast<uint8_t*>(pLo);
+      for (int jj = 0; jj < 2; ++jj)
+        if (lane + 32 * jj < T) {
+          uint32_t lo;
+          if (masked[jj] && mx - x[jj] > 255) {   // beyond the table: the clamped tail (host guarantees mask_code reaches it)
+            lo = e_mask;
+            ef[jj] = e_mask_f;
+            rc[jj] = r_mask;
+          } else {
+            const uint4 t = sLut[mx - x[jj]];
+            hi += t.x;
+            lo = t.y;
+            ef[jj] = __uint_as_float(t.z);
+            rc[jj] = __uint_as_float(t.w);
+          }
+          lo0 += lo & 0xffffu;
+          lo1 += lo >> 16;
+        }
+      // exact row sum: <= 64 entries below 2^55, so each of the three partial sums stays below 2^32
+      const unsigned long long hs = __reduce_add_sync(0xffffffffu, hi);
+      const unsigned long long ls = static_cast<unsigned long long>(__reduce_add_sync(0xffffffffu, lo0)) +
+                                    (static_cast<unsigned long long>(__reduce_add_sync(0xffffffffu, lo1)) << 16);
+      const float tot = __ull2float_rn((hs << 32) + ls);      // < 64 * 2^55: fits 64 bits, rounded once
+      const float tot2 = fmul(tot, 2.0f), tot43 = fmul(tot, 1.33333337306976318359375f);
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const int j = lane + 32 * jj;
-      if (j < T) {
-        const uint32_t c = log2_code(tot, ef[jj]);
-        const uint32_t pv = c == 255u ? 0u : (1u << (15 - c));
-        bHi[j] = uint8_t(pv >> 8);
-        bLo[j] = uint8_t(pv & 0xffu);
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = lane + 32 * jj;
+        if (j < T) {
+          float gmax = 0.f;
+          uint32_t pv = prob_bits_fast(tot2, tot43, rc[jj], gmax) & 0xffffu;
+          if (!(gmax < PROB_GUARD)) pv = shr_clamp(0x8000u, log2_code(tot, ef[jj]));      // next to a rounding / log2 boundary: IEEE division
+          bHi[j] = uint8_t(pv >> 8);
+          bLo[j] = uint8_t(pv & 0xffu);
+        }
       }
-    }
-    __syncwarp();
+      __syncwarp();
 #pragma unroll
-    for (int cc = 0; cc < DH / 32; ++cc) {
-      const int c = lane + 32 * cc;
-      const uint32_t* vt = sVt + c * VSTR;
-      int ah = 0, al = 0;
-      for (int w = 0; w < (T + 3) / 4; ++w) {
-        const uint32_t v = vt[w];
-        ah = dp4a_us_w(pHi[w], v, ah);
-        al = dp4a_us_w(pLo[w], v, al);
+      for (int cc = 0; cc < DH / 32; ++cc) {
+        const int c = lane + 32 * cc;
+        const uint32_t* vt = sVt + c * VSTR;
+        int ah = 0, al = 0;
+        for (int w = 0; w < (T + 3) / 4; ++w) {
+          const uint32_t v = vt[w];
+          ah = dp4a_us_w(pHi[w], v, ah);
+          al = dp4a_us_w(pLo[w], v, al);
+        }
+        a.out[(int64_t(win) * T + i) * (H * DH) + h * DH + c] = int8_t(sat_s8(fmul(float(ah * 256 + al), a.out_mult)));
       }
-      a.out[(int64_t(win) * T + i) * (H * DH) + h * DH + c] = int8_t(sat_s8(fmul(float(ah * 256 + al), a.out_mult)));
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
 int launch_window_attention(const p2v_window_attention_args& a, uint32_t e_mask, cudaStream_t stream) {
-  const int grid = a.n_windows * a.H;
-  if (a.dh == 32) window_attention_kernel<32><<<grid, WA_WARPS * 32, 0, stream>>>(a, e_mask);
-  else window_attention_kernel<64><<<grid, WA_WARPS * 32, 0, stream>>>(a, e_mask);
+  const int units = a.n_windows * a.H;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = std::min(units, sms * 16);       // 16 CTAs of 128 threads per SM, each walks units grid apart
+  int ex = 0;
+  const bool pot2 = std::frexp(a.s_attn2, &ex) == 0.5f;
+#define P2V_WA(DH_) \
+  if (pot2) window_attention_kernel<DH_, true><<<grid, WA_WARPS * 32, 0, stream>>>(a, e_mask, units); \
+  else window_attention_kernel<DH_, false><<<grid, WA_WARPS * 32, 0, stream>>>(a, e_mask, units);
+  if (a.dh == 32) { P2V_WA(32) } else { P2V_WA(64) }
+#undef P2V_WA
   count_launch();
   return check_launch("window_attention_i8");
 }
