@@ -103,6 +103,10 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   const int64_t total = int64_t(B) * Cin * H * gw;  // segments
   const int K = Cin * P * P;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  // int8 codes ([-128, 127] bounds) at a power-of-two scale take the division-free path
+  const bool pot = (__float_as_uint(s) & 0x007fffffu) == 0u && s > 0.f && lo >= -128.f && hi <= 127.f;
+  const float rs = fdiv(1.f, s), mlo = fadd(RMAGIC, lo), mhi = fadd(RMAGIC, hi);
+  const bool vec16 = P % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   for (int64_t seg = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; seg < total; seg += stride) {
     const int j = int(seg % gw);
     int64_t t = seg / gw;
@@ -113,10 +117,33 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
     const float4* src = reinterpret_cast<const float4*>(img + ((int64_t(b) * Cin + c) * H + yy) * W + j * P);
     const int i = yy / P, py = yy % P;
     uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t(b) * gh * gw + int64_t(i) * gw + j) * K + (c * P + py) * P);
-    for (int v = 0; v < P / 4; ++v) {
-      const float4 f = __ldg(src + v);
-      dst[v] = pack4_s8(int(quant_code(f.x, s, zp, lo, hi)), int(quant_code(f.y, s, zp, lo, hi)),
-                        int(quant_code(f.z, s, zp, lo, hi)), int(quant_code(f.w, s, zp, lo, hi)));
+    if (pot) {
+      // power-of-two scale: x * (1/s) == x / s exactly; RNE and the clamp on the 1.5 * 2^23-biased sum (monotone in its argument,
+      // so the clamp is right for any magnitude); no division, FRND or F2I per pixel, one 16-byte store per four words
+      uint32_t w4[4];
+      for (int v0 = 0; v0 < P / 4; v0 += 4) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          if (v0 + v < P / 4) {
+            const float4 f = __ldg(src + v0 + v);
+            const float t0 = fminf(fmaxf(fadd(fadd(fmul(f.x, rs), zp), RMAGIC), mlo), mhi), t1 = fminf(fmaxf(fadd(fadd(fmul(f.y, rs), zp), RMAGIC), mlo), mhi);
+            const float t2 = fminf(fmaxf(fadd(fadd(fmul(f.z, rs), zp), RMAGIC), mlo), mhi), t3 = fminf(fmaxf(fadd(fadd(fmul(f.w, rs), zp), RMAGIC), mlo), mhi);
+            w4[v] = pack4_sat(t0, t1, t2, t3);
+          }
+        }
+        if (vec16 && v0 + 4 <= P / 4) *reinterpret_cast<uint4*>(dst + v0) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        else {
+#pragma unroll
+          for (int v = 0; v < 4; ++v)
+            if (v0 + v < P / 4) dst[v0 + v] = w4[v];
+        }
+      }
+    } else {
+      for (int v = 0; v < P / 4; ++v) {
+        const float4 f = __ldg(src + v);
+        dst[v] = pack4_s8(int(quant_code(f.x, s, zp, lo, hi)), int(quant_code(f.y, s, zp, lo, hi)),
+                          int(quant_code(f.z, s, zp, lo, hi)), int(quant_code(f.w, s, zp, lo, hi)));
+      }
     }
   }
 }

@@ -65,6 +65,25 @@ def test_patchify_matches_conv_layout():
     assert torch.equal(conv, ref @ w.reshape(5, -1).T)
 
 
+@pytest.mark.parametrize("P,s,zp", [(16, 2.0 ** -5, 0.0), (16, 2.0 ** -3, 3.0), (16, 0.0231, 0.0), (4, 2.0 ** -6, 0.0), (4, 0.0173, -2.0)])
+def test_patchify_quantizer_paths(P, s, zp):
+    """power-of-two scales take the division-free path (reciprocal multiply, magic-constant RNE, 16-byte stores), the others
+    the reference-order division: ties, saturation on both sides, huge / tiny magnitudes and a zero point"""
+    torch.manual_seed(int(P + 1000 * s))
+    B = 2
+    img = torch.randn(B, 3, 224, 224) * 2.0
+    flat = img.view(-1)
+    k = torch.arange(-300, 300, dtype=torch.float32)
+    flat[:600] = (k + 0.5) * s                      # exact ties (for a power-of-two s) across and beyond the int8 range
+    flat[600:608] = torch.tensor([1e30, -1e30, 3.4e38, -3.4e38, 1e-30, -1e-30, 0.0, -0.0])
+    flat[608:616] = torch.tensor([4194303.5, -4194303.5, 8388607.0, -8388609.0, 12582912.0, -12582912.0, 16777216.0, -16777217.0]) * s
+    cols = ops.quantize_patchify(img.to(DEV), P, s, zero_point=zp).cpu()
+    q = (img / s + zp).round().clamp(-128, 127)
+    g = 224 // P
+    ref = q.reshape(B, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(B * g * g, 3 * P * P)
+    assert torch.equal(cols.float(), ref), "%d codes differ" % int((cols.float() != ref).sum())
+
+
 # ------------------------------------------------------------------------------------------------ GEMM
 def _acc_exact(A, W):
     return (A.to(DEV).double() @ W.to(DEV).double().T).round().to(torch.int64)
