@@ -260,24 +260,37 @@ class VitEngine:
             for _, fn in prog["steps"]:
                 fn()
             return prog["ws"]["logits"]
-        key = (bits, B)
+        self._graph(prog, (bits, B), 0).replay()
+        return prog["ws"]["logits"]
+
+    def _graph(self, prog, key, first):
+        """CUDA graph of prog's steps[first:] (first = 1: everything after patchify, see __call__)"""
         if key not in self.graphs:
             for _, fn in prog["steps"]:   # eager warm-up: sets kernel attributes, loads modules
                 fn()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                for _, fn in prog["steps"]:
+                for _, fn in prog["steps"][first:]:
                     fn()
             self.graphs[key] = g
-        self.graphs[key].replay()
-        return prog["ws"]["logits"]
+        return self.graphs[key]
 
     def __call__(self, x, bit_config, taps=None):
         if not x.is_cuda:
             raise RuntimeError("p2vit_b200: the quantized forward runs on the GPU only (input is on %s)" % x.device)
         B = x.shape[0]
-        img = self.static_input(B, bit_config)
+        bits = tuple(bit_config)
+        prog = self._program(bits, B)
+        img, pl = prog["ws"]["img"], prog["plan"]
+        if (taps is None and self.use_graph and pl.input_quant and x.dtype == torch.float32 and x.is_contiguous()
+                and x.shape == img.shape and x.data_ptr() != img.data_ptr()):
+            # the only kernel that reads the images is patchify (qact_input + patch gather): launch it on the caller's tensor and
+            # replay the graph of the rest - no 4-byte-per-pixel device-to-device copy into the program's own input buffer
+            g = self._graph(prog, (bits, B, "after patchify"), 1)      # (its first use warms up with the program's own buffer)
+            ops.quantize_patchify(x, pl.P, pl.s_in, out=prog["ws"]["cols"])
+            g.replay()
+            return prog["ws"]["logits"].clone()
         if x.data_ptr() != img.data_ptr():
             img.copy_(x)
         return self.run_static(B, bit_config, taps).clone()
