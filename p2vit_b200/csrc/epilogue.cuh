@@ -140,6 +140,18 @@ __device__ __forceinline__ void epilogue_math(const EpiParams& p, const float* c
     int4 Z4 = make_int4(0, 0, 0, 0);
     if (has_zp) Z4 = *reinterpret_cast<const int4*>(cp + CP_Z * BN + c0 + j4);
     const int Zv[4] = {Z4.x, Z4.y, Z4.z, Z4.w};
+    float Pv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (EPI == P2V_EPI_EMBED) {     // position embedding of this token, four columns per 16-byte load (a lane = a row: one line per lane)
+      const float* pp = p.pos + size_t(tok + 1) * N + col0 + j4;
+      if ((N & 3) == 0 && col0 + j4 + 4 <= N) {
+        const float4 P4 = __ldg(reinterpret_cast<const float4*>(pp));
+        Pv[0] = P4.x; Pv[1] = P4.y; Pv[2] = P4.z; Pv[3] = P4.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col0 + j4 + e < N) Pv[e] = __ldg(pp + e);
+      }
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = j4 + e;
@@ -176,9 +188,7 @@ __device__ __forceinline__ void epilogue_math(const EpiParams& p, const float* c
       } else if (EPI == P2V_EPI_EMBED) {
         const float c = quant_div<EXACT>(y, e_sm, e_rsm, slow);
         const float ecode = quant_div<EXACT>(fmul(c, e_sm), p.aux_scale, e_raux, slow);
-        const int n = col0 + j;
-        const float pv = n < N ? __ldg(p.pos + size_t(tok + 1) * N + n) : 0.f;
-        const float v = fadd(fmul(ecode, p.aux_scale), pv);
+        const float v = fadd(fmul(ecode, p.aux_scale), Pv[e]);
         q[j] = quant_div_s8<EXACT>(v, Ov[e], Rv[e], slow);
       }
     }
