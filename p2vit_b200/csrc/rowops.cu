@@ -301,8 +301,9 @@ __device__ __noinline__ void ln_pot_row_slow(const p2v_layernorm_args& a, const 
 //   cleared and its exponent set to 7:  (bits(A) & 0x807f0000) | 0x43000000;
 //   RNE(v) for |v| < 2^22 = (v + 1.5*2^23) - 1.5*2^23, fused with the preceding power-of-two scaling into one FFMA;
 //   the final saturation to int8 is pack4_sat's.  `mant_max` collects max(mantissa(A)) for the caller's corner-case test.
+template <bool CLAMP_MID>
 __device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const float (&g)[4], const float (&bt)[4], const float (&f)[4],
-                                                     const int (&xv)[4], bool clamp_mid, uint32_t& mant_max) {
+                                                     const int (&xv)[4], uint32_t& mant_max) {
   float r[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -315,7 +316,7 @@ __device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const f
     const float Bv = rintf(fmul(fsub(bt[e], fmul(mos, g[e])), twoN));
     const float sum = __fmaf_rn(sM, __int2float_rn(xv[e]), Bv);     // sM * x is exact (8 x 11 bits): one rounding, as fadd(fmul(..), Bv)
     float yq = fsub(__fmaf_rn(sum, rtwoN, RMAGIC), RMAGIC);          // RNE(sum / 2^N)
-    if (clamp_mid) yq = fminf(fmaxf(yq, -128.f), 127.f);
+    if (CLAMP_MID) yq = fminf(fmaxf(yq, -128.f), 127.f);      // compile-time: two FMNMX per element that the ViT LayerNorms do not need
     r[e] = __fmaf_rn(yq, f[e], RMAGIC);                              // RNE(yq * f) + RMAGIC, saturated below
   }
   return pack4_sat(r[0], r[1], r[2], r[3]);
@@ -329,7 +330,7 @@ __device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const f
 //   Bv = RNE(fl(fl(b - fl(m*g))*ros)*2^N) == RNE(fl(b' - fl(m*g'))*2^N),  b' = b*ros
 //   q  = sat(RNE(((yq*os)/pd)/next))  == sat(RNE(yq*f))
 // (scaling by a power of two commutes with rounding), so the codes equal the generic kernel's bit for bit.
-template <int LPR, int WPLN>
+template <int LPR, int WPLN, bool CLAMP_MID>
 __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_args a) {
   constexpr int GPW = 32 / LPR;                       // rows per warp iteration
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
     uint32_t mant_max = 0;
     if (in_range) {
 #pragma unroll
-      for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_fast_word(t, mos, g[i], bt[i], f[i], xv[i], a.clamp_mid != 0, mant_max);
+      for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_fast_word<CLAMP_MID>(t, mos, g[i], bt[i], f[i], xv[i], mant_max);
     }
     if (!in_range || mant_max >= 0x007ffff0u) {
       ln_pot_row_slow(a, xr, orow, sub, LPR, WPLN, t, mos, clamp_hi);     // rare: out of line, constants re-read from memory
@@ -410,17 +411,22 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
   }
 }
 
-template <int LPR, int WPLN>
-static void launch_ln_pot(const p2v_layernorm_args& a, cudaStream_t stream) {
+template <int LPR, int WPLN, bool CLAMP_MID>
+static void launch_ln_pot_c(const p2v_layernorm_args& a, cudaStream_t stream) {
   constexpr int GPW = 32 / LPR;
   const int rows_per_block = 4 * GPW;
   // persistent: several rows per lane group so the register-resident channel constants are amortised; one wave of resident blocks
   static int occ = 0;
   if (!occ) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_pot_kernel<LPR, WPLN>, 128, 0) != cudaSuccess || occ < 1) occ = 3;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_pot_kernel<LPR, WPLN, CLAMP_MID>, 128, 0) != cudaSuccess || occ < 1) occ = 3;
   }
   const int blocks = std::max(1, std::min((a.rows + rows_per_block - 1) / rows_per_block, num_sms() * occ));
-  layernorm_pot_kernel<LPR, WPLN><<<blocks, 128, 0, stream>>>(a);
+  layernorm_pot_kernel<LPR, WPLN, CLAMP_MID><<<blocks, 128, 0, stream>>>(a);
+}
+template <int LPR, int WPLN>
+static void launch_ln_pot(const p2v_layernorm_args& a, cudaStream_t stream) {
+  if (a.clamp_mid) launch_ln_pot_c<LPR, WPLN, true>(a, stream);
+  else launch_ln_pot_c<LPR, WPLN, false>(a, stream);
 }
 
 int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
