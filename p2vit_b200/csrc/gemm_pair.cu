@@ -189,24 +189,36 @@ __device__ __forceinline__ float quant_pot(float x) { return fadd(x, RMAGIC); }
 // Columns are processed four at a time; a group in which some column's reciprocal bounds disagree (a quotient within a few
 // ulps of a rounding tie, ~1e-5 of the quotients) is redone on the spot with the IEEE division for those columns - the branch
 // is short and keeps no extra state alive, so a hit costs a few hundred cycles of one warp instead of stalling the tile.
+// 16-byte read of the warp's constant table through its 32-bit shared address.  The table used to be addressed through a generic
+// pointer derived from the dynamic shared-memory base; under register pressure the compiler re-derived that pointer for every
+// 4-column group (S2R SR_CgaCtaId / SR_TID.X, the 1024-byte alignment arithmetic: ~4 of the 37 instructions per 32 outputs of the
+// RESIDUAL epilogue, ncu r1n).  An opaque 32-bit address cannot be rematerialised.
+__device__ __forceinline__ float4 prm_ld4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 template <int EPI, bool POT, bool GST>
-__device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const int (&acc)[16], const uint4 resx, uint4& out, const GeluSteps& gst) {
+__device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const uint32_t prm, const int (&acc)[16], const uint4 resx, uint4& out,
+                                           const GeluSteps& gst) {
   uint32_t ow[4];
   const uint32_t rw[4] = {resx.x, resx.y, resx.z, resx.w};
   uint32_t gst_near = 0xffffffffu;
 #pragma unroll
   for (int j4 = 0; j4 < 16; j4 += 4) {
-    const float4 S4 = *reinterpret_cast<const float4*>(prm + PR_S * 64 + j4);
-    const float4 B4 = *reinterpret_cast<const float4*>(prm + PR_B * 64 + j4);
+    // RESIDUAL (9 rows, the tightest on registers) reads through the opaque shared address; the other epilogues keep the generic
+    // pointer: their volatile loads would be ordered against the GELU table lookups and cost more than the re-derivation saves
+    const float4 S4 = EPI == P2V_EPI_RESIDUAL ? prm_ld4(prm + (PR_S * 64 + j4) * 4) : *reinterpret_cast<const float4*>(prmg + PR_S * 64 + j4);
+    const float4 B4 = EPI == P2V_EPI_RESIDUAL ? prm_ld4(prm + (PR_B * 64 + j4) * 4) : *reinterpret_cast<const float4*>(prmg + PR_B * 64 + j4);
     const float Sv[4] = {S4.x, S4.y, S4.z, S4.w}, Bv[4] = {B4.x, B4.y, B4.z, B4.w};
     float t[4];
     if (EPI == P2V_EPI_RESIDUAL) {
-      const float4 a4 = *reinterpret_cast<const float4*>(prm + PR_MLO * 64 + j4);
-      const float4 b4 = *reinterpret_cast<const float4*>(prm + PR_MHI * 64 + j4);
-      const float4 c4 = *reinterpret_cast<const float4*>(prm + PR_M * 64 + j4);
-      const float4 d4 = *reinterpret_cast<const float4*>(prm + PR_RS * 64 + j4);
-      const float4 e4 = *reinterpret_cast<const float4*>(prm + PR_ROLO * 64 + j4);
-      const float4 f4 = *reinterpret_cast<const float4*>(prm + PR_ROHI * 64 + j4);
+      const float4 a4 = prm_ld4(prm + (PR_MLO * 64 + j4) * 4);
+      const float4 b4 = prm_ld4(prm + (PR_MHI * 64 + j4) * 4);
+      const float4 c4 = prm_ld4(prm + (PR_M * 64 + j4) * 4);
+      const float4 d4 = prm_ld4(prm + (PR_RS * 64 + j4) * 4);
+      const float4 e4 = prm_ld4(prm + (PR_ROLO * 64 + j4) * 4);
+      const float4 f4 = prm_ld4(prm + (PR_ROHI * 64 + j4) * 4);
       const float MLv[4] = {a4.x, a4.y, a4.z, a4.w}, MHv[4] = {b4.x, b4.y, b4.z, b4.w}, Mv[4] = {c4.x, c4.y, c4.z, c4.w};
       const float RSv[4] = {d4.x, d4.y, d4.z, d4.w}, OLv[4] = {e4.x, e4.y, e4.z, e4.w}, OHv[4] = {f4.x, f4.y, f4.z, f4.w};
       float y[4], r[4];
@@ -221,7 +233,7 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
         t[e] = quant_iv<false>(fadd(r[e], fmul(k, Mv[e])), OLv[e], OHv[e], 1.f, flag);
       }
       if (flag) {
-        const float4 g4 = *reinterpret_cast<const float4*>(prm + PR_RO_ * 64 + j4);
+        const float4 g4 = prm_ld4(prm + (PR_RO_ * 64 + j4) * 4);
         const float Ov[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -242,7 +254,7 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
       ow[j4 >> 2] = pack4_low_bytes(q[0], q[1], q[2], q[3]);
       continue;
     } else if (POT && EPI == P2V_EPI_GELU) {
-      const float4 R4 = *reinterpret_cast<const float4*>(prm + PR_RO * 64 + j4);
+      const float4 R4 = *reinterpret_cast<const float4*>(prmg + PR_RO * 64 + j4);
       const float Rv[4] = {R4.x, R4.y, R4.z, R4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -250,8 +262,8 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
         t[e] = __fmaf_rn(gelu_erf(y), Rv[e], RMAGIC);      // g * 2^k is exact
       }
     } else {
-      const float4 a4 = *reinterpret_cast<const float4*>(prm + PR_OLO * 64 + j4);
-      const float4 b4 = *reinterpret_cast<const float4*>(prm + PR_OHI * 64 + j4);
+      const float4 a4 = *reinterpret_cast<const float4*>(prmg + PR_OLO * 64 + j4);
+      const float4 b4 = *reinterpret_cast<const float4*>(prmg + PR_OHI * 64 + j4);
       const float OLv[4] = {a4.x, a4.y, a4.z, a4.w}, OHv[4] = {b4.x, b4.y, b4.z, b4.w};
       float y[4];
       uint32_t flag = 0;
@@ -262,7 +274,7 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
         t[e] = quant_iv<false>(y[e], OLv[e], OHv[e], 1.f, flag);
       }
       if (flag) {
-        const float4 g4 = *reinterpret_cast<const float4*>(prm + PR_O * 64 + j4);
+        const float4 g4 = *reinterpret_cast<const float4*>(prmg + PR_O * 64 + j4);
         const float Ov[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) t[e] = quant_iv<true>(y[e], OLv[e], OHv[e], Ov[e], flag);
@@ -274,9 +286,9 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prm, const 
     if (gst_near <= 16u) {     // some y within 8 ulps of the threshold it consulted: the chunk takes the direct evaluation
 #pragma unroll 1
       for (int j4 = 0; j4 < 16; j4 += 4) {
-        const float4 S4 = *reinterpret_cast<const float4*>(prm + PR_S * 64 + j4);
-        const float4 B4 = *reinterpret_cast<const float4*>(prm + PR_B * 64 + j4);
-        const float4 R4 = *reinterpret_cast<const float4*>(prm + PR_RO * 64 + j4);
+        const float4 S4 = *reinterpret_cast<const float4*>(prmg + PR_S * 64 + j4);
+        const float4 B4 = *reinterpret_cast<const float4*>(prmg + PR_B * 64 + j4);
+        const float4 R4 = *reinterpret_cast<const float4*>(prmg + PR_RO * 64 + j4);
         const int a0 = j4 == 0 ? acc[0] : j4 == 4 ? acc[4] : j4 == 8 ? acc[8] : acc[12];
         const int a1 = j4 == 0 ? acc[1] : j4 == 4 ? acc[5] : j4 == 8 ? acc[9] : acc[13];
         const int a2 = j4 == 0 ? acc[2] : j4 == 4 ? acc[6] : j4 == 8 ? acc[10] : acc[14];
@@ -476,6 +488,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int cg = e >> 2;
     const int W = g.W, nch = W >> 4;
     float* prm = prm_all + e * ROWS * 64;
+    uint32_t prm32 = ring + g.off_prm + uint32_t(e) * uint32_t(ROWS) * 256u;     // the same table as a shared-window address (prm_ld4)
+    asm volatile("" : "+r"(prm32));
     const uint32_t tempty0 = mapa_u32(bar_tempty, 0);
     // byte offset of this lane's 16-byte chunk c inside the warp's staging block (row pitch W bytes)
     const uint32_t row_off = uint32_t(lane) * uint32_t(W);
@@ -539,7 +553,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           resx.x ^= 0x80808080u; resx.y ^= 0x80808080u; resx.z ^= 0x80808080u; resx.w ^= 0x80808080u;
         }
         uint4 o;
-        pair_chunk<EPI, POT, GST>(prm + c * 16, cur, resx, o, gst);
+        pair_chunk<EPI, POT, GST>(prm + c * 16, prm32 + uint32_t(c) * 64u, cur, resx, o, gst);
         if (c == 0) {
           if (!RESID) {                     // the previous tile's store must have finished reading this block
             if (lane == 0) bulk_wait_read0();
