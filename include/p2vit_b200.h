@@ -223,6 +223,9 @@ typedef struct {
                                (layers.py:396-410 with x_int = 32*x0) */
   float out_mult;           /* 2^-15 * s_v / s_attn3 */
   const p2v_softmax_lut* lut_dev;
+  const int32_t* out_row_map;   /* optional [n_windows * T]: row (window order) -> destination row of `out`; NULL = same row.
+                                   window_reverse + roll (swin_quant.py:426-436) applied by the store, so the proj GEMM that
+                                   follows reads and writes token order and needs no scatter */
 } p2v_window_attention_args;
 
 int p2v_window_attention_i8(const p2v_window_attention_args* args_host, void* stream);

@@ -49,7 +49,7 @@ class WindowAttentionArgs(C.Structure):
         ("qkv", C.c_void_p), ("out", C.c_void_p),
         ("score_mult", C.c_float), ("s_attn1", C.c_float), ("s_attn2", C.c_float),
         ("bias", C.c_void_p), ("labels", C.c_void_p), ("mask_code", C.c_int), ("mask_exp_int", C.c_uint32),
-        ("out_mult", C.c_float), ("lut_dev", C.c_void_p),
+        ("out_mult", C.c_float), ("lut_dev", C.c_void_p), ("out_row_map", C.c_void_p),
     ]
 
 

@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(WA_WARPS * 32) window_attention_kernel(p2v_win
         }
       }
       __syncwarp();
+      const int64_t orow = a.out_row_map ? int64_t(__ldg(a.out_row_map + int64_t(win) * T + i)) : int64_t(win) * T + i;
 #pragma unroll
       for (int cc = 0; cc < DH / 32; ++cc) {
         const int c = lane + 32 * cc;
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(WA_WARPS * 32) window_attention_kernel(p2v_win
           ah = dp4a_us_w(pHi[w], v, ah);
           al = dp4a_us_w(pLo[w], v, al);
         }
-        a.out[(int64_t(win) * T + i) * (H * DH) + h * DH + c] = int8_t(sat_s8(fmul(float(ah * 256 + al), a.out_mult)));
+        a.out[orow * (H * DH) + h * DH + c] = int8_t(sat_s8(fmul(float(ah * 256 + al), a.out_mult)));
       }
       __syncwarp();
     }

@@ -160,13 +160,13 @@ def attention(args, simt=False):
 
 
 def window_attention_args(qkv, out, n_windows, T, H, dh, windows_per_image, score_mult, s_attn1, s_attn2, bias, labels, mask_code,
-                          mask_exp_int, out_mult, lut_dev):
+                          mask_exp_int, out_mult, lut_dev, out_row_map=None):
     a = WindowAttentionArgs()
     a.n_windows, a.T, a.H, a.dh, a.windows_per_image = n_windows, T, H, dh, windows_per_image
     a.qkv, a.out = ptr(qkv), ptr(out)
     a.score_mult, a.s_attn1, a.s_attn2 = float(score_mult), float(s_attn1), float(s_attn2)
     a.bias, a.labels, a.mask_code, a.mask_exp_int = ptr(bias), ptr(labels), int(mask_code), int(mask_exp_int)
-    a.out_mult, a.lut_dev = float(out_mult), ptr(lut_dev)
+    a.out_mult, a.lut_dev, a.out_row_map = float(out_mult), ptr(lut_dev), ptr(out_row_map)
     return a
 
 

@@ -231,12 +231,13 @@ class SwinEngine:
                                                                      out_i8=qkv, pot=p["qkv_pot"]))))
                 T = p["T"]
                 wa = ops.window_attention_args(qkv, ao, R // T, T, st["heads"], p["dh"], (H // p["ws"]) ** 2, p["score_mult"], p["s_attn1"],
-                                               p["s_attn2"], p["bias"], p["labels"], p["mask_code"], p["mask_exp"], p["out_mult"], p["lut"])
+                                               p["s_attn2"], p["bias"], p["labels"], p["mask_code"], p["mask_exp"], p["out_mult"], p["lut"],
+                                               out_row_map=to_tok)      # window_reverse + roll in the store: `ao` is in token order
                 steps.append((pre + "attn.qact3", (lambda wa=wa: ops.window_attention(wa))))
                 gp = p["proj"]
                 steps.append((pre + "qact2", gemm(ops.gemm_args(ao, gp.W, ops.EPI_RESIDUAL, gp.acc_scale, bias=gp.bias, out_scale=p["proj_out"],
                                                                 mid_scale=p["proj_mid"], res_scale=p["res1_scale"], res=ra, out_i8=rb,
-                                                                row_map=to_tok, pot=intmath.is_pot(gp.acc_scale)))))
+                                                                pot=intmath.is_pot(gp.acc_scale)))))
                 steps.append((pre + "mlp.qact0", ln(p["ln2"], rb, R, C, lnb, clamp_mid=True)))
                 g1 = p["fc1"]
                 steps.append((pre + "mlp.qact1", gemm(ops.gemm_args(lnb, g1.W, ops.EPI_GELU, g1.acc_scale, bias=g1.bias, out_scale=p["fc1_out"],
