@@ -536,6 +536,42 @@ def test_attention_tcgen05_every_probability_code(s_as, spread, mult_fudge):
     assert bad == 0, "%d probability read-backs differ between tcgen05 and dp4a attention" % bad
 
 
+def test_kernels_are_deterministic_over_repeated_launches():
+    """a data race shows up as run-to-run differences long before it shows up against the oracle (an exchange-free pass 1 of
+    the attention kernel once passed every parity test by luck): 12 launches of the attention kernel and of the three
+    CTA-pair GEMM epilogues on the same inputs must agree bit for bit"""
+    B, T, H = 128, 197, 6
+    qkv, (m1, m2, lut), _ = _attention_case(B, T, H, seed=21, s_as=2.0 ** -4, spread=60)
+    first = None
+    for _ in range(12):
+        out = torch.empty((B * T, H * 64), dtype=torch.int8, device=DEV)
+        ops.attention(ops.attention_args(qkv, out, B, T, H, 64, m1, m2, lut))
+        if first is None:
+            first = out
+        else:
+            assert torch.equal(out, first), "attention_tc: %d codes differ between launches" % int((out != first).sum())
+    M, N, K = 197 * 64, 384, 1536
+    A, W, bias = _gemm_inputs(M, N, K, seed=5)
+    fac = torch.tensor([1.0, 2.0, 4.0, 8.0])
+    g = torch.Generator().manual_seed(9)
+    res = _rand_codes(M, N, seed=6).to(DEV)
+    kw = dict(bias=bias.to(DEV), out_scale=(0.0171 * fac[torch.randint(0, 4, (N,), generator=g)]).to(DEV),
+              mid_scale=(0.00931 * fac[torch.randint(0, 4, (N,), generator=g)]).to(DEV),
+              res_scale=(0.0123 * fac[torch.randint(0, 4, (N,), generator=g)]).to(DEV), res=res, pot=True)
+    ops.set_gemm_variant(2)
+    try:
+        first = None
+        for _ in range(12):
+            o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
+            ops.gemm(ops.gemm_args(A.to(DEV), W.to(DEV), ops.EPI_RESIDUAL, torch.full((N,), 2.0 ** -13, device=DEV), out_i8=o8, **kw))
+            if first is None:
+                first = o8
+            else:
+                assert torch.equal(o8, first), "gemm_pair residual: %d codes differ between launches" % int((o8 != first).sum())
+    finally:
+        ops.set_gemm_variant(0)
+
+
 # ------------------------------------------------------------------------------------------------ observers' kernels
 def test_minmax_and_mse_scores():
     torch.manual_seed(9)
