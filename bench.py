@@ -93,6 +93,23 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Multi-GPU runs: keep this rank's threads (and so its pinned staging buffers, first touch) on the CPUs NVML names as local to
+    its GPU - eight ranks pulling 154 MB of pixels per step across the socket interconnect is what held the 8-GPU e2e figure back.
+    Returns the number of CPUs bound to (0 = left alone)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        n = os.cpu_count()
+        mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index), (n + 63) // 64)
+        cpus = [i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def cpu_reference_run(name, batch, steps, warmup, threads=None):
     """the reference's algorithm (oracle/port.py, fp32 fake-quant, torch CPU ops) on the host cores."""
     from oracle.port import VitOracle
@@ -185,6 +202,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else 0      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -420,7 +438,8 @@ def main():
             "dtype": "int8 (int32 accumulate, fp32 requant epilogue)", "data": "synthetic",
             "config": {"workload": workload, "global_batch": B * world, "bit_config": ("[%s]*%d" % (args.bits, len(bits))) if args.bits in ("8", "4") else "".join(str(b) for b in bits), "calibration": calib_src,
                        "calibration_seconds": round(calib_s, 2), "l2": "inputs larger than L2 (fp32 images %.0f MB + int8 workspace per step)" % (B * 3 * 224 * 224 * 4 / 1e6),
-                       "parallelism": "dp%d (batch sharded, no collective in the forward)" % world, "cuda_graph": True},
+                       "parallelism": "dp%d (batch sharded, no collective in the forward)" % world, "cuda_graph": True,
+                       "host_cpus_bound_to_gpu_numa_node": numa_cpus},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 * world, "d2h_bytes_per_step": B * 1000 * 4 * world,
                     "ms_per_step": ms_e2e / args.steps, "path": "pinned host fp32 images -> H2D (copy stream, double buffered) -> model(x, bit_config) -> logits D2H"},
             "gpu_launches": (eng.launches_per_forward() if is_swin else eng.launches_per_forward(bits)) * args.steps,
