@@ -30,6 +30,7 @@ namespace p2v {
 constexpr int PBM = 128;                 // rows per CTA (pair tile: 256)
 constexpr int PBK = 128;                 // K bytes per pipeline stage (one 128-byte swizzle row)
 constexpr int P_EPI_WARPS = 16;
+constexpr int P_EPI_GROUPS = 4;          // column groups of 4 warps (one per TMEM lane quarter) sharing a constant table
 constexpr int P_THREADS = 128 + P_EPI_WARPS * 32;   // warpgroup 0: TMA producer, MMA issuer, 2 idle warps; warpgroups 1-4: epilogue
 constexpr int P_ACC_COLS = 256;          // TMEM columns per accumulator stage
 constexpr uint32_t P_A_BYTES = PBM * PBK;
@@ -487,8 +488,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t quarter = uint32_t(warp) & 3u;         // TMEM lane quarter this warp may read
     const int cg = e >> 2;
     const int W = g.W, nch = W >> 4;
-    float* prm = prm_all + e * ROWS * 64;
-    uint32_t prm32 = ring + g.off_prm + uint32_t(e) * uint32_t(ROWS) * 256u;     // the same table as a shared-window address (prm_ld4)
+    // one constant table per column group, shared by its four warps (one per TMEM lane quarter): warp-private tables cost 36 KB of
+    // shared memory for the RESIDUAL epilogue - the difference between a 3-stage and a 5-stage operand ring next to a resident W tile
+    float* prm = prm_all + cg * ROWS * 64;
+    uint32_t prm32 = ring + g.off_prm + uint32_t(cg) * uint32_t(ROWS) * 256u;    // the same table as a shared-window address (prm_ld4)
     asm volatile("" : "+r"(prm32));
     const uint32_t tempty0 = mapa_u32(bar_tempty, 0);
     // byte offset of this lane's 16-byte chunk c inside the warp's staging block (row pitch W bytes)
@@ -500,8 +503,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     TileIter ti(g, pair, npairs);
     {
       const int n0 = ti.nt * g.BN + cg * W;
-      nx0 = load_raw_col<EPI>(p, n0 + lane, ti.left > 0);
-      nx1 = load_raw_col<EPI>(p, n0 + 32 + lane, ti.left > 0 && 32 + lane < W);
+      nx0 = load_raw_col<EPI>(p, n0 + lane, ti.left > 0 && quarter == 0);          // the quarter-0 warp fills the group's table
+      nx1 = load_raw_col<EPI>(p, n0 + 32 + lane, ti.left > 0 && quarter == 0 && 32 + lane < W);
     }
     uint32_t it = 0;
     int prm_nt = -1;           // column tile whose constants the warp's table holds
@@ -514,17 +517,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t slot = RESID ? (it & slot_mask) : 0u, ruse = it >> g.nslot_log2;
       const uint32_t my_stg = stg + slot * slot_bytes + uint32_t(e) * warp_stg;
       // this tile's column constants (fetched during the previous tile) into the table, then fetch the next tile's
-      if (nt != prm_nt) {
-        __syncwarp();
-        store_col<EPI, POT>(prm, lane, nx0);
-        if (32 + lane < W) store_col<EPI, POT>(prm, 32 + lane, nx1);
-        __syncwarp();
+      if (nt != prm_nt) {       // the four warps of the group walk the same tile sequence: they all take this branch together
+        named_barrier(1 + uint32_t(cg), 128);       // every warp of the group is done reading the previous column tile's constants
+        if (quarter == 0) {
+          store_col<EPI, POT>(prm, lane, nx0);
+          if (32 + lane < W) store_col<EPI, POT>(prm, 32 + lane, nx1);
+        }
+        named_barrier(1 + uint32_t(cg), 128);       // ... and sees the new ones
         prm_nt = nt;
       }
       if (ti.left > 0 && ti.nt != nt) {
         const int nn0 = ti.nt * g.BN + cg * W;
-        nx0 = load_raw_col<EPI>(p, nn0 + lane, true);
-        nx1 = load_raw_col<EPI>(p, nn0 + 32 + lane, 32 + lane < W);
+        nx0 = load_raw_col<EPI>(p, nn0 + lane, quarter == 0);
+        nx1 = load_raw_col<EPI>(p, nn0 + 32 + lane, quarter == 0 && 32 + lane < W);
       }
       if (lane == 0) PTRACE(3 + e, it, 0);
       if (RESID) mbar_wait(bar_rfull + 8 * slot, ruse & 1u);
@@ -640,7 +645,7 @@ static bool plan_pair(const p2v_gemm_args& a, int bn, int rows, bool gst, PairGe
   g.nkb = (a.K + PBK - 1) / PBK;
   g.swz = g.W == 64 ? 2 : (g.W == 32 ? 1 : 0);
   g.nslot_log2 = a.epilogue == P2V_EPI_RESIDUAL ? (g.W == 32 ? 2 : 1) : 0;
-  const size_t prm_bytes = size_t(P_EPI_WARPS) * rows * 64 * 4 + (gst ? P2V_GELU_STEPS_SMEM_MAX : 0);
+  const size_t prm_bytes = size_t(P_EPI_GROUPS) * rows * 64 * 4 + (gst ? P2V_GELU_STEPS_SMEM_MAX : 0);
   const size_t bhalf = size_t(g.BN / 2) * PBK;
   for (;;) {
     const size_t stg_bytes = (size_t(1) << g.nslot_log2) * P_EPI_WARPS * 32 * g.W;
@@ -659,7 +664,7 @@ static bool plan_pair(const p2v_gemm_args& a, int bn, int rows, bool gst, PairGe
     g.off_bres = uint32_t(g.nstages) * g.stage_bytes;
     g.off_stg = g.off_bres + uint32_t(g.bres ? bres_bytes : 0);
     g.off_prm = g.off_stg + uint32_t(stg_bytes);
-    g.off_gst = g.off_prm + uint32_t(P_EPI_WARPS) * rows * 64 * 4;
+    g.off_gst = g.off_prm + uint32_t(P_EPI_GROUPS) * rows * 64 * 4;
     g.smem_bytes = uint32_t(1024 + g.off_prm + prm_bytes);
     return true;
   }
