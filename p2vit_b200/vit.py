@@ -450,8 +450,8 @@ def _vit(embed_dim, depth, num_heads, input_quant, quant, calibrate, cfg, **kwar
 
 def _no_pretrained(pretrained):
     if pretrained:
-        raise RuntimeError("pretrained checkpoints need network access; load a state dict with model.load_state_dict() "
-                           "(key names equal the reference's) or use p2vit_b200.synth for seeded synthetic weights")
+        raise RuntimeError("pretrained checkpoints need network access; load a local file with p2vit_b200.load_checkpoint(model, path) "
+                           "(DeiT / Swin .pth, Flax ViT .npz; key names equal the reference's) or use p2vit_b200.synth for seeded synthetic weights")
 
 
 def deit_tiny_patch16_224(pretrained=False, quant=False, calibrate=False, cfg=None, **kwargs):
