@@ -271,11 +271,11 @@ def main():
     # ---------------- e2e: pinned host images -> H2D -> model(x, bits) -> logits D2H, every step
     out_host = torch.empty((B, 1000), dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream(device=dev)
-    staging = [torch.empty_like(img) for _ in range(2)]
+    staging_f32 = [torch.empty_like(img) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_steps(n):
+    def e2e_steps(n, host=host, staging=staging_f32):
         main_s = torch.cuda.current_stream()
         with torch.cuda.stream(copy_stream):
             staging[0].copy_(host, non_blocking=True)
@@ -304,6 +304,28 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_e2e = float(ms)
+
+    # ---------------- e2e_u8: the same call with the decoder's 8-bit pixels (ToTensor + Normalize + qact_input through the
+    # per-channel code table on the device, bit-identical logits: tests/test_gpu_model.py::test_uint8_pixels_equal_host_normalised_fp32)
+    ms_e2e_u8 = None
+    if getattr(model, "input_quant", True):
+        from p2vit_b200.data import PREPROCESS
+        fam = "swin" if is_swin else ("deit" if args.model.startswith("deit") else "vit")
+        model.set_pixel_normalization(PREPROCESS[fam]["mean"], PREPROCESS[fam]["std"])
+        mean = torch.tensor(PREPROCESS[fam]["mean"]).view(1, 3, 1, 1)
+        std = torch.tensor(PREPROCESS[fam]["std"]).view(1, 3, 1, 1)
+        host_u8 = host.mul(std).add(mean).mul(255).round().clamp(0, 255).to(torch.uint8).contiguous().pin_memory()
+        staging_u8 = [torch.empty(host_u8.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+        e2e_steps(args.warmup, host_u8, staging_u8)
+        barrier()
+        ev0.record()
+        e2e_steps(args.steps, host_u8, staging_u8)
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_e2e_u8 = float(ms)
     sampler.stop_flag = True
 
     # ---------------- per-kernel-family device time (eager launches, CUDA events on the launching stream)
@@ -442,6 +464,10 @@ def main():
                        "host_cpus_bound_to_gpu_numa_node": numa_cpus},
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 * world, "d2h_bytes_per_step": B * 1000 * 4 * world,
                     "ms_per_step": ms_e2e / args.steps, "path": "pinned host fp32 images -> H2D (copy stream, double buffered) -> model(x, bit_config) -> logits D2H"},
+            "e2e_u8": None if ms_e2e_u8 is None else {
+                "value": total_imgs / (ms_e2e_u8 * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * world,
+                "d2h_bytes_per_step": B * 1000 * 4 * world, "ms_per_step": ms_e2e_u8 / args.steps,
+                "path": "pinned host uint8 pixels -> H2D -> model(x_u8, bit_config) (code-table patchify) -> logits D2H; same logits as e2e"},
             "gpu_launches": (eng.launches_per_forward() if is_swin else eng.launches_per_forward(bits)) * args.steps,
             "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line))

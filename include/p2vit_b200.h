@@ -53,6 +53,12 @@ int p2v_dequantize_i8(const int8_t* q, float* y, int64_t n, int C, int64_t inner
 int p2v_quantize_patchify(const float* img, int8_t* out, int B, int Cin, int H, int W, int P,
                           float scale, float zp, int lo, int hi, void* stream);
 
+/* The same step for 8-bit pixels [B,Cin,H,W] (what an image decoder produces, a quarter of the PCIe bytes): ToTensor (x/255),
+ * Normalize ((x-mean)/std; test_quant.py:112-127,565-597) and qact_input depend only on (channel, byte), so `lut` [Cin,256] holds the
+ * int8 code of each byte per channel - tabulated by the caller with p2v_quantize_patchify on the 256 normalised values, which makes
+ * the result identical to the fp32 entry point on the normalised image. */
+int p2v_patchify_u8_lut(const uint8_t* img, const int8_t* lut, int8_t* out, int B, int Cin, int H, int W, int P, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * QLinear / QConv2d(patch-embed) + the QAct(s) that follow it      (layers.py:202-209, 96-103)
  *   acc[m,n] = sum_k A[m,k] * W[n,k]            int8 x int8 -> int32, tcgen05.mma kind::i8

@@ -34,6 +34,7 @@ int launch_quantize(const float* x, int8_t* q, float* y, int64_t n, int C, int64
                     float zp, int lo, int hi, cudaStream_t stream);
 int launch_dequantize(const int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale, float zp,
                       cudaStream_t stream);
+int launch_patchify_u8(const uint8_t* img, const int8_t* lut, int8_t* out, int B, int Cin, int H, int W, int P, cudaStream_t stream);
 int launch_patchify(const float* img, int8_t* out, int B, int Cin, int H, int W, int P, float scale, float zp, int lo, int hi,
                     cudaStream_t stream);
 int launch_fill_cls(int8_t* out, const int8_t* cls_row, int B, int T, int N, cudaStream_t stream);
@@ -100,6 +101,12 @@ int p2v_quantize_patchify(const float* img, int8_t* out, int B, int Cin, int H, 
   P2V_REQUIRE(P % 4 == 0 && W % 4 == 0, "patchify: P and W must be multiples of 4");
   P2V_REQUIRE(lo >= -128 && hi <= 127, "patchify: int8 carrier only");
   return launch_patchify(img, out, B, Cin, H, W, P, scale, zp, lo, hi, (cudaStream_t)stream);
+}
+int p2v_patchify_u8_lut(const uint8_t* img, const int8_t* lut, int8_t* out, int B, int Cin, int H, int W, int P, void* stream) {
+  P2V_REQUIRE(img && lut && out && B > 0 && Cin > 0 && Cin <= 64 && P > 0 && H % P == 0 && W % P == 0, "patchify_u8: bad shape");
+  P2V_REQUIRE(P % 4 == 0 && W % 4 == 0 && (reinterpret_cast<uintptr_t>(img) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+              "patchify_u8: P and W must be multiples of 4, buffers 4-byte aligned");
+  return launch_patchify_u8(img, lut, out, B, Cin, H, W, P, (cudaStream_t)stream);
 }
 int p2v_build_gelu_table(float out_scale, void* table_dev, void* stream) {
   P2V_REQUIRE(table_dev != nullptr && (reinterpret_cast<uintptr_t>(table_dev) & 15) == 0, "build_gelu_table: table must be 16-byte aligned");

@@ -157,6 +157,55 @@ int launch_patchify(const float* img, int8_t* out, int B, int Cin, int H, int W,
   return check_launch("patchify");
 }
 
+// ------------------------------------------------------------------------------------------------
+// 8-bit pixels: ToTensor + Normalize + qact_input of a pixel depend only on (channel, byte), so the host tabulates the 256
+// codes per channel (with the fp32 quantizer above) and this kernel is a table gather fused with the patch gather:
+// 1 byte read + 1 byte written per pixel instead of 4 + 1.  Thread = one P-pixel row segment, like patchify_kernel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patchify_u8_kernel(const uint8_t* __restrict__ img, const int8_t* __restrict__ lut,
+                                                          int8_t* __restrict__ out, int B, int Cin, int H, int W, int P) {
+  extern __shared__ uint8_t lut_s[];
+  for (int i = threadIdx.x; i < Cin * 256; i += blockDim.x) lut_s[i] = uint8_t(lut[i]);
+  __syncthreads();
+  const int gw = W / P, gh = H / P;
+  const int64_t total = int64_t(B) * Cin * H * gw;
+  const int K = Cin * P * P;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const bool vec16 = P % 16 == 0 && W % 16 == 0 && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(img)) & 15) == 0;
+  auto code4 = [](const uint8_t* l, uint32_t w) {
+    return uint32_t(l[w & 255u]) | (uint32_t(l[(w >> 8) & 255u]) << 8) | (uint32_t(l[(w >> 16) & 255u]) << 16) | (uint32_t(l[w >> 24]) << 24);
+  };
+  for (int64_t seg = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; seg < total; seg += stride) {
+    const int j = int(seg % gw);
+    int64_t t = seg / gw;
+    const int yy = int(t % H);
+    t /= H;
+    const int c = int(t % Cin);
+    const int b = int(t / Cin);
+    const uint8_t* src = img + ((int64_t(b) * Cin + c) * H + yy) * W + j * P;
+    const int i = yy / P, py = yy % P;
+    int8_t* dst = out + (int64_t(b) * gh * gw + int64_t(i) * gw + j) * K + (c * P + py) * P;
+    const uint8_t* l = lut_s + c * 256;
+    if (vec16) {
+      for (int v = 0; v < P / 16; ++v) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(src) + v);
+        reinterpret_cast<uint4*>(dst)[v] = make_uint4(code4(l, w.x), code4(l, w.y), code4(l, w.z), code4(l, w.w));
+      }
+    } else {
+      for (int v = 0; v < P / 4; ++v)
+        reinterpret_cast<uint32_t*>(dst)[v] = code4(l, __ldg(reinterpret_cast<const uint32_t*>(src) + v));
+    }
+  }
+}
+
+int launch_patchify_u8(const uint8_t* img, const int8_t* lut, int8_t* out, int B, int Cin, int H, int W, int P, cudaStream_t stream) {
+  const int64_t total = int64_t(B) * Cin * H * (W / P);
+  const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 8));
+  patchify_u8_kernel<<<blocks, 256, Cin * 256, stream>>>(img, lut, out, B, Cin, H, W, P);
+  count_launch();
+  return check_launch("patchify_u8");
+}
+
 __global__ void fill_cls_kernel(int8_t* __restrict__ out, const int8_t* __restrict__ cls_row, int B, int T, int N) {
   const int b = blockIdx.x;
   for (int n = threadIdx.x; n < N; n += blockDim.x) out[size_t(b) * (T + 1) * N + n] = cls_row[n];

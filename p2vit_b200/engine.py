@@ -158,6 +158,7 @@ class VitEngine:
         self.use_graph = use_graph
         self.simt_gemm = simt_gemm      # tests only: route GEMMs and attention through the dp4a cross-check kernels
         self.plans, self.programs, self.graphs = {}, {}, {}
+        self._pixel_luts = {}
 
     # ---- workspace + argument blocks for one (bit_config, batch)
     def _program(self, bits, B):
@@ -283,6 +284,8 @@ class VitEngine:
         bits = tuple(bit_config)
         prog = self._program(bits, B)
         img, pl = prog["ws"]["img"], prog["plan"]
+        if x.dtype == torch.uint8:
+            return self._call_u8(x, prog, bits, B, taps)
         if (taps is None and self.use_graph and pl.input_quant and x.dtype == torch.float32 and x.is_contiguous()
                 and x.shape == img.shape and x.data_ptr() != img.data_ptr()):
             # the only kernel that reads the images is patchify (qact_input + patch gather): launch it on the caller's tensor and
@@ -294,6 +297,30 @@ class VitEngine:
         if x.data_ptr() != img.data_ptr():
             img.copy_(x)
         return self.run_static(B, bit_config, taps).clone()
+
+    def _call_u8(self, x, prog, bits, B, taps):
+        """8-bit pixels: ToTensor + Normalize + qact_input through the per-channel code table (ops.pixel_code_table; the
+        normalisation is the one set with model.set_pixel_normalization), then the graph of everything after patchify."""
+        pl, ws = prog["plan"], prog["ws"]
+        norm = getattr(self.model, "pixel_norm", None)
+        if norm is None:
+            raise RuntimeError("uint8 input needs model.set_pixel_normalization(mean, std) (test_quant.py:112-127)")
+        if not pl.input_quant:
+            raise NotImplementedError("uint8 input needs an input quantizer (input_quant=True models)")
+        if taps is not None or tuple(x.shape) != tuple(ws["img"].shape) or not x.is_contiguous():
+            raise ValueError("uint8 input: contiguous [B,3,%d,%d] batch expected (no taps)" % tuple(ws["img"].shape[2:]))
+        key = (norm, float(pl.s_in))
+        if key not in self._pixel_luts:
+            self._pixel_luts[key] = ops.pixel_code_table(norm[0], norm[1], pl.s_in, x.device)
+        if self.use_graph:
+            g = self._graph(prog, (bits, B, "after patchify"), 1)
+            ops.patchify_u8(x, self._pixel_luts[key], pl.P, out=ws["cols"])
+            g.replay()
+        else:
+            ops.patchify_u8(x, self._pixel_luts[key], pl.P, out=ws["cols"])
+            for _, fn in prog["steps"][1:]:
+                fn()
+        return ws["logits"].clone()
 
 
 def T_side(pl):

@@ -65,6 +65,31 @@ def quantize_patchify(img, patch, scale, zero_point=0.0, lo=-128, hi=127, out=No
     return out
 
 
+def patchify_u8(img_u8, lut, patch, out=None):
+    """uint8 pixels [B,Cin,H,W] + per-channel code table [Cin,256] -> int8 patch rows (same layout as quantize_patchify)."""
+    if img_u8.dtype != torch.uint8 or lut.dtype != torch.int8 or not img_u8.is_contiguous():
+        raise ValueError("patchify_u8: contiguous uint8 image and int8 table expected")
+    B, Cin, H, W = img_u8.shape
+    if tuple(lut.shape) != (Cin, 256):
+        raise ValueError("patchify_u8: table must be [Cin, 256]")
+    rows, K = B * (H // patch) * (W // patch), Cin * patch * patch
+    if out is None:
+        out = torch.empty((rows, K), dtype=torch.int8, device=img_u8.device)
+    check(_lib.load().p2v_patchify_u8_lut(ptr(img_u8), ptr(lut), ptr(out), B, Cin, H, W, patch, stream()), "patchify_u8_lut")
+    return out
+
+
+def pixel_code_table(mean, std, patch_scale, device):
+    """[Cin,256] int8: qact_input code of ToTensor + Normalize of every byte value (x/255, then (x - mean)/std in fp32, the order
+    torchvision applies; reference test_quant.py:565-597), produced by the fp32 quantizer kernel itself."""
+    mean = torch.as_tensor(mean, dtype=torch.float32, device=device).reshape(-1, 1)
+    std = torch.as_tensor(std, dtype=torch.float32, device=device).reshape(-1, 1)
+    v = torch.arange(256, dtype=torch.float32, device=device).div(255).reshape(1, 256)
+    x = v.sub(mean).div(std)                                     # [Cin, 256]
+    Cin = x.shape[0]
+    return quantize_patchify(x.reshape(1, Cin, 16, 16).contiguous(), 16, patch_scale).reshape(Cin, 256).contiguous()
+
+
 def gemm_args(A, W, epilogue, acc_scale, bias=None, out_scale=None, mid_scale=None, res_scale=None, res=None, pos=None,
               aux_scale=0.0, tokens_per_image=0, out_i8=None, out_f32=None, pot=False, zp_corr=None, row_map=None, gelu_table=None):
     M, K = A.shape

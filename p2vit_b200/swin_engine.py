@@ -179,6 +179,7 @@ class SwinEngine:
     def __init__(self, model, use_graph=True):
         self.model, self.use_graph = model, use_graph
         self.plan, self.programs, self.graphs = None, {}, {}
+        self._pixel_luts = {}
 
     def _program(self, B):
         if B in self.programs:
@@ -311,6 +312,39 @@ class SwinEngine:
             raise RuntimeError("p2vit_b200: the quantized forward runs on the GPU only (input is on %s)" % x.device)
         B = x.shape[0]
         img = self.static_input(B)
+        if x.dtype == torch.uint8:
+            return self._call_u8(x, B, taps)
         if x.data_ptr() != img.data_ptr():
             img.copy_(x)
         return self.run_static(B, taps).clone()
+
+    def _call_u8(self, x, B, taps):
+        """8-bit pixels through the per-channel code table (see VitEngine._call_u8); steps[0] is the fp32 patchify it replaces."""
+        prog, pl = self._program(B), self.plan
+        ws = prog["ws"]
+        norm = getattr(self.model, "pixel_norm", None)
+        if norm is None:
+            raise RuntimeError("uint8 input needs model.set_pixel_normalization(mean, std) (test_quant.py:112-127)")
+        if taps is not None or tuple(x.shape) != tuple(ws["img"].shape) or not x.is_contiguous():
+            raise ValueError("uint8 input: contiguous [B,3,%d,%d] batch expected (no taps)" % tuple(ws["img"].shape[2:]))
+        key = (norm, float(pl.s_in))
+        if key not in self._pixel_luts:
+            self._pixel_luts[key] = ops.pixel_code_table(norm[0], norm[1], pl.s_in, x.device)
+        assert prog["steps"][0][0] == "patchify"
+        gkey = (B, "after patchify")
+        if self.use_graph and gkey not in self.graphs:
+            for _, fn in prog["steps"]:
+                fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _, fn in prog["steps"][1:]:
+                    fn()
+            self.graphs[gkey] = g
+        ops.patchify_u8(x, self._pixel_luts[key], pl.P, out=ws["cols"])
+        if self.use_graph:
+            self.graphs[gkey].replay()
+        else:
+            for _, fn in prog["steps"][1:]:
+                fn()
+        return ws["logits"].clone()

@@ -262,6 +262,15 @@ _Q_TYPES = (QConv2d, QLinear, QAct, QIntSoftmax)
 class QuantModelMixin:
     """flag protocol and calibrated-state exchange shared by the ViT and Swin model classes"""
 
+    pixel_norm = None
+
+    def set_pixel_normalization(self, mean, std):
+        """Declare the ToTensor + Normalize constants of the data pipeline (test_quant.py:112-127; p2vit_b200.data.PREPROCESS) so
+        the quantized forward also accepts the decoder's uint8 pixels [B,3,H,W]: `model(x_u8, bit_config)` then equals
+        `model(((x_u8.float() / 255) - mean) / std, bit_config)` bit for bit, with a quarter of the host-to-device bytes."""
+        self.pixel_norm = (tuple(float(m) for m in mean), tuple(float(v) for v in std))
+        return self
+
     # ---- flag protocol (vit_fquant.py:797-828)
     def model_quant(self, flag="on"):
         if flag == "on":

@@ -366,3 +366,28 @@ def test_mixed_precision_search_flow():
     for cfg, acc in popu:
         assert len(cfg) == n and set(cfg) <= {4, 8} and search.model_cost(res["flops"], cfg) <= lim
         assert runner.validate(m, batches, cfg)[1] == acc            # deterministic: the memoised score is reproducible
+
+
+def test_uint8_pixels_equal_host_normalised_fp32(golden):
+    """`model(x_u8)` after set_pixel_normalization == `model(Normalize(ToTensor(x_u8)))`: logits bit for bit, through the graph
+    and the eager engine; without the normalisation constants the byte input is refused"""
+    from p2vit_b200.data import PREPROCESS
+    g = golden("deit_tiny_minmax")
+    m = _model("deit_tiny", g)
+    bits = [8] * (4 * m.depth + 2)
+    gen = torch.Generator().manual_seed(11)
+    x8 = torch.randint(0, 256, (6, 3, 224, 224), generator=gen, dtype=torch.uint8)
+    x8[:, :, ::16, :] //= 3                                            # some structure across patches
+    with pytest.raises(RuntimeError):
+        m(x8.cuda(), bits)
+    pp = PREPROCESS["deit"]
+    m.set_pixel_normalization(pp["mean"], pp["std"])
+    mean, std = torch.tensor(pp["mean"]).view(1, 3, 1, 1), torch.tensor(pp["std"]).view(1, 3, 1, 1)
+    xf = x8.float().div(255).sub(mean).div(std)
+    want = m(xf.cuda(), bits)[0].cpu()
+    got = m(x8.cuda(), bits)[0].cpu()
+    assert torch.equal(got, want)
+    assert torch.equal(m(x8.cuda(), bits)[0].cpu(), want)                # graph replay
+    eng = VitEngine(m, use_graph=False)
+    assert torch.equal(eng(x8.cuda(), bits).cpu(), want)
+    assert len(set(want.argmax(1).tolist())) > 1

@@ -626,3 +626,40 @@ def test_layernorm_floor_log2_follows_fp32_rounding():
                            torch.ones(C, device=DEV), 1.0, True, out_f32=of)
     ops.layernorm(a)
     assert torch.equal(of.cpu(), ref), "mismatches %d" % int((of.cpu() != ref).sum())
+
+
+# ------------------------------------------------------------------------------------------------ 8-bit pixel ingest
+def _u8_batch(B, side, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, 256, (B, 3, side, side), generator=g, dtype=torch.uint8)
+    x.view(-1)[:256] = torch.arange(256, dtype=torch.uint8)           # every byte value, whatever the draw
+    return x
+
+
+@pytest.mark.parametrize("P,s,mean,std", [(16, 2.0 ** -5, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)), (16, 0.0231, (0.5, 0.5, 0.5), (0.5, 0.5, 0.5)),
+                                          (4, 2.0 ** -6, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+def test_patchify_u8_equals_fp32_path_on_normalised_pixels(P, s, mean, std):
+    """ToTensor + Normalize on the host (the reference's data pipeline, test_quant.py:565-597) then the fp32 entry point,
+    against the byte entry point with the per-channel code table"""
+    x8 = _u8_batch(3, 224, seed=P)
+    m, sd = torch.tensor(mean).view(1, 3, 1, 1), torch.tensor(std).view(1, 3, 1, 1)
+    xf = x8.float().div(255).sub(m).div(sd)
+    want = ops.quantize_patchify(xf.to(DEV), P, s).cpu()
+    # and against plain torch, so the table is not only self-consistent
+    q = (xf / s).round().clamp(-128, 127)
+    g = 224 // P
+    assert torch.equal(want.float(), q.reshape(3, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(3 * g * g, 3 * P * P))
+    lut = ops.pixel_code_table(mean, std, s, DEV)
+    assert lut.shape == (3, 256) and lut.dtype == torch.int8
+    got = ops.patchify_u8(x8.to(DEV), lut, P).cpu()
+    assert torch.equal(got, want), "%d codes differ" % int((got != want).sum())
+
+
+def test_patchify_u8_rejects_bad_arguments():
+    lut = torch.zeros((3, 256), dtype=torch.int8, device=DEV)
+    with pytest.raises(ValueError):
+        ops.patchify_u8(torch.zeros((1, 3, 32, 32), device=DEV), lut, 16)                       # fp32 image
+    with pytest.raises(ValueError):
+        ops.patchify_u8(torch.zeros((1, 3, 32, 32), dtype=torch.uint8, device=DEV), lut[:2], 16)  # table of another channel count
+    with pytest.raises(RuntimeError):
+        ops.patchify_u8(torch.zeros((1, 3, 30, 32), dtype=torch.uint8, device=DEV), lut, 16)      # H not a multiple of P

@@ -144,3 +144,17 @@ def test_window_attention_kernel_vs_torch():
     ops.window_attention(a)
     bad = int((out.cpu().float().reshape(nW, T, C) != ref).sum())
     assert bad == 0, "%d of %d codes differ" % (bad, ref.numel())
+
+
+def test_swin_uint8_pixels_equal_host_normalised_fp32(golden):
+    from p2vit_b200.data import PREPROCESS
+    g = golden("swin_micro_minmax")
+    m = _model(g)
+    pp = PREPROCESS["swin"]
+    m.set_pixel_normalization(pp["mean"], pp["std"])
+    gen = torch.Generator().manual_seed(12)
+    x8 = torch.randint(0, 256, (4, 3, 224, 224), generator=gen, dtype=torch.uint8)
+    mean, std = torch.tensor(pp["mean"]).view(1, 3, 1, 1), torch.tensor(pp["std"]).view(1, 3, 1, 1)
+    want = m(x8.float().div(255).sub(mean).div(std).cuda())[0].cpu()
+    assert torch.equal(m(x8.cuda())[0].cpu(), want)
+    assert torch.equal(m(x8.cuda())[0].cpu(), want)
