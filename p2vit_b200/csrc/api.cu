@@ -1,6 +1,7 @@
 // extern "C" surface of libp2vit_b200.so (include/p2vit_b200.h): argument validation + launch.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include "common.cuh"
 
@@ -14,6 +15,13 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("P2VIT_PDL");
+    return e && e[0] == '1';          // off unless asked for, until the A/B on the GPU has been read
+  }();
+  return on;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int check_launch(const char* what) {

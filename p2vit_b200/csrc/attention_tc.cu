@@ -116,6 +116,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == AT_SM_WARPS) {
@@ -406,8 +408,8 @@ int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
   // power-of-two score multiplier in [2^-20, 2^8]: RMAGIC * (1 - mult) is then exact and so is the fused scaling
   int mexp = 0;
   const bool potm = std::frexp(a.score_mult, &mexp) == 0.5f && mexp >= -19 && mexp <= 9;
-  if (potm) attention_tc_kernel<true><<<grid, AT_THREADS, AT_SMEM_ALLOC, stream>>>(tmQ, tmKV, p);
-  else attention_tc_kernel<false><<<grid, AT_THREADS, AT_SMEM_ALLOC, stream>>>(tmQ, tmKV, p);
+  if (potm) launch_pdl(attention_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
+  else launch_pdl(attention_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
   count_launch();
   return check_launch("attention_tc");
 }

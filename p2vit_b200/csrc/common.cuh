@@ -22,6 +22,31 @@ int check_launch(const char* what);
     }                               \
   } while (0)
 
+// Programmatic dependent launch.  Every kernel of the forward is launched with the programmatic-stream-serialization attribute
+// (launch_pdl) and runs  <prologue on constants: barrier init, TMEM allocation, tables> ; pdl_wait() ; pdl_trigger() ; <work>.
+// pdl_wait returns when the preceding kernel has completed and its stores are visible, so everything that reads activations or
+// writes a buffer comes after it; pdl_trigger (after the wait: at most one kernel runs ahead) lets the next kernel's CTAs take an SM
+// as soon as this kernel's CTA on it exits, and run their prologue under this kernel's tail.  Every PDL-launched kernel must reach
+// pdl_wait - a kernel that finished without it would let its successor overtake its predecessor.  P2VIT_PDL=0 turns the attribute off
+// (the device instructions are no-ops then).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }

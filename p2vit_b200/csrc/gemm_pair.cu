@@ -380,6 +380,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
+  pdl_wait();                  // the prologue above touched constants only (common.cuh: programmatic dependent launch)
+  pdl_trigger();
   const uint32_t tmem_base = tmem_slot;
 
   // Register file: 16 K registers per SM sub-partition hold 1 control warp + 4 epilogue warps.  The kernel starts with 96 per
@@ -707,7 +709,7 @@ static int launch_pair(const p2v_gemm_args& a, const PairGeom& g, const CUtensor
   }
   const int grid = 2 * std::min(g.tiles, max_pairs());
   EpiParams p = make_epi_params(a);
-  kern<<<grid, P_THREADS, g.smem_bytes, stream>>>(tmA, tmB, tmO, tmR, p, g);
+  launch_pdl(kern, dim3(grid), dim3(P_THREADS), g.smem_bytes, stream, tmA, tmB, tmO, tmR, p, g);
   count_launch();
   return check_launch("gemm_pair");
 }

@@ -66,6 +66,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
+  pdl_trigger();
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
@@ -206,7 +208,7 @@ static int launch_tc_bn(const p2v_gemm_args& a, cudaStream_t stream) {
       P2V_REQUIRE(e == cudaSuccess, "gemm_tc: cannot set %zu bytes of dynamic shared memory: %s", smem, cudaGetErrorString(e)); \
       attr = true;                                                                                                         \
     }                                                                                                                      \
-    kern<<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, p, tiles_m, tiles_n);                                               \
+    launch_pdl(kern, dim3(grid), dim3(TC_THREADS), smem, stream, tmA, tmB, p, tiles_m, tiles_n);                                             \
   }
   if (GTAB) {
     P2V_TC_LAUNCH(P2V_EPI_GELU, true)

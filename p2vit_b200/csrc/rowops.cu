@@ -99,6 +99,8 @@ int launch_dequantize(const int8_t* q, float* y, int64_t n, int C, int64_t inner
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ img, int8_t* __restrict__ out, int B, int Cin,
                                                        int H, int W, int P, float s, float zp, float lo, float hi) {
+  pdl_wait();
+  pdl_trigger();
   const int gw = W / P, gh = H / P;
   const int64_t total = int64_t(B) * Cin * H * gw;  // segments
   const int K = Cin * P * P;
@@ -152,7 +154,7 @@ int launch_patchify(const float* img, int8_t* out, int B, int Cin, int H, int W,
                     cudaStream_t stream) {
   const int64_t total = int64_t(B) * Cin * H * (W / P);
   const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 16));
-  patchify_kernel<<<blocks, 256, 0, stream>>>(img, out, B, Cin, H, W, P, scale, zp, float(lo), float(hi));
+  launch_pdl(patchify_kernel, dim3(blocks), dim3(256), 0, stream, img, out, B, Cin, H, W, P, scale, zp, float(lo), float(hi));
   count_launch();
   return check_launch("patchify");
 }
@@ -165,6 +167,8 @@ int launch_patchify(const float* img, int8_t* out, int B, int Cin, int H, int W,
 __global__ void __launch_bounds__(256) patchify_u8_kernel(const uint8_t* __restrict__ img, const int8_t* __restrict__ lut,
                                                           int8_t* __restrict__ out, int B, int Cin, int H, int W, int P) {
   extern __shared__ uint8_t lut_s[];
+  pdl_wait();
+  pdl_trigger();
   for (int i = threadIdx.x; i < Cin * 256; i += blockDim.x) lut_s[i] = uint8_t(lut[i]);
   __syncthreads();
   const int gw = W / P, gh = H / P;
@@ -201,18 +205,20 @@ __global__ void __launch_bounds__(256) patchify_u8_kernel(const uint8_t* __restr
 int launch_patchify_u8(const uint8_t* img, const int8_t* lut, int8_t* out, int B, int Cin, int H, int W, int P, cudaStream_t stream) {
   const int64_t total = int64_t(B) * Cin * H * (W / P);
   const int blocks = int(std::min<int64_t>((total + 255) / 256, int64_t(num_sms()) * 8));
-  patchify_u8_kernel<<<blocks, 256, Cin * 256, stream>>>(img, lut, out, B, Cin, H, W, P);
+  launch_pdl(patchify_u8_kernel, dim3(blocks), dim3(256), size_t(Cin) * 256, stream, img, lut, out, B, Cin, H, W, P);
   count_launch();
   return check_launch("patchify_u8");
 }
 
 __global__ void fill_cls_kernel(int8_t* __restrict__ out, const int8_t* __restrict__ cls_row, int B, int T, int N) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   for (int n = threadIdx.x; n < N; n += blockDim.x) out[size_t(b) * (T + 1) * N + n] = cls_row[n];
 }
 
 int launch_fill_cls(int8_t* out, const int8_t* cls_row, int B, int T, int N, cudaStream_t stream) {
-  fill_cls_kernel<<<B, 128, 0, stream>>>(out, cls_row, B, T, N);
+  launch_pdl(fill_cls_kernel, dim3(B), dim3(128), 0, stream, out, cls_row, B, T, N);
   count_launch();
   return check_launch("fill_cls");
 }
@@ -225,6 +231,8 @@ __device__ __forceinline__ float div_by(float x, float s) { return POT ? fmul(x,
 
 template <int WPL, bool POT>
 __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
+  pdl_wait();
+  pdl_trigger();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nwords = a.C >> 2;
@@ -381,6 +389,8 @@ __device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const f
 // (scaling by a power of two commutes with rounding), so the codes equal the generic kernel's bit for bit.
 template <int LPR, int WPLN, bool CLAMP_MID>
 __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_args a) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int GPW = 32 / LPR;                       // rows per warp iteration
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
@@ -470,7 +480,7 @@ static void launch_ln_pot_c(const p2v_layernorm_args& a, cudaStream_t stream) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_pot_kernel<LPR, WPLN, CLAMP_MID>, 128, 0) != cudaSuccess || occ < 1) occ = 3;
   }
   const int blocks = std::max(1, std::min((a.rows + rows_per_block - 1) / rows_per_block, num_sms() * occ));
-  layernorm_pot_kernel<LPR, WPLN, CLAMP_MID><<<blocks, 128, 0, stream>>>(a);
+  launch_pdl(layernorm_pot_kernel<LPR, WPLN, CLAMP_MID>, dim3(blocks), dim3(128), 0, stream, a);
 }
 template <int LPR, int WPLN>
 static void launch_ln_pot(const p2v_layernorm_args& a, cudaStream_t stream) {
@@ -505,8 +515,8 @@ int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
   const int wpl = (a.C / 4 + 31) / 32;
   const int blocks = std::min((a.rows + 7) / 8, num_sms() * 8);
 #define P2V_LN(W)                                                                   \
-  if (a.pot_scales) layernorm_kernel<W, true><<<blocks, 256, 0, stream>>>(a);       \
-  else layernorm_kernel<W, false><<<blocks, 256, 0, stream>>>(a);
+  if (a.pot_scales) launch_pdl(layernorm_kernel<W, true>, dim3(blocks), dim3(256), 0, stream, a);       \
+  else launch_pdl(layernorm_kernel<W, false>, dim3(blocks), dim3(256), 0, stream, a);
   if (wpl <= 1) { P2V_LN(1) } else if (wpl <= 2) { P2V_LN(2) } else if (wpl <= 3) { P2V_LN(3) } else if (wpl <= 4) { P2V_LN(4) }
   else if (wpl <= 6) { P2V_LN(6) } else if (wpl <= 8) { P2V_LN(8) } else if (wpl <= 12) { P2V_LN(12) }
   else if (wpl <= 16) { P2V_LN(16) } else { P2V_LN(32) }

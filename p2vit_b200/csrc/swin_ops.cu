@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(WA_WARPS * 32) window_attention_kernel(p2v_win
   __shared__ uint32_t sQ[WA_MAXT * DW], sK[WA_MAXT * KSTR], sVt[DH * VSTR], sP[WA_WARPS * 2 * TW];
   __shared__ uint4 sLut[256];          // hi, lo, bits(exp_f32), bits(1 / exp_f32)
   __shared__ int8_t sLab[WA_MAXT];
+  pdl_wait();
+  pdl_trigger();
   const int T = a.T, H = a.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row_bytes = int64_t(3) * H * DH;
@@ -168,8 +170,8 @@ int launch_window_attention(const p2v_window_attention_args& a, uint32_t e_mask,
   int ex = 0;
   const bool pot2 = std::frexp(a.s_attn2, &ex) == 0.5f;
 #define P2V_WA(DH_) \
-  if (pot2) window_attention_kernel<DH_, true><<<grid, WA_WARPS * 32, 0, stream>>>(a, e_mask, units); \
-  else window_attention_kernel<DH_, false><<<grid, WA_WARPS * 32, 0, stream>>>(a, e_mask, units);
+  if (pot2) launch_pdl(window_attention_kernel<DH_, true>, dim3(grid), dim3(WA_WARPS * 32), 0, stream, a, e_mask, units); \
+  else launch_pdl(window_attention_kernel<DH_, false>, dim3(grid), dim3(WA_WARPS * 32), 0, stream, a, e_mask, units);
   if (a.dh == 32) { P2V_WA(32) } else { P2V_WA(64) }
 #undef P2V_WA
   count_launch();
@@ -179,6 +181,8 @@ int launch_window_attention(const p2v_window_attention_args& a, uint32_t e_mask,
 // ------------------------------------------------------------------------------------------------ patch-merging gather
 __global__ void __launch_bounds__(256) gather_rows_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out,
                                                           const int32_t* __restrict__ src, int64_t total16, int segs, int C16) {
+  pdl_wait();
+  pdl_trigger();
   // one 16-byte chunk per thread: chunk index -> (output row, segment, chunk in segment)
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total16; i += int64_t(gridDim.x) * blockDim.x) {
     const int ch = int(i % C16);
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const int8_t* __restri
 int launch_gather_rows(const int8_t* in, int8_t* out, const int32_t* src, int rows_out, int segs, int C, cudaStream_t stream) {
   const int64_t total16 = int64_t(rows_out) * segs * (C / 16);
   const int blocks = int(std::min<int64_t>((total16 + 255) / 256, 148 * 16));
-  gather_rows_kernel<<<blocks, 256, 0, stream>>>(in, out, src, total16, segs, C / 16);
+  launch_pdl(gather_rows_kernel, dim3(blocks), dim3(256), 0, stream, in, out, src, total16, segs, C / 16);
   count_launch();
   return check_launch("gather_rows_i8");
 }
@@ -199,6 +203,8 @@ int launch_gather_rows(const int8_t* in, int8_t* out, const int32_t* src, int ro
 // ------------------------------------------------------------------------------------------------ token average pool + QAct
 __global__ void __launch_bounds__(128) avgpool_quant_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int T, int C,
                                                             float s_in, float s_out) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     int s = 0;
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(128) avgpool_quant_kernel(const int8_t* __rest
 }
 
 int launch_avgpool_quant(const int8_t* in, int8_t* out, int B, int T, int C, float s_in, float s_out, cudaStream_t stream) {
-  avgpool_quant_kernel<<<B, 128, 0, stream>>>(in, out, T, C, s_in, s_out);
+  launch_pdl(avgpool_quant_kernel, dim3(B), dim3(128), 0, stream, in, out, T, C, s_in, s_out);
   count_launch();
   return check_launch("avgpool_quant_i8");
 }
