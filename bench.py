@@ -165,6 +165,11 @@ def make_bit_config(kind, model):
 
 
 def main():
+    # stdout carries the JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its version banner there
+    # when the box sets NCCL_DEBUG) go to stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -195,7 +200,7 @@ def main():
                 "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                                  "sample": "oracle/port.py quantized forward, batch %d" % cb},
                 "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        _emit(line, real_stdout)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
@@ -470,9 +475,15 @@ def main():
                 "path": "pinned host uint8 pixels -> H2D -> model(x_u8, bit_config) (code-table patchify) -> logits D2H; same logits as e2e"},
             "gpu_launches": (eng.launches_per_forward() if is_swin else eng.launches_per_forward(bits)) * args.steps,
             "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    _emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _emit(line, real_stdout):
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
