@@ -16,12 +16,22 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-bool pdl_enabled() {
-  static const bool on = [] {
+// 0 = never, 1 = every launch, 2 (default) = launches that are being captured into a CUDA graph.  The engines capture the
+// forward once per (bit_config, batch) and every constant a kernel reads ahead of its dependency wait was written at plan time;
+// eager launches (per-operator modules, taps) may follow a torch kernel that has just produced such a constant, so they keep the
+// plain stream order.
+static int pdl_mode() {
+  static const int mode = [] {
     const char* e = std::getenv("P2VIT_PDL");
-    return e && e[0] == '1';          // off unless asked for, until the A/B on the GPU has been read
+    return e && e[0] == '0' ? 0 : (e && e[0] == '1' ? 1 : 2);
   }();
-  return on;
+  return mode;
+}
+bool pdl_enabled(cudaStream_t stream) {
+  const int m = pdl_mode();
+  if (m != 2) return m == 1;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(stream, &st) == cudaSuccess && st == cudaStreamCaptureStatusActive;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int check_launch(const char* what) {

@@ -27,11 +27,11 @@ int check_launch(const char* what);
 // pdl_wait returns when the preceding kernel has completed and its stores are visible, so everything that reads activations or
 // writes a buffer comes after it; pdl_trigger (after the wait: at most one kernel runs ahead) lets the next kernel's CTAs take an SM
 // as soon as this kernel's CTA on it exits, and run their prologue under this kernel's tail.  Every PDL-launched kernel must reach
-// pdl_wait - a kernel that finished without it would let its successor overtake its predecessor.  P2VIT_PDL=0 turns the attribute off
-// (the device instructions are no-ops then).
+// pdl_wait - a kernel that finished without it would let its successor overtake its predecessor.  The attribute is set for launches
+// captured into a CUDA graph (api.cu: pdl_mode; P2VIT_PDL=0 never, =1 always); without it the device instructions are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled();
+bool pdl_enabled(cudaStream_t stream);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -41,7 +41,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled(stream) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);

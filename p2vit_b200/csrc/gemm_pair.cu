@@ -380,8 +380,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
-  pdl_wait();                  // the prologue above touched constants only (common.cuh: programmatic dependent launch)
-  pdl_trigger();
+  // Programmatic dependent launch (common.cuh): the dependency wait sits in the roles that touch activations - the producer after it
+  // has started the first resident W tile (a constant), the epilogue warps before their first tile; the MMA warp reads shared memory only.
   const uint32_t tmem_base = tmem_slot;
 
   // Register file: 16 K registers per SM sub-partition hold 1 control warp + 4 epilogue warps.  The kernel starts with 96 per
@@ -399,7 +399,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t bfull0 = mapa_u32(bar_bfull, 0);
       uint32_t itk = 0, it = 0;
       int cur_nt = -1;
-      for (TileIter ti(g, pair, npairs); ti.left > 0; ti.next(), ++it) {
+      TileIter ti(g, pair, npairs);
+      if (g.bres && ti.left > 0) {      // first W tile before the dependency wait: it overlaps the previous kernel's tail
+        const int nb0 = ti.nt * g.BN + int(rank) * (g.BN / 2);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(bar_bfull, 2u * uint32_t(g.nkb) * bhalf_bytes);
+          for (int kb = 0; kb < g.nkb; ++kb) tma_load_2d_pair(bres_base + kb * bhalf_bytes, &tmB, bfull0, kb * PBK, nb0);
+        }
+        __syncwarp();
+        cur_nt = ti.nt;
+      }
+      pdl_wait();
+      pdl_trigger();
+      for (; ti.left > 0; ti.next(), ++it) {
         const int mt = ti.mt, nt = ti.nt;
         const int m0 = mt * 256 + int(rank) * PBM, nb0 = nt * g.BN + int(rank) * (g.BN / 2);
         PTRACE(2, it, 0);
@@ -508,6 +520,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       nx0 = load_raw_col<EPI>(p, n0 + lane, ti.left > 0 && quarter == 0);          // the quarter-0 warp fills the group's table
       nx1 = load_raw_col<EPI>(p, n0 + 32 + lane, ti.left > 0 && quarter == 0 && 32 + lane < W);
     }
+    pdl_wait();                // everything above read constants; the residual codes and the output buffer come after the dependency
     uint32_t it = 0;
     int prm_nt = -1;           // column tile whose constants the warp's table holds
     int pending_slot = -1;     // RESID: staging slot whose store has been issued but not yet released to the producer

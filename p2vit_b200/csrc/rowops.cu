@@ -389,8 +389,6 @@ __device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const f
 // (scaling by a power of two commutes with rounding), so the codes equal the generic kernel's bit for bit.
 template <int LPR, int WPLN, bool CLAMP_MID>
 __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_args a) {
-  pdl_wait();
-  pdl_trigger();
   constexpr int GPW = 32 / LPR;                       // rows per warp iteration
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
@@ -428,6 +426,8 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
     gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
     gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
   }
+  pdl_wait();          // the channel constants above are plan-time data; the rows are the previous kernel's output (common.cuh)
+  pdl_trigger();
   for (int row = warp_global * GPW + grp; row < a.rows; row += row_stride) {
     const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
     int xv[WPLN][4];
