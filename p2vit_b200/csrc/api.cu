@@ -27,7 +27,19 @@ static int pdl_mode() {
   }();
   return mode;
 }
-bool pdl_enabled(cudaStream_t stream) {
+static thread_local int t_pdl_kind = PDL_OTHER;
+void pdl_next_kind(int kind) { t_pdl_kind = kind; }
+int pdl_take_kind() {
+  const int k = t_pdl_kind;
+  t_pdl_kind = PDL_OTHER;
+  return k;
+}
+bool pdl_enabled(cudaStream_t stream, int kind) {
+  static const int kinds = [] {
+    const char* e = std::getenv("P2VIT_PDL_KINDS");
+    return e ? std::atoi(e) : (PDL_GEMM | PDL_LAYERNORM);     // measured (tools/ab_pdl_kinds.sh): attention loses 1 % with it, the small kernels gain nothing
+  }();
+  if (!(kinds & kind)) return false;
   const int m = pdl_mode();
   if (m != 2) return m == 1;
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;

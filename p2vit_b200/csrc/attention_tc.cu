@@ -408,6 +408,7 @@ int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
   // power-of-two score multiplier in [2^-20, 2^8]: RMAGIC * (1 - mult) is then exact and so is the fused scaling
   int mexp = 0;
   const bool potm = std::frexp(a.score_mult, &mexp) == 0.5f && mexp >= -19 && mexp <= 9;
+  pdl_next_kind(PDL_ATTENTION);
   if (potm) launch_pdl(attention_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
   else launch_pdl(attention_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
   count_launch();

@@ -31,7 +31,10 @@ int check_launch(const char* what);
 // captured into a CUDA graph (api.cu: pdl_mode; P2VIT_PDL=0 never, =1 always); without it the device instructions are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled(cudaStream_t stream);
+enum { PDL_GEMM = 1, PDL_ATTENTION = 2, PDL_LAYERNORM = 4, PDL_OTHER = 8 };     // P2VIT_PDL_KINDS masks kernel families (experiments)
+bool pdl_enabled(cudaStream_t stream, int kind);
+void pdl_next_kind(int kind);      // family of the next launch_pdl on this thread (reset to PDL_OTHER by the launch)
+int pdl_take_kind();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -41,7 +44,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled(stream) ? 1 : 0;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled(stream, pdl_take_kind()) ? 1 : 0;
   cfg.attrs = at;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);

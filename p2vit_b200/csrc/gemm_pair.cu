@@ -722,6 +722,7 @@ static int launch_pair(const p2v_gemm_args& a, const PairGeom& g, const CUtensor
   }
   const int grid = 2 * std::min(g.tiles, max_pairs());
   EpiParams p = make_epi_params(a);
+  pdl_next_kind(PDL_GEMM);
   launch_pdl(kern, dim3(grid), dim3(P_THREADS), g.smem_bytes, stream, tmA, tmB, tmO, tmR, p, g);
   count_launch();
   return check_launch("gemm_pair");

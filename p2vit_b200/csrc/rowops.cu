@@ -480,6 +480,7 @@ static void launch_ln_pot_c(const p2v_layernorm_args& a, cudaStream_t stream) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_pot_kernel<LPR, WPLN, CLAMP_MID>, 128, 0) != cudaSuccess || occ < 1) occ = 3;
   }
   const int blocks = std::max(1, std::min((a.rows + rows_per_block - 1) / rows_per_block, num_sms() * occ));
+  pdl_next_kind(PDL_LAYERNORM);
   launch_pdl(layernorm_pot_kernel<LPR, WPLN, CLAMP_MID>, dim3(blocks), dim3(128), 0, stream, a);
 }
 template <int LPR, int WPLN>

@@ -33,8 +33,6 @@ __global__ void __launch_bounds__(WA_WARPS * 32) window_attention_kernel(p2v_win
   __shared__ uint32_t sQ[WA_MAXT * DW], sK[WA_MAXT * KSTR], sVt[DH * VSTR], sP[WA_WARPS * 2 * TW];
   __shared__ uint4 sLut[256];          // hi, lo, bits(exp_f32), bits(1 / exp_f32)
   __shared__ int8_t sLab[WA_MAXT];
-  pdl_wait();
-  pdl_trigger();
   const int T = a.T, H = a.H;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t row_bytes = int64_t(3) * H * DH;
@@ -52,6 +50,8 @@ __global__ void __launch_bounds__(WA_WARPS * 32) window_attention_kernel(p2v_win
   uint8_t* bHi = reinterpret_cast<uint8_t*>(pHi);
   uint8_t* bLo = reinterpret_cast<uint8_t*>(pLo);
   constexpr int CH = DH / 16;
+  pdl_wait();          // tables and zero fills above are independent of the previous kernel (common.cuh)
+  pdl_trigger();
 
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int win = unit / H, h = unit % H;
