@@ -391,3 +391,35 @@ def test_uint8_pixels_equal_host_normalised_fp32(golden):
     eng = VitEngine(m, use_graph=False)
     assert torch.equal(eng(x8.cuda(), bits).cpu(), want)
     assert len(set(want.argmax(1).tolist())) > 1
+
+
+@pytest.mark.parametrize("mode,kinds", [("1", "15"), ("0", "15"), ("2", "15")])
+def test_programmatic_dependent_launch_modes_keep_the_logits(golden, mode, kinds):
+    """P2VIT_PDL / P2VIT_PDL_KINDS are read once per process: a child runs DeiT-T through the graph in the always-on, the off and the
+    all-families graph mode; its logits must be this process's (default mode: block GEMMs + LayerNorm inside graphs) bit for bit"""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    g = golden("deit_tiny_minmax")
+    m = _model("deit_tiny", g)
+    x = synth.synth_images(8, seed=21).cuda()
+    bits = [8] * (4 * m.depth + 2)
+    m(x, bits)
+    want = hashlib.sha256(m(x, bits)[0].cpu().numpy().tobytes()).hexdigest()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import hashlib, numpy as np, torch\n"
+        "from p2vit_b200 import Config, build_model, synth\n"
+        "g = np.load('tests/golden/deit_tiny_minmax.npz')\n"
+        "m = build_model('deit_tiny', Config(), seed=int(g['meta.seed']), device='cuda')\n"
+        "m.load_quant_state({k[6:]: g[k] for k in g.files if k.startswith('state/')}); m.model_quant()\n"
+        "x = synth.synth_images(8, seed=21).cuda()\n"
+        "bits = [8] * (4 * m.depth + 2)\n"
+        "hs = {hashlib.sha256(m(x, bits)[0].cpu().numpy().tobytes()).hexdigest() for _ in range(4)}\n"
+        "assert len(hs) == 1, hs\n"
+        "print('sha', hs.pop())\n")
+    env = dict(os.environ, P2VIT_PDL=mode, P2VIT_PDL_KINDS=kinds, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    assert ("sha " + want) in r.stdout, (want, r.stdout[-200:])
