@@ -150,18 +150,7 @@ def make_bit_config(kind, model):
     n = 4 * model.depth + 2
     if kind in ("8", "4"):
         return [int(kind)] * n
-    import random
-    rnd = random.Random(0)
-    flops = model.flops_list()
-    budget = 1.1 * sum(f * 4 for f in flops)
-    while True:
-        cfg = [8]
-        for _ in range(model.depth):
-            a, m = rnd.choice([4, 8]), rnd.choice([4, 8])
-            cfg += [a, a, m, m]
-        cfg.append(rnd.choice([4, 8]))
-        if sum(f * b for f, b in zip(flops, cfg)) <= budget:
-            return cfg
+    return synth.mixed_bit_config(model.flops_list(), model.depth)
 
 
 def main():

@@ -97,7 +97,12 @@ def main():
     ap.add_argument("--taps", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--mixed", action="store_true", help="also store logitsmix for the seeded {4,8} draw of synth.mixed_bit_config "
+                                                         "(test_quant.py:323-341 sampling rule) and the draw itself as bits_mixed")
+    ap.add_argument("--threads", type=int, default=0)
     args = ap.parse_args()
+    if args.threads:
+        torch.set_num_threads(args.threads)
 
     torch.manual_seed(0)
     model, c, synth, ref = build_reference_vit(args.model, args.method, args.seed)
@@ -117,7 +122,7 @@ def main():
                 hooks.append(m.register_forward_hook(lambda mod, i, o, name=name: taps.__setitem__(name, o.detach().clone())))
     t0 = time.time()
     with torch.no_grad():
-        logits8 = model(x, [8] * nb, False)[0]
+        logits8, flops, _ = model(x, [8] * nb, False)
     t_fwd = time.time() - t0
     for h in hooks:
         h.remove()
@@ -125,6 +130,11 @@ def main():
         out["tap8/" + k] = v.numpy().astype(np.float32)
     with torch.no_grad():
         logits4 = model(x, [4] * nb, False)[0]
+    if args.mixed:
+        mixed = synth.mixed_bit_config([int(f) for f in flops], c["depth"])
+        with torch.no_grad():
+            out["logitsmix"] = model(x, mixed, False)[0].numpy()
+        out["bits_mixed"] = np.array(mixed, dtype=np.int64)
     out["logits8"] = logits8.numpy()
     out["logits4"] = logits4.numpy()
     out["meta.model"] = np.array(args.model)

@@ -51,13 +51,20 @@ _LN2 = torch.log(torch.tensor([2.0]))
 
 def round_ln(x, mode=None):
     """floor/ceil/nearest-in-linear-distance power-of-two exponent (minmax.py:50-64)."""
-    y = torch.div(torch.log(x), _LN2)
+    y = torch.div(torch.log(x), _LN2.to(x.device))
     if mode == "ceil":
         return torch.ceil(y)
     y = torch.floor(y)
     if mode == "floor":
         return y
     return torch.gt(x - 2 ** y, 2 ** (y + 1) - x) + y
+
+
+def tdiv(x, c):
+    """x / c as an IEEE division on every backend: torch-CUDA turns `tensor / python_scalar` into a multiplication by the
+    reciprocal (ATen BinaryDivTrueKernel.cu, is_cpu_scalar branch), torch-CPU divides.  The golden vectors come from the
+    reference's CPU run, so the division is the arithmetic to restate; a 0-dim tensor divisor on x's device keeps it one."""
+    return x / torch.tensor(float(c), dtype=x.dtype, device=x.device)
 
 
 def act_shape(x):
@@ -249,7 +256,7 @@ def int_layernorm(x, in_scale, out_scale, weight, bias, exact_sums=False, in_sca
         xd = x_q.double()
         sum_x = xd.sum(dim=-1).float()
         sum_sq = (xd * xd).sum(dim=-1).float()
-        mean = (sum_x / C) * s1
+        mean = tdiv(sum_x, C) * s1
     else:
         sum_x = x_q.sum(dim=-1)
         sum_sq = (x_q ** 2).sum(dim=-1)
@@ -257,8 +264,9 @@ def int_layernorm(x, in_scale, out_scale, weight, bias, exact_sums=False, in_sca
     var = C * sum_sq - sum_x ** 2
     # torch's CPU sqrt goes through MKL VML (<= 1 ulp, not correctly rounded: ~0.1% of inputs differ from IEEE sqrt, which is
     # what torch-CUDA and the kernels compute); the canonical (exact) variant uses the correctly rounded one
-    root = torch.from_numpy(np.sqrt(var.numpy())) if exact_sums else torch.sqrt(var)
-    std = (s1 / C) * root
+    # (on a CUDA device torch.sqrt is the IEEE one already)
+    root = torch.from_numpy(np.sqrt(var.numpy())) if (exact_sums and not var.is_cuda) else torch.sqrt(var)
+    std = tdiv(s1, C) * root
     g = weight.reshape(1, 1, -1)
     A = (s1 / std).unsqueeze(-1) * g / out_scale
     N = torch.clamp(7 - torch.floor(torch.log2(A.abs())), 0, 31)
@@ -302,6 +310,16 @@ def int_softmax_log2(x, s, bits=4, exact_sums=False, codes=None):
 
 def _exact_row_sum_f32(e):
     """Exactly-rounded fp32 of the row sum of integer-valued fp32 numbers (< 2^64)."""
+    if e.is_cuda:
+        # device form: hi / lo 32-bit halves summed in int64, recombined in int64 (needs the total < 2^63), int64 -> fp32 is
+        # round-to-nearest-even (cvt.rn.f32.s64); larger values take the host path below
+        if float(e.max()) * e.shape[-1] < 2.0 ** 62:
+            a = e.double()
+            hi = torch.floor(a / 4294967296.0)
+            lo = a - hi * 4294967296.0
+            tot = (hi.long().sum(dim=-1, keepdim=True) << 32) + lo.long().sum(dim=-1, keepdim=True)
+            return tot.float()
+        return _exact_row_sum_f32(e.cpu()).to(e.device)
     a = e.detach().numpy().astype(np.float64)  # exact: fp32 -> fp64
     hi = np.floor(a / 4294967296.0)
     lo = a - hi * 4294967296.0
@@ -372,8 +390,11 @@ class VitOracle:
     """Functional ViT/DeiT: calibrate() then forward_quant(); state in self.q (name -> quantizer)."""
 
     def __init__(self, sd, embed_dim, depth, num_heads, input_quant=True, method="minmax",
-                 ptf=True, exact_sums=False, patch=16, **_):
-        self.sd = {k: v.float() for k, v in sd.items()}
+                 ptf=True, exact_sums=False, patch=16, device="cpu", **_):
+        # device="cuda": the same restatement evaluated by torch's CUDA backend (SURVEY 8c: IEEE sqrt and CUDA erff instead of
+        # MKL VML sqrt / Sleef erf) - what the -m gpu tests use for strict all-image comparisons with the kernels
+        self.dev = torch.device(device)
+        self.sd = {k: v.float().to(self.dev) for k, v in sd.items()}
         self.D, self.L, self.H, self.P = embed_dim, depth, num_heads, patch
         self.input_quant, self.exact = input_quant, exact_sums
         ln_obs, ln_mode = ("ptf", "channel_wise") if ptf else (method, "layer_wise")
@@ -415,19 +436,17 @@ class VitOracle:
     def load_state(self, st):
         for nm, qq in self.q.items():
             if isinstance(qq, _ActQ):
-                qq.scale = torch.as_tensor(st[nm + ".scale"]).float()
-                qq.zp = torch.as_tensor(st[nm + ".zero_point"]).long()
-                if BITS[qq.bit][2] is True and qq.obs.mode == "layer_wise":
-                    pass
+                qq.scale = torch.as_tensor(st[nm + ".scale"]).float().to(self.dev)
+                qq.zp = torch.as_tensor(st[nm + ".zero_point"]).long().to(self.dev)
             else:
                 for bit in W_BIT_ORDER:
                     k = "%s.scale.%s" % (nm, bit)
                     if k in st:
-                        qq.scale[bit] = torch.as_tensor(st[k]).float()
-                        qq.zp[bit] = torch.as_tensor(st["%s.zero_point.%s" % (nm, bit)]).long()
+                        qq.scale[bit] = torch.as_tensor(st[k]).float().to(self.dev)
+                        qq.zp[bit] = torch.as_tensor(st["%s.zero_point.%s" % (nm, bit)]).long().to(self.dev)
         for k, v in st.items():
             if k.endswith(".channel_scale"):
-                self.cs[k[: -len(".channel_scale")]] = torch.as_tensor(v).float()
+                self.cs[k[: -len(".channel_scale")]] = torch.as_tensor(v).float().to(self.dev)
 
     # ---- shared pieces
     def _ln(self, x, name, eps=1e-6):
@@ -562,6 +581,7 @@ class VitOracle:
         tap = (lambda n, v: taps.__setitem__(n, v.clone())) if taps is not None else (lambda n, v: None)
         wname = lambda b: "int%d" % b
         B = x.shape[0]
+        x = x.to(self.dev)
         if self.input_quant:
             x = q["qact_input"](x)
             tap("qact_input", x)

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .port import BITS, _ActQ, _WeightQ, fake_quant, int_layernorm, int_softmax_log2  # noqa: F401
+from .port import BITS, _ActQ, _WeightQ, fake_quant, int_layernorm, int_softmax_log2, tdiv  # noqa: F401
 
 
 def window_partition(x, ws):
@@ -62,8 +62,9 @@ def shifted_window_mask(H, W, ws, shift):
 
 
 class SwinOracle:
-    def __init__(self, sd, embed_dim, depths, num_heads, method="minmax", exact_sums=False, window=7, patch=4, img=224, **_):
-        self.sd = {k: v.float() for k, v in sd.items()}
+    def __init__(self, sd, embed_dim, depths, num_heads, method="minmax", exact_sums=False, window=7, patch=4, img=224, device="cpu", **_):
+        self.dev = torch.device(device)      # "cuda": same restatement on torch's CUDA backend (see oracle/port.py)
+        self.sd = {k: v.float().to(self.dev) for k, v in sd.items()}
         self.C0, self.depths, self.heads, self.ws, self.P = embed_dim, tuple(depths), tuple(num_heads), window, patch
         self.grid = img // patch
         self.exact = exact_sums
@@ -90,17 +91,17 @@ class SwinOracle:
     def load_state(self, st):
         for nm, qq in self.q.items():
             if isinstance(qq, _ActQ):
-                qq.scale = torch.as_tensor(st[nm + ".scale"]).float()
-                qq.zp = torch.as_tensor(st[nm + ".zero_point"]).long()
+                qq.scale = torch.as_tensor(st[nm + ".scale"]).float().to(self.dev)
+                qq.zp = torch.as_tensor(st[nm + ".zero_point"]).long().to(self.dev)
             else:
                 for bit in ("uint3", "uint4", "int4", "int8"):
                     k = "%s.scale.%s" % (nm, bit)
                     if k in st:
-                        qq.scale[bit] = torch.as_tensor(st[k]).float()
-                        qq.zp[bit] = torch.as_tensor(st["%s.zero_point.%s" % (nm, bit)]).long()
+                        qq.scale[bit] = torch.as_tensor(st[k]).float().to(self.dev)
+                        qq.zp[bit] = torch.as_tensor(st["%s.zero_point.%s" % (nm, bit)]).long().to(self.dev)
         for k, v in st.items():
             if k.endswith(".channel_scale"):
-                self.cs[k[: -len(".channel_scale")]] = torch.as_tensor(v).float()
+                self.cs[k[: -len(".channel_scale")]] = torch.as_tensor(v).float().to(self.dev)
 
     # ---- matmuls: reference fp32 form, or exact integer accumulation (canonical)
     def _lin(self, h, aq, wq, w, bias):
@@ -127,7 +128,7 @@ class SwinOracle:
         qh, kh, vh = qkv[0], qkv[1], qkv[2]
         q1, qa1, qa2, qa3 = q[p + "attn.qact1"], q[p + "attn.qact_attn1"], q[p + "attn.qact2"], q[p + "attn.qact3"]
         table = q[p + "attn.qact_table"](sd[p + "attn.relative_position_bias_table"])
-        bias = table[self.rpi.view(-1)].view(N, N, -1).permute(2, 0, 1).contiguous()
+        bias = table[self.rpi.view(-1).to(self.dev)].view(N, N, -1).permute(2, 0, 1).contiguous()
         if self.exact:
             cq, ck, cv = (torch.round(t / q1.scale.reshape(())).double() for t in (qh, kh, vh))
             S = (cq @ ck.transpose(-2, -1)).float()
@@ -140,6 +141,7 @@ class SwinOracle:
         tap(p + "attn.qact2", a)
         codes = torch.round(a / qa2.scale.reshape(()))
         if mask is not None:
+            mask = mask.to(self.dev)
             nW = mask.shape[0]
             a = (a.view(B_ // nW, nW, heads, N, N) + mask.unsqueeze(1).unsqueeze(0)).view(-1, heads, N, N)
             codes = (codes.view(B_ // nW, nW, heads, N, N) + torch.round(mask / qa2.scale.reshape(())).unsqueeze(1).unsqueeze(0)).view(-1, heads, N, N)
@@ -161,7 +163,7 @@ class SwinOracle:
         q, sd, ws = self.q, self.sd, self.ws
         tap = (lambda n, v: taps.__setitem__(n, v.clone())) if taps is not None else (lambda n, v: None)
         B = x.shape[0]
-        x = q["qact_input"](x)
+        x = q["qact_input"](x.to(self.dev))
         tap("qact_input", x)
         if self.exact:
             P, gs = self.P, self.grid
@@ -222,7 +224,7 @@ class SwinOracle:
         tap("qact2", x)
         if self.exact:   # mean of the codes: exact integer sum, one fp32 product and one fp32 division
             s = q["qact2"].scale.reshape(())
-            x = (torch.round(x / s).double().sum(1).float() * s) / float(x.shape[1])
+            x = tdiv(torch.round(x / s).double().sum(1).float() * s, x.shape[1])
         else:
             x = F.adaptive_avg_pool1d(x.transpose(1, 2), 1).flatten(1)
         x = q["qact3"](x)

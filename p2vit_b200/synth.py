@@ -16,7 +16,7 @@ import zlib
 import numpy as np
 import torch
 
-__all__ = ["VIT_CONFIGS", "SWIN_CONFIGS", "synth_vit_state_dict", "synth_swin_state_dict", "synth_images"]
+__all__ = ["VIT_CONFIGS", "SWIN_CONFIGS", "synth_vit_state_dict", "synth_swin_state_dict", "synth_images", "mixed_bit_config"]
 
 # name -> dict(embed_dim, depth, num_heads, input_quant)      vit_fquant.py:942-1074
 VIT_CONFIGS = {
@@ -136,3 +136,20 @@ def synth_images(batch, seed=0, start=0, size=224):
         coarse = g.standard_normal(size=(3, cells, cells), dtype=np.float32)
         out[i] = np.float32(0.6) * noise + np.float32(0.8) * np.kron(coarse, np.ones((16, 16), np.float32))
     return torch.from_numpy(out)
+
+
+def mixed_bit_config(flops, depth, seed=0):
+    """A 1 + 4*depth + 1 entry {4,8} bit_config drawn by the sampling rule of the reference's search (test_quant.py:323-341):
+    first layer 8 bit, the attention pair and the MLP pair of a block share a width, sum(MACs_i * bits_i) <= 1.1 * sum(MACs_i * 4).
+    `flops` = the per-layer MAC list the forward returns.  ViT-L (depth 24) gives the 98-entry config of BASELINE config C5."""
+    import random
+    rnd = random.Random(seed)
+    budget = 1.1 * sum(f * 4 for f in flops)
+    while True:
+        cfg = [8]
+        for _ in range(depth):
+            a, m = rnd.choice([4, 8]), rnd.choice([4, 8])
+            cfg += [a, a, m, m]
+        cfg.append(rnd.choice([4, 8]))
+        if sum(f * b for f, b in zip(flops, cfg)) <= budget:
+            return cfg

@@ -160,16 +160,99 @@ def test_per_op_parity_at_model_scale(golden, name, wbits, B):
     assert all(v[1] <= 1 for v in gelu) and tot / n < 1e-5, "GELU epilogue: %d of %d codes differ" % (tot, n)
 
 
-def test_deit_tiny_end_to_end_vs_reference_golden(golden):
-    """End to end the only admissible differences are tie flips (GELU erf ulp: the reference's CPU GELU uses Sleef's erf),
-    but this synthetic random-weight network amplifies a single flipped code to the whole image within a few blocks, so the
-    check is: most images bit-identical to the reference's logits, the rest explained by test_per_op_parity_at_model_scale."""
-    g = golden("deit_tiny_minmax")
-    m = _model("deit_tiny", g)
-    x = synth.synth_images(int(g["meta.eval"]), seed=1).cuda()
-    got = m(x, [8] * 50)[0].cpu().numpy()
-    same = (got == g["logits8"]).all(axis=1)
-    assert same.mean() >= 0.5, "only %d of %d images are bit-identical to the reference" % (same.sum(), same.size)
+def _engine_vs_cuda_oracle(m, o, st, x, bits):
+    """free-running comparison (no teacher forcing): every engine step's int8 buffer against the oracle's tap of the same
+    run, then the logits.  Returns ({step: mismatches}, engine logits, oracle logits) - all on the CPU."""
+    taps, ref_taps = {}, {}
+    ref = o.forward_quant(x, bits, ref_taps).cpu()
+    got = VitEngine(m, use_graph=False)(x.cuda(), bits, taps=taps).cpu()
+    B, D = x.shape[0], m.embed_dim
+    pairs = [("cls", "qact1", "qact1.scale")]
+    for i in range(m.depth):
+        p = "blocks.%d." % i
+        pairs += [(p + "norm1", p + "attn.qact0", p + "attn.qact0.scale"), (p + "attn.qact1", p + "attn.qact1", p + "attn.qact1.scale"),
+                  (p + "attn.qact2", p + "attn.qact2", p + "attn.qact2.scale"), (p + "qact2", p + "qact2", p + "qact2.scale"),
+                  (p + "norm2", p + "mlp.qact0", p + "mlp.qact0.scale"), (p + "mlp.qact1", p + "mlp.qact1", p + "mlp.qact1.scale"),
+                  (p + "qact4", p + "qact4", p + "qact4.scale")]
+    pairs.append(("qact2", "qact2", "qact2.scale"))
+    rep = {}
+    for step, tap, sk in pairs:
+        r = ref_taps[tap]
+        sc = torch.as_tensor(st[sk]).to(r.device).reshape(*([1] * (r.dim() - 1)), -1)
+        zk = sk[:-len("scale")] + "zero_point"
+        zp = torch.as_tensor(st[zk]).to(r.device).reshape(*([1] * (r.dim() - 1)), -1) if zk in st else 0
+        rc = (torch.round(r / sc) + zp).to(torch.int64)
+        gc = taps[step].reshape(rc.shape).to(torch.int64)
+        rep[step] = int((gc != rc).sum())
+    return rep, got, ref
+
+
+@pytest.mark.parametrize("name,B,wbits", [("deit_tiny", 8, 8), ("deit_small", 8, 8), ("deit_small", 8, 4), ("deit_tiny", 32, 8)])
+def test_model_scale_strict_parity_vs_cuda_oracle(golden, name, B, wbits):
+    """The strict model-scale bar (north_star: codes bit-exact, top-1 identical): DeiT-Tiny / DeiT-Small with the
+    reference-calibrated state, free running over the whole network against the oracle evaluated by torch's CUDA backend
+    (same erff and IEEE sqrt as the kernels, so no backend-dependent rounding tie is left).  EVERY step's codes,
+    EVERY logit of EVERY image and top-1 must be identical."""
+    g = golden(name + "_minmax")
+    st = _state(g)
+    c = synth.VIT_CONFIGS[name]
+    o = VitOracle(synth.synth_vit_state_dict(**c, seed=0), **c, exact_sums=True, device="cuda")
+    o.load_state(st)
+    m = _model(name, g)
+    x = synth.synth_images(B, seed=1)
+    bits = [wbits] * (4 * c["depth"] + 2)
+    rep, got, ref = _engine_vs_cuda_oracle(m, o, st, x, bits)
+    bad = {k: v for k, v in rep.items() if v}
+    assert not bad, "engine steps differ from the CUDA-evaluated oracle: %s" % bad
+    assert torch.equal(got, ref), "%d logits differ" % int((got != ref).sum())
+    assert torch.equal(got.argmax(1), ref.argmax(1))
+    assert torch.equal(m(x.cuda(), bits)[0].cpu(), ref), "graph path differs"
+    assert len(set(ref.argmax(1).tolist())) > 1, "top-1 must depend on the image for the check to mean anything"
+
+
+@pytest.mark.parametrize("name", ["deit_tiny", "deit_small"])
+def test_end_to_end_vs_reference_golden_logits(golden, name):
+    """Second, documented bound: the logits of the UNMODIFIED reference as run on the build container's CPU
+    (tests/golden/<name>_minmax.npz).  The same algorithm evaluated by another backend differs from that run in exactly one
+    place: erf (Sleef on the CPU, CUDA erff in the kernels and in torch-CUDA; they disagree in the last bit on a third of all
+    arguments, tools/diag_backend.py), which matters when GELU's output lands on a rounding tie of mlp.qact1.  These
+    random-weight networks amplify one flipped code to the whole image, so an image either reproduces the reference's logits
+    bit for bit or diverges completely.  Asserted here, per image, against the CPU oracle's free-running taps (the CPU oracle
+    reproduces the golden logits bit for bit: tests/test_oracle_golden.py): the FIRST step at which the kernels leave the
+    reference's trajectory is a GELU step, there by one LSB in a handful of codes - and nothing else ever differs first.
+    Kernels == reference algorithm on the CUDA backend for every image is test_model_scale_strict_parity_vs_cuda_oracle."""
+    g = golden(name + "_minmax")
+    st = _state(g)
+    m = _model(name, g)
+    c = synth.VIT_CONFIGS[name]
+    B = int(g["meta.eval"])
+    x = synth.synth_images(B, seed=1)
+    bits = [8] * (4 * c["depth"] + 2)
+    o = VitOracle(synth.synth_vit_state_dict(**c, seed=0), **c, exact_sums=True)
+    o.load_state(st)
+    ref_taps, taps = {}, {}
+    ref = o.forward_quant(x, bits, ref_taps)
+    assert np.array_equal(ref.numpy(), g["logits8"]), "the CPU oracle must reproduce the reference's own logits"
+    got = VitEngine(m, use_graph=False)(x.cuda(), bits, taps=taps).cpu()
+    order = [("cls", "qact1")]
+    for i in range(m.depth):
+        p = "blocks.%d." % i
+        order += [(p + "norm1", p + "attn.qact0"), (p + "attn.qact1", p + "attn.qact1"), (p + "attn.qact2", p + "attn.qact2"),
+                  (p + "qact2", p + "qact2"), (p + "norm2", p + "mlp.qact0"), (p + "mlp.qact1", p + "mlp.qact1"), (p + "qact4", p + "qact4")]
+    first = {}
+    for step, tap in order:
+        r = ref_taps[tap]
+        rc = torch.round(r / torch.as_tensor(st[tap + ".scale"]).reshape(1, 1, -1)).to(torch.int64)
+        d = (taps[step].cpu().reshape(rc.shape).to(torch.int64) - rc).abs().reshape(B, -1)
+        for b in range(B):
+            if b not in first and int(d[b].max()) > 0:
+                first[b] = (step, int(d[b].max()), int((d[b] > 0).sum()))
+    same = (got == ref).all(dim=1)
+    assert set(first) == {b for b in range(B) if not bool(same[b])}, (first, same)
+    for b, (step, mx, n) in first.items():
+        assert step.endswith("mlp.qact1") and mx == 1 and n <= 8, "image %d leaves the reference trajectory at %s (%d codes, max %d LSB)" % (b, step, n, mx)
+    assert int(same.sum()) >= B // 2
+    print("%s: %d of %d images bit-identical to the reference-on-CPU logits; first divergences: %s" % (name, int(same.sum()), B, first))
 
 
 def test_graph_replay_and_simt_cross_check(golden):
