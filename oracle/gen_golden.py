@@ -143,6 +143,7 @@ def main():
     out["meta.calib"] = np.array(args.calib)
     out["meta.eval"] = np.array(args.eval)
     out["meta.torch"] = np.array(torch.__version__)
+    out["meta.threads"] = np.array(torch.get_num_threads())   # the reference's fp32 reductions depend on it (tests pin it)
     out["meta.ref_calib_seconds"] = np.array(t_cal, dtype=np.float32)
     out["meta.ref_fwd_seconds"] = np.array(t_fwd, dtype=np.float32)
     path = args.out or os.path.join(ROOT, "tests", "golden", "%s_%s.npz" % (args.model, args.method))
