@@ -49,6 +49,18 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def int8_peaks():
+    """dense INT8 tensor throughput measured on this pool's B200s (tools/int8_peak.py: cuBLASLt int8 x int8 -> int32 at 8192^3 /
+    16384 x 8192^2 through torch._int_mm; committed as profiles/int8_peak.json): (burst TOP/s for a kernel timed alone, sustained
+    TOP/s for a seconds-long loop, source).  MEASURED_PEAKS.json has no int8 figure; without the file: 2 x the bf16 numbers."""
+    p = os.path.join(ROOT, "profiles", "int8_peak.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["int8_tops_burst"]), float(d["int8_tops_sustained"]), "measured cuBLASLt int8 GEMM (profiles/int8_peak.json)"
+    _, bf, bfs, src = peaks()
+    return 2.0 * bf, 2.0 * bfs, "2 x %s bf16 cuBLAS (no int8 measurement found)" % src
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -111,7 +123,8 @@ def bind_to_gpu_numa_node(index):
 
 
 def cpu_reference_run(name, batch, steps, warmup, threads=None):
-    """the reference's algorithm (oracle/port.py, fp32 fake-quant, torch CPU ops) on the host cores."""
+    """the reference's algorithm (oracle/port.py, fp32 fake-quant, torch CPU ops) on the host cores: BASELINE.md section 3 -
+    all host threads, warm-up, then the BEST of `steps` forwards of `batch` images (W8A8)."""
     from oracle.port import VitOracle
 
     torch.set_num_threads(threads or os.cpu_count())
@@ -129,11 +142,23 @@ def cpu_reference_run(name, batch, steps, warmup, threads=None):
     bits = [8] * (4 * c["depth"] + 2)
     for _ in range(warmup):
         o.forward_quant(x, bits)
-    t0 = time.time()
+    best = None
     for _ in range(steps):
+        t0 = time.time()
         out = o.forward_quant(x, bits)
-    dt = time.time() - t0
-    return batch * steps / dt, dt / steps, torch.get_num_threads(), calib_s, out
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    return batch / best, best, torch.get_num_threads(), calib_s, out
+
+
+def state_sha16(model):
+    """fingerprint of the frozen quantizer state (every rank of a multi-GPU calibration must freeze the same one)"""
+    import hashlib
+    h = hashlib.sha256()
+    for k, v in sorted(model.export_quant_state().items()):
+        h.update(k.encode())
+        h.update(v.contiguous().numpy().tobytes())
+    return h.hexdigest()[:16]
 
 
 def load_state(name):

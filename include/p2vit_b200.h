@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define P2V_ABI_VERSION 1
+#define P2V_ABI_VERSION 2
 
 int p2v_abi_version(void);
 const char* p2v_last_error(void);
@@ -102,6 +102,14 @@ typedef struct {
                                reverse + inverse cyclic shift fused into the store (swin_quant.py:426-436) */
   int pot_scales;           /* REQUANT/GELU/DEQUANT: 1 = acc_scale and out_scale are exact powers of two (division == exact
                                multiply); RESIDUAL: 1 = acc_scale is (acc*acc_scale exact; mid/out scales stay general) */
+  /* Zero points of asymmetric activation quantizers (observer/omse.py:30-57, quantizer/uniform.py:83-86,125; integer valued,
+   * within [-128,127]; all 0 for the symmetric observers).  The INPUT zero point enters through zp_corr.  With a zero point the
+   * output code is  sat(RNE(fl(fl(y / scale) + zp)))  and a dequantized value is  fl((code - zp) * scale):
+   *   out_zp  REQUANT / GELU / DEQUANT: zero point of the output QAct
+   *   mid_zp  EMBED: zero point of patch_embed.qact        aux_zp  EMBED: zero point of qact_embed
+   * (RESIDUAL's mid / out quantizers and EMBED's out quantizer are the channel-wise PTF ones: symmetric by construction,
+   * ptf.py:120).  Non-zero values need pot_scales = 0 and run on csrc/gemm_tc.cu. */
+  float out_zp, mid_zp, aux_zp;
 } p2v_gemm_args;
 
 /* Step table of  y -> sat(RNE(gelu_erf(y) / out_scale))  for a power-of-two out_scale (layers_quant.py:373-375).  The
@@ -123,7 +131,7 @@ int p2v_build_gelu_table(float out_scale, void* table_dev, void* stream);
 
 int p2v_gemm_i8(const p2v_gemm_args* args_host, void* stream);
 /* Two tcgen05 kernels implement p2v_gemm_i8 with identical results: csrc/gemm_pair.cu (CTA pairs, cta_group::2, TMA-staged
- * output; REQUANT / GELU / RESIDUAL with int8 output, N % 16 == 0, no row_map / zp_corr) and csrc/gemm_tc.cu (everything
+ * output; REQUANT / GELU / RESIDUAL with int8 output, N % 16 == 0, no row_map / zero points) and csrc/gemm_tc.cu (everything
  * else and small M).  variant: 0 = automatic (default), 1 = always gemm_tc.cu, 2 = gemm_pair.cu whenever it applies
  * (tests cross-check the two). Process-wide, not thread safe. */
 void p2v_set_gemm_variant(int variant);
@@ -158,6 +166,8 @@ typedef struct {
                                  fused into the store (swin_quant.py:408-419) */
   int clamp_mid;            /* 1: y_q is clamped to [-128,127] first - a QAct at the LayerNorm's own output scale sits between the
                                LayerNorm and the smoothing divide (Swin: norm2 -> qact3 -> Mlp, swin_quant.py:439-446) */
+  float next_zp;            /* zero point of the QAct after the LN (0 unless its observer is asymmetric; needs pot_scales = 0):
+                               out_i8 = sat(RNE(fl(fl(fl(y_q*out_scale[c]) / post_div[c]) / next_scale) + next_zp)) */
 } p2v_layernorm_args;
 
 int p2v_layernorm_int(const p2v_layernorm_args* args_host, void* stream);
@@ -197,6 +207,11 @@ typedef struct {
   const p2v_softmax_lut* lut_dev;
   uint8_t* probs_or_null;   /* optional dump of softmax codes [B,H,T,T] (tests) */
   int8_t* scores_or_null;   /* optional dump of qact_attn1 codes [B,H,T,T] (tests) */
+  /* asymmetric qact1 / qact_attn1 / qact2 (omse): S = sum_d (q - zp_qkv)(k - zp_qkv);  c = sat(RNE(fl(S*score_mult) + zp_score));
+   * the softmax works on c (a zero point cancels in x - rowmax);  O = sum_j 2^(15-code_j) (v_j - zp_qkv);
+   * out_i8 = sat(RNE(fl(O*out_mult) + zp_out)).  All integer valued; 0 for symmetric observers. */
+  int zp_qkv;
+  float zp_score, zp_out;
 } p2v_attention_args;
 
 /* Head dim 64, T <= 224 and no debug dumps: tcgen05 kernel (csrc/attention_tc.cu: TMA-fed S = q k^T and O = P v on
@@ -249,13 +264,31 @@ int p2v_avgpool_quant_i8(const int8_t* in, int8_t* out, int B, int T, int C, flo
  * (`inner` as in p2v_quantize_f32).  minmax: float [2,C] (row 0 = min, row 1 = max),
  * initialised by the kernel (not accumulated).
  * ------------------------------------------------------------------------------------------- */
-int p2v_minmax_per_channel(const float* x, float* minmax, int64_t n, int C, int64_t inner, void* stream);
+/* `scratch`: caller-owned device buffer of at least p2v_minmax_scratch_bytes(...) bytes (block partials; the library holds
+ * no device memory of its own, so concurrent streams cannot collide on it) */
+int64_t p2v_minmax_scratch_bytes(int64_t n, int C, int64_t inner);
+int p2v_minmax_per_channel(const float* x, float* minmax, int64_t n, int C, int64_t inner, float* scratch, void* stream);
 /* sum over all elements of (x - fq_k(x))^2 for K candidate scales (minmax.py:165-201 activation case,
  * omse.py:30-57, ptf.py:123-149): scales [K, n_scale]; out double [K, n_scale_out] where
- * n_scale_out = C if per_channel_out else 1.  fq_k(x) = (sat_lo_hi(RNE(x/s + zp_k)) - zp_k) * s. */
+ * n_scale_out = C if per_channel_out else 1.  fq_k(x) = (sat_lo_hi(RNE(x/s + zp_k)) - zp_k) * s.
+ * Block partials go to `scratch` (>= p2v_quant_mse_scratch_bytes(...) bytes) and are folded in a fixed order: the scores are
+ * bit-reproducible, so the argmin of near-tied candidates is too. */
+int64_t p2v_quant_mse_scratch_bytes(int64_t n, int C, int64_t inner, int K, int per_channel_out);
 int p2v_quant_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales,
                          const float* zps_or_null, int K, int n_scale, int per_channel_out,
-                         int lo, int hi, double* out, void* stream);
+                         int lo, int hi, double* out, double* scratch, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Percentile observer                                              (observer/percentile.py:26-55)
+ * One pass of a most-significant-digit radix select over the order-preserving integer image of fp32
+ * (key = bits ^ 0x80000000 for non-negative values, ~bits for negative ones): among the elements whose key
+ * satisfies (key & prefix_mask) == prefix_value, hist[(key >> shift) & (2^nbits - 1)] += 1.  `hist` holds 2^nbits
+ * unsigned 64-bit counters and is ACCUMULATED into (the caller zeroes it).  Integer counts add exactly across the
+ * ranks of a data-parallel calibration (all-reduce SUM), so three passes (12 + 12 + 8 bits) give the global k-th
+ * smallest element - what torch.quantile / np.percentile sort for in the reference - bit for bit, with no sort.
+ * ------------------------------------------------------------------------------------------- */
+int p2v_radix_hist_f32(const float* x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value, int shift, int nbits,
+                       unsigned long long* hist, void* stream);
 
 #ifdef __cplusplus
 }

@@ -476,8 +476,9 @@ class VitOracle:
     def _lin(self, h, aq, wq, w, bit, bias):
         w_hat = wq.fq(w, bit)
         wm = w_hat.reshape(w.shape[0], -1)
-        if not self.exact or aq is None or aq.scale.numel() != 1 or bool((aq.zp != 0).any()):
+        if not self.exact or aq is None or aq.scale.numel() != 1:
             return F.linear(h, wm, bias)
+        # (with a zero point, round(h / s) is the centred code q - zp: the accumulation below is sum_k (q - zp) w, exact)
         ws = wq.scale[bit].reshape(-1, 1).float()
         wc = torch.round(wm / ws)
         acc = (self._codes(h, aq).double() @ wc.double().T).float()
@@ -489,8 +490,7 @@ class VitOracle:
         """h: dequantized qkv (attn.qact1 output) -> dequantized attn.qact2 output, plus the score / probability taps"""
         dh = self.D // self.H
         qh, kh, vh = self._heads(h)
-        canonical = self.exact and not bool((q1.zp != 0).any() or (qs.zp != 0).any() or (q2.zp != 0).any())
-        if not canonical:
+        if not self.exact:
             a = qs((qh @ kh.transpose(-2, -1)) * dh ** -0.5)
             p = int_softmax_log2(a, qs.scale, 4, self.exact)
             return a, p, q2((p @ vh).transpose(1, 2).reshape(B, -1, self.D))
@@ -498,13 +498,16 @@ class VitOracle:
         cq, ck, cv = (torch.round(t / q1.scale.reshape(())).double() for t in (qh, kh, vh))
         S = (cq @ ck.transpose(-2, -1)).float()
         mult = (s1 * s1 * dh ** -0.5 / sa).float()
-        ca = torch.clamp(torch.round(S * mult), -128, 127)
-        a = ca * qs.scale.reshape(())
+        # zero points (asymmetric observers; all 0 otherwise): cq / ck / cv are the centred codes q - zp, the score code is
+        # clamp(RNE(fl(fl(S * mult) + zp_s))), the softmax works on the codes (a zero point cancels in x - rowmax)
+        zs, z2 = qs.zp.reshape(()).float(), q2.zp.reshape(()).float()
+        ca = torch.clamp(torch.round(S * mult + zs), -128, 127)
+        a = (ca - zs) * qs.scale.reshape(())
         p = int_softmax_log2(a, qs.scale, 4, True, codes=ca)
         O = ((p.double() * 32768.0) @ cv).float()
         omult = (s1 / s2 / 32768.0).float()
-        c2 = torch.clamp(torch.round(O * omult), -128, 127)
-        return a, p, (c2 * q2.scale.reshape(())).transpose(1, 2).reshape(B, -1, self.D)
+        c2 = torch.clamp(torch.round(O * omult + z2), -128, 127)
+        return a, p, ((c2 - z2) * q2.scale.reshape(())).transpose(1, 2).reshape(B, -1, self.D)
 
     # ---- calibration forward (FP values + observers), test_quant.py:275-312
     @torch.no_grad()

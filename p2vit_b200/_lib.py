@@ -27,6 +27,7 @@ class GemmArgs(C.Structure):
         ("out_i8", C.c_void_p), ("out_f32", C.c_void_p),
         ("gelu_table", C.c_void_p), ("row_map", C.c_void_p),
         ("pot_scales", C.c_int),
+        ("out_zp", C.c_float), ("mid_zp", C.c_float), ("aux_zp", C.c_float),
     ]
 
 
@@ -39,7 +40,7 @@ class LayerNormArgs(C.Structure):
         ("out_scale", C.c_void_p), ("post_div", C.c_void_p),
         ("next_scale", C.c_float), ("pot_scales", C.c_int),
         ("out_i8", C.c_void_p), ("out_f32", C.c_void_p),
-        ("out_row_map", C.c_void_p), ("clamp_mid", C.c_int),
+        ("out_row_map", C.c_void_p), ("clamp_mid", C.c_int), ("next_zp", C.c_float),
     ]
 
 
@@ -60,6 +61,7 @@ class AttentionArgs(C.Structure):
         ("score_mult", C.c_float), ("out_mult", C.c_float),
         ("lut_dev", C.c_void_p),
         ("probs_or_null", C.c_void_p), ("scores_or_null", C.c_void_p),
+        ("zp_qkv", C.c_int), ("zp_score", C.c_float), ("zp_out", C.c_float),
     ]
 
 
@@ -87,8 +89,11 @@ SYMBOLS = {
     "p2v_window_attention_i8": (_I, [C.POINTER(WindowAttentionArgs), _P]),
     "p2v_gather_rows_i8": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "p2v_avgpool_quant_i8": (_I, [_P, _P, _I, _I, _I, _F, _F, _P]),
-    "p2v_minmax_per_channel": (_I, [_P, _P, _I64, _I, _I64, _P]),
-    "p2v_quant_mse_scores": (_I, [_P, _I64, _I, _I64, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "p2v_minmax_scratch_bytes": (_I64, [_I64, _I, _I64]),
+    "p2v_minmax_per_channel": (_I, [_P, _P, _I64, _I, _I64, _P, _P]),
+    "p2v_quant_mse_scratch_bytes": (_I64, [_I64, _I, _I64, _I, _I]),
+    "p2v_quant_mse_scores": (_I, [_P, _I64, _I, _I64, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "p2v_radix_hist_f32": (_I, [_P, _I64, C.c_uint32, C.c_uint32, _I, _I, _P, _P]),
 }
 
 _lib = None
@@ -107,7 +112,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library diverge
         fn.restype, fn.argtypes = res, args
-    if lib.p2v_abi_version() != 1:
+    if lib.p2v_abi_version() != 2:
         raise RuntimeError("p2vit_b200: ABI version mismatch")
     _lib = lib
     return lib

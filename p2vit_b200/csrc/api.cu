@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <atomic>
 #include "common.cuh"
 
@@ -76,9 +77,13 @@ bool attention_tc_supported(const p2v_attention_args& a);
 int launch_window_attention(const p2v_window_attention_args& a, uint32_t e_mask, cudaStream_t stream);
 int launch_gather_rows(const int8_t* in, int8_t* out, const int32_t* src, int rows_out, int segs, int C, cudaStream_t stream);
 int launch_avgpool_quant(const int8_t* in, int8_t* out, int B, int T, int C, float s_in, float s_out, cudaStream_t stream);
-int launch_minmax(const float* x, float* minmax, int64_t n, int C, int64_t inner, cudaStream_t stream);
+int launch_minmax(const float* x, float* minmax, int64_t n, int C, int64_t inner, float* part, cudaStream_t stream);
+int64_t minmax_scratch_bytes(int64_t n, int C, int64_t inner);
 int launch_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales, const float* zps, int K, int n_scale,
-                      int per_channel_out, int lo, int hi, double* out, cudaStream_t stream);
+                      int per_channel_out, int lo, int hi, double* out, double* part, cudaStream_t stream);
+int64_t mse_scratch_bytes(int64_t n, int C, int64_t inner, int K, int per_channel_out);
+int launch_radix_hist(const float* x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value, int shift, int nbits,
+                      unsigned long long* hist, cudaStream_t stream);
 
 static int validate_gemm(const p2v_gemm_args* a) {
   P2V_REQUIRE(a != nullptr, "gemm: null args");
@@ -93,6 +98,12 @@ static int validate_gemm(const p2v_gemm_args* a) {
   if (e == P2V_EPI_F32 || e == P2V_EPI_DEQUANT) P2V_REQUIRE(a->out_f32 != nullptr, "gemm: out_f32 required");
   else P2V_REQUIRE(a->out_i8 != nullptr, "gemm: out_i8 required");
   if (e == P2V_EPI_RESIDUAL) P2V_REQUIRE(a->mid_scale && a->res_scale && a->res, "gemm: residual epilogue needs mid_scale, res_scale, res");
+  if (a->out_zp != 0.f || a->mid_zp != 0.f || a->aux_zp != 0.f) {
+    P2V_REQUIRE(!a->pot_scales, "gemm: zero points need the general epilogues (pot_scales = 0)");
+    P2V_REQUIRE(e != P2V_EPI_RESIDUAL && e != P2V_EPI_F32, "gemm: this epilogue's quantizers are symmetric (no zero point)");
+    P2V_REQUIRE(a->out_zp == rintf(a->out_zp) && a->mid_zp == rintf(a->mid_zp) && a->aux_zp == rintf(a->aux_zp) && fabsf(a->out_zp) <= 128.f &&
+                fabsf(a->mid_zp) <= 128.f && fabsf(a->aux_zp) <= 128.f, "gemm: zero points must be integers within [-128,127]");
+  }
   if (e == P2V_EPI_EMBED) P2V_REQUIRE(a->mid_scale && a->pos && a->tokens_per_image > 0 && a->M % a->tokens_per_image == 0,
                                       "gemm: embed epilogue needs mid_scale, pos and M %% tokens_per_image == 0");
   return 0;
@@ -160,6 +171,7 @@ int p2v_layernorm_int(const p2v_layernorm_args* a, void* stream) {
   P2V_REQUIRE(a->rows > 0 && a->C > 0 && a->C % 4 == 0 && a->C <= 4096, "layernorm: C=%d must be a multiple of 4, <= 4096", a->C);
   P2V_REQUIRE(a->out_i8 || a->out_f32, "layernorm: no output");
   P2V_REQUIRE(a->x_row_stride % 4 == 0, "layernorm: row stride must be a multiple of 4 bytes");
+  P2V_REQUIRE(a->next_zp == 0.f || !a->pot_scales, "layernorm: a zero point needs the general kernel (pot_scales = 0)");
   return launch_layernorm(*a, (cudaStream_t)stream);
 }
 int p2v_int_softmax_log2(const int8_t* scores, uint8_t* out, int64_t rows, int n, const p2v_softmax_lut* lut, void* stream) {
@@ -198,15 +210,29 @@ int p2v_avgpool_quant_i8(const int8_t* in, int8_t* out, int B, int T, int C, flo
   P2V_REQUIRE(in && out && B > 0 && T > 0 && C > 0 && s_in > 0.f && s_out > 0.f, "avgpool_quant: bad arguments");
   return launch_avgpool_quant(in, out, B, T, C, s_in, s_out, (cudaStream_t)stream);
 }
-int p2v_minmax_per_channel(const float* x, float* minmax, int64_t n, int C, int64_t inner, void* stream) {
-  P2V_REQUIRE(x && minmax && n > 0 && C > 0 && inner > 0 && n % (int64_t(C) * inner) == 0, "minmax: bad arguments");
-  return launch_minmax(x, minmax, n, C, inner, (cudaStream_t)stream);
+int64_t p2v_minmax_scratch_bytes(int64_t n, int C, int64_t inner) {
+  if (n <= 0 || C <= 0 || inner <= 0) return 0;
+  return minmax_scratch_bytes(n, C, inner);
+}
+int p2v_minmax_per_channel(const float* x, float* minmax, int64_t n, int C, int64_t inner, float* scratch, void* stream) {
+  P2V_REQUIRE(x && minmax && scratch && n > 0 && C > 0 && inner > 0 && n % (int64_t(C) * inner) == 0, "minmax: bad arguments");
+  return launch_minmax(x, minmax, n, C, inner, scratch, (cudaStream_t)stream);
+}
+int64_t p2v_quant_mse_scratch_bytes(int64_t n, int C, int64_t inner, int K, int per_channel_out) {
+  if (n <= 0 || C <= 0 || inner <= 0 || K <= 0) return 0;
+  return mse_scratch_bytes(n, C, inner, K, per_channel_out);
 }
 int p2v_quant_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales, const float* zps, int K,
-                         int n_scale, int per_channel_out, int lo, int hi, double* out, void* stream) {
-  P2V_REQUIRE(x && scales && out && n > 0 && C > 0 && inner > 0 && K > 0 && K <= 96, "mse_scores: bad arguments (K <= 96)");
+                         int n_scale, int per_channel_out, int lo, int hi, double* out, double* scratch, void* stream) {
+  P2V_REQUIRE(x && scales && out && scratch && n > 0 && C > 0 && inner > 0 && K > 0 && K <= 96, "mse_scores: bad arguments (K <= 96)");
   P2V_REQUIRE(n_scale == 1 || n_scale == C, "mse_scores: n_scale must be 1 or C");
-  return launch_mse_scores(x, n, C, inner, scales, zps, K, n_scale, per_channel_out, lo, hi, out, (cudaStream_t)stream);
+  return launch_mse_scores(x, n, C, inner, scales, zps, K, n_scale, per_channel_out, lo, hi, out, scratch, (cudaStream_t)stream);
+}
+int p2v_radix_hist_f32(const float* x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value, int shift, int nbits,
+                       unsigned long long* hist, void* stream) {
+  P2V_REQUIRE(x && hist && n > 0 && nbits >= 1 && nbits <= 12 && shift >= 0 && shift + nbits <= 32, "radix_hist: bad arguments");
+  P2V_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "radix_hist: x must be 16-byte aligned");
+  return launch_radix_hist(x, n, prefix_mask, prefix_value, shift, nbits, hist, (cudaStream_t)stream);
 }
 
 }  // extern "C"

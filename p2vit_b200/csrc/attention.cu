@@ -68,16 +68,27 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(p2v_atte
     int code[NJ];
     int mx = -128;
     const uint32_t* qi = sQ + i * DW;
+    // asymmetric qact1 (zp_qkv = z): sum (q - z)(k - z) = q.k - z (sum q + sum k) + DH z^2
+    const int z = a.zp_qkv;
+    int sq = 0;
+    if (z != 0) {
+#pragma unroll
+      for (int w = 0; w < DW; ++w) sq = __dp4a(int(qi[w]), 0x01010101, sq);
+    }
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
       const int j = lane + 32 * jj;
       code[jj] = -1000;
       if (j < T) {
         const uint32_t* kj = sK + j * KSTR;
-        int s = 0;
+        int s = 0, sk = 0;
 #pragma unroll
-        for (int w = 0; w < DW; ++w) s = __dp4a(int(qi[w]), int(kj[w]), s);
-        code[jj] = sat_s8(fmul(float(s), a.score_mult));
+        for (int w = 0; w < DW; ++w) {
+          s = __dp4a(int(qi[w]), int(kj[w]), s);
+          if (z != 0) sk = __dp4a(int(kj[w]), 0x01010101, sk);
+        }
+        s += DH * z * z - z * (sq + sk);
+        code[jj] = sat_s8(fadd(fmul(float(s), a.score_mult), a.zp_score));
         mx = max(mx, code[jj]);
       }
     }
@@ -91,20 +102,23 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(p2v_atte
     const float tot = u96_to_f32(hi, lo);
     uint8_t* bHi = reinterpret_cast<uint8_t*>(pHi);
     uint8_t* bLo = reinterpret_cast<uint8_t*>(pLo);
+    int psum = 0;
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
       const int j = lane + 32 * jj;
       if (j < T) {
         const uint32_t c = log2_code(tot, sLe[mx - code[jj]]);
         const uint32_t pv = c == 255u ? 0u : (1u << (15 - c));
+        psum += int(pv);
         bHi[j] = uint8_t(pv >> 8);
         bLo[j] = uint8_t(pv & 0xffu);
         if (a.probs_or_null) a.probs_or_null[(int64_t(blockIdx.x) * T + i) * T + j] = uint8_t(c);
         if (a.scores_or_null) a.scores_or_null[(int64_t(blockIdx.x) * T + i) * T + j] = int8_t(code[jj]);
       }
     }
+    psum = __reduce_add_sync(0xffffffffu, psum);
     __syncwarp();
-    // ---- O = sum_j 2^(15-code_j) v_j ; lane owns channels lane, lane+32
+    // ---- O = sum_j 2^(15-code_j) (v_j - z) ; lane owns channels lane, lane+32
 #pragma unroll
     for (int cc = 0; cc < DH / 32; ++cc) {
       const int c = lane + 32 * cc;
@@ -115,8 +129,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_simt_kernel(p2v_atte
         ah = dp4a_us(pHi[w], v, ah);
         al = dp4a_us(pLo[w], v, al);
       }
-      const int O = ah * 256 + al;
-      a.out[(int64_t(b) * T + i) * (H * DH) + h * DH + c] = int8_t(sat_s8(fmul(float(O), a.out_mult)));
+      const int O = ah * 256 + al - z * psum;
+      a.out[(int64_t(b) * T + i) * (H * DH) + h * DH + c] = int8_t(sat_s8(fadd(fmul(float(O), a.out_mult), a.zp_out)));
     }
     __syncwarp();
   }

@@ -51,6 +51,11 @@ constexpr uint32_t AT_SMEM = AT_OFF_BARS + 64;
 // The kernel has no static shared memory, so its dynamic window starts at the 1 KB the system reserves per CTA and is
 // 1024-aligned already; 128 bytes of slack, checked at run time (two CTAs of 112 KB + tables have to fit one SM).
 constexpr size_t AT_SMEM_ALLOC = AT_SMEM + 128;
+// Asymmetric qact1 (zero point z, omse observers): a constant tile of the byte -z (one K / V tile large) turns the correction
+// terms into MMAs on the same accumulators,  (q - z)(k - z) = q k + (-z) k + q (-z) + dh z^2  and  P (v - z) = P v + P (-z),
+// so the softmax warps only add the scalar dh z^2.  The tile costs 14 KB: one CTA per SM for that variant.
+constexpr uint32_t AT_OFF_ZC = (AT_SMEM + 1023u) & ~1023u;
+constexpr size_t AT_SMEM_ALLOC_ZP = AT_OFF_ZC + AT_KV_ROWS * AT_DH + 128;
 static_assert(AT_OFF_K % 1024 == 0 && AT_OFF_V % 1024 == 0 && AT_OFF_P % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 struct AttTcParams {
@@ -61,6 +66,8 @@ struct AttTcParams {
   float score_mult, out_mult;
   const p2v_softmax_lut* lut;
   int8_t* out;
+  int zp_qkv, zc2;          // ZP variant: zero point z of q / k / v and dh * z^2
+  float zp_score, zp_out;   // ZP variant: zero points of qact_attn1 and qact2
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const int (&r)[16]) {
@@ -87,12 +94,13 @@ __device__ __forceinline__ void quarter_exchange_sync(uint32_t quarter) {
 
 // POTM: score_mult is a power of two (minmax observers), so S * mult is exact and one FFMA on the magic-biased integer does
 // the conversion, the scaling and the RNE together; otherwise the reference's separately rounded product is kept.
-template <bool POTM>
+template <bool POTM, bool ZP>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttTcParams p) {
+  static_assert(!(POTM && ZP), "zero points come with raw fp32 scales");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  if (base - smem_u32(smem_raw) + AT_SMEM > uint32_t(AT_SMEM_ALLOC)) __trap();     // dynamic window not aligned as assumed
+  if (base - smem_u32(smem_raw) + (ZP ? AT_OFF_ZC + AT_KV_ROWS * AT_DH : AT_SMEM) > uint32_t(ZP ? AT_SMEM_ALLOC_ZP : AT_SMEM_ALLOC)) __trap();     // dynamic window not aligned as assumed
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + AT_OFF_BARS;
   const uint32_t bar_qk = bars, bar_v = bars + 8, bar_s = bars + 16, bar_p = bars + 24, bar_o = bars + 32, bar_free = bars + 40;
@@ -112,6 +120,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int d = max(i - 1, 0);
     s_lut[i] = make_uint2(p.lut->hi[d], p.lut->lo[d]);
     s_rcp[i] = make_float2(fdiv(1.0f, p.lut->exp_f32[d]), 0.f);
+  }
+  // -z as an int8 byte; z = -128 has no int8 negative: the tile then holds 64 and the correction MMAs are issued twice
+  const int zreps = ZP ? (p.zp_qkv == -128 ? 2 : 1) : 0;
+  if (ZP) {
+    const uint32_t zb = uint32_t(p.zp_qkv == -128 ? 64 : -p.zp_qkv) & 0xffu;
+    const uint32_t zw = zb * 0x01010101u;
+    for (int i = threadIdx.x; i < AT_KV_ROWS * AT_DH / 16; i += AT_THREADS)
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + AT_OFF_ZC + uint32_t(i) * 16u), "r"(zw) : "memory");
+    fence_proxy_async_smem();
   }
   tc_fence_before();
   __syncthreads();
@@ -159,6 +176,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             for (int k = 0; k < AT_DH / 32; ++k)
               umma_i8(tmem_base, make_smem_desc(base + AT_OFF_Q + mt * 128 * AT_DH + k * 32, 16, 512, UMMA_LAYOUT_SW64),
                       make_smem_desc(base + AT_OFF_K + k * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_qk, uint32_t(k > 0));
+            if (ZP) {       // + (-z) k + q (-z): the constant tile as the A operand, then as the B operand
+              for (int rep = 0; rep < zreps; ++rep)
+#pragma unroll
+                for (int k = 0; k < AT_DH / 32; ++k) {
+                  umma_i8(tmem_base, make_smem_desc(base + AT_OFF_ZC + k * 32, 16, 512, UMMA_LAYOUT_SW64),
+                          make_smem_desc(base + AT_OFF_K + k * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_qk, 1u);
+                  umma_i8(tmem_base, make_smem_desc(base + AT_OFF_Q + mt * 128 * AT_DH + k * 32, 16, 512, UMMA_LAYOUT_SW64),
+                          make_smem_desc(base + AT_OFF_ZC + k * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_qk, 1u);
+                }
+            }
             tc_commit(bar_s);
           }
           __syncwarp();
@@ -171,12 +198,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (mt == 0) mbar_wait(bar_v, hcount & 1u);
           tc_fence_after();
           if (elect_one()) {
-            for (int plane = 0; plane < 2; ++plane)
+            for (int plane = 0; plane < 2; ++plane) {
               for (int ks = 0; ks < p.ksteps; ++ks)
                 umma_i8(tmem_base + plane * AT_DH,
                         make_kmajor_sw128_desc(base + AT_OFF_P + plane * AT_P_PLANE + (ks >> 2) * AT_P_CHUNK + (ks & 3) * 32),
                         make_smem_desc(base + AT_OFF_V + ks * 32 * AT_DH, AT_KV_ROWS * AT_DH, 512, UMMA_LAYOUT_SW64), idesc_pv,
                         uint32_t(ks > 0));
+              if (ZP) {     // + P (-z)
+                for (int rep = 0; rep < zreps; ++rep)
+                  for (int ks = 0; ks < p.ksteps; ++ks)
+                    umma_i8(tmem_base + plane * AT_DH,
+                            make_kmajor_sw128_desc(base + AT_OFF_P + plane * AT_P_PLANE + (ks >> 2) * AT_P_CHUNK + (ks & 3) * 32),
+                            make_smem_desc(base + AT_OFF_ZC + ks * 32 * AT_DH, AT_KV_ROWS * AT_DH, 512, UMMA_LAYOUT_SW64), idesc_pv, 1u);
+              }
+            }
             tc_commit(bar_o);
           }
           __syncwarp();
@@ -232,7 +267,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tmem_ld2(tlane + AT_XMAX + 2 * (half ^ 1u), o0, o1);
             smax = max(smax, int(o0));
           }
-          const int mx = sat_s8(fmul(float(smax), mult));
+          // ZP: the accumulator holds S - dh z^2 (the same offset in every column, so the row max is unaffected)
+          const int mx = ZP ? sat_s8(fadd(fmul(float(smax + p.zc2), mult), p.zp_score)) : sat_s8(fmul(float(smax), mult));
           // ---- pass 2: exact row sum of exp_int(max - code) over my units; the table address of d = max - code goes back to
           //      TMEM over S.  u = RMAGIC + RNE(S * mult); v = sat((code + 128) / 256) clamps the code to [-128, 128] (FFMA.SAT,
           //      exact); RMAGIC + 2048 v has 8 (code_sat + 128) in its low mantissa bits, so one subtraction from
@@ -246,6 +282,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const float uq = POTM ? __fmaf_rn(__int_as_float(acc[e] + 0x4B400000), mult, potm_c)
+                               : ZP ? fadd(fadd(fmul(__int2float_rn(acc[e] + p.zc2), mult), p.zp_score), RMAGIC)
                                     : fadd(fmul(__int2float_rn(acc[e]), mult), RMAGIC);
               const float v = fma_sat(uq, 0.00390625f, -49151.5f);
               const uint32_t addr = rowk - __float_as_uint(__fmaf_rn(v, 2048.f, RMAGIC));
@@ -341,7 +378,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               for (int e4 = 0; e4 < 4; ++e4) {
                 float r[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) r[e] = fadd(fmul(__int2float_rn(ah[j + e4 * 4 + e] * 256 + al[j + e4 * 4 + e]), p.out_mult), RMAGIC);
+                for (int e = 0; e < 4; ++e) {
+                  const float o = fmul(__int2float_rn(ah[j + e4 * 4 + e] * 256 + al[j + e4 * 4 + e]), p.out_mult);
+                  r[e] = fadd(ZP ? fadd(o, p.zp_out) : o, RMAGIC);
+                }
                 w[e4] = pack4_sat(r[0], r[1], r[2], r[3]);
               }
               *reinterpret_cast<uint4*>(orow + j) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -395,22 +435,32 @@ int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
   p.mtiles = (a.T + 127) / 128;
   p.score_mult = a.score_mult; p.out_mult = a.out_mult;
   p.lut = a.lut_dev; p.out = a.out;
+  p.zp_qkv = a.zp_qkv; p.zc2 = a.dh * a.zp_qkv * a.zp_qkv; p.zp_score = a.zp_score; p.zp_out = a.zp_out;
+  const bool zp = a.zp_qkv != 0 || a.zp_score != 0.f || a.zp_out != 0.f;
+  P2V_REQUIRE(a.zp_qkv >= -128 && a.zp_qkv <= 127, "attention: zp_qkv=%d outside the int8 range", a.zp_qkv);
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC));
-    P2V_REQUIRE(e == cudaSuccess, "attention_tc: cannot set %zu bytes of dynamic shared memory: %s", AT_SMEM_ALLOC, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC_ZP));
+    P2V_REQUIRE(e == cudaSuccess, "attention_tc: cannot set %zu bytes of dynamic shared memory: %s", AT_SMEM_ALLOC_ZP, cudaGetErrorString(e));
+  }
+  if (zp) {      // asymmetric quantizers: constant-tile variant, one CTA per SM
+    pdl_next_kind(PDL_ATTENTION);
+    launch_pdl(attention_tc_kernel<false, true>, dim3(std::min(p.total_heads, sms)), dim3(AT_THREADS), AT_SMEM_ALLOC_ZP, stream, tmQ, tmKV, p);
+    count_launch();
+    return check_launch("attention_tc");
   }
   const int grid = std::min(p.total_heads, 2 * sms);
   // power-of-two score multiplier in [2^-20, 2^8]: RMAGIC * (1 - mult) is then exact and so is the fused scaling
   int mexp = 0;
   const bool potm = std::frexp(a.score_mult, &mexp) == 0.5f && mexp >= -19 && mexp <= 9;
   pdl_next_kind(PDL_ATTENTION);
-  if (potm) launch_pdl(attention_tc_kernel<true>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
-  else launch_pdl(attention_tc_kernel<false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
+  if (potm) launch_pdl(attention_tc_kernel<true, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
+  else launch_pdl(attention_tc_kernel<false, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
   count_launch();
   return check_launch("attention_tc");
 }

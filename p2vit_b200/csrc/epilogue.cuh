@@ -30,6 +30,7 @@ struct EpiParams {  // device-side copy of p2v_gemm_args (pointers only)
   int8_t* out_i8;
   float* out_f32;
   const void* gelu_table;   // device p2v_gelu_table or NULL
+  float out_zp, mid_zp, aux_zp;   // zero points of asymmetric QActs (0 otherwise; general epilogues only)
   int dbg;   // P2V_DBG experiments (perf triage only): bit 0 = skip the global stores, bit 1 = skip residual loads
 };
 
@@ -42,6 +43,7 @@ inline EpiParams make_epi_params(const p2v_gemm_args& a) {
   p.gelu_table = a.gelu_table;
   p.aux_scale = a.aux_scale; p.tokens_per_image = a.tokens_per_image;
   p.out_i8 = a.out_i8; p.out_f32 = a.out_f32;
+  p.out_zp = a.out_zp; p.mid_zp = a.mid_zp; p.aux_zp = a.aux_zp;
   static const int dbg = getenv("P2V_DBG") ? atoi(getenv("P2V_DBG")) : 0;
   p.dbg = dbg;
   return p;
@@ -52,24 +54,27 @@ inline EpiParams make_epi_params(const p2v_gemm_args& a) {
 // false alarms for saturated |q|) the caller redoes the span with EXACT = true, i.e. with the IEEE quotient.  No branch per element: the fast pass is straight-line code
 // (RNE through the 1.5*2^23 magic constant - exact for |q| < 2^22, saturating beyond), so the compiler can interleave
 // the 16 / 32 independent columns a thread owns.
+// `zp`: zero point of an asymmetric quantizer (uniform.py:83-86: (x / scale + zp).round()), an integer in [-128,127]: |q| < 256
+// before saturation, so |y*rs - fl(y/s)| < 4.6e-5 and the sum fl(. + zp) adds at most one ulp of 256 (1.5e-5) on either side - the
+// guard band is 1e-4 wide.  zp = 0 adds nothing.
 template <bool EXACT>
-__device__ __forceinline__ float quant_div(float y, float s, float rs, bool& slow) {
+__device__ __forceinline__ float quant_div(float y, float s, float rs, bool& slow, float zp = 0.f) {
   float k;
   if (EXACT) {
-    k = rintf(fdiv(y, s));
+    k = rintf(fadd(fdiv(y, s), zp));
   } else {
-    const float qa = fmul(y, rs);
+    const float qa = fadd(fmul(y, rs), zp);
     k = rintf(qa);
-    slow |= fabsf(fsub(qa, k)) > 0.49997f;
+    slow |= fabsf(fsub(qa, k)) > 0.4999f;
   }
   return fminf(fmaxf(k, -128.f), 127.f);
 }
 // same, result as int8 code (one saturating conversion instead of round + clamp + convert)
 template <bool EXACT>
-__device__ __forceinline__ int quant_div_s8(float y, float s, float rs, bool& slow) {
-  if (EXACT) return sat_s8(fdiv(y, s));
-  const float qa = fmul(y, rs);
-  slow |= fabsf(fsub(qa, rintf(qa))) > 0.49997f;
+__device__ __forceinline__ int quant_div_s8(float y, float s, float rs, bool& slow, float zp = 0.f) {
+  if (EXACT) return sat_s8(fadd(fdiv(y, s), zp));
+  const float qa = fadd(fmul(y, rs), zp);
+  slow |= fabsf(fsub(qa, rintf(qa))) > 0.4999f;
   return sat_s8(qa);
 }
 
@@ -167,17 +172,17 @@ __device__ __forceinline__ void epilogue_math(const EpiParams& p, const float* c
       if (EPI == P2V_EPI_F32) {
         f[j] = y;
       } else if (EPI == P2V_EPI_REQUANT) {
-        q[j] = quant_div_s8<EXACT>(y, Ov[e], Rv[e], slow);
+        q[j] = quant_div_s8<EXACT>(y, Ov[e], Rv[e], slow, p.out_zp);
       } else if (EPI == P2V_EPI_DEQUANT) {
-        const float k = quant_div<EXACT>(y, Ov[e], Rv[e], slow);
+        const float k = quant_div<EXACT>(y, Ov[e], Rv[e], slow, p.out_zp);
         q[j] = int(k);
-        f[j] = fmul(k, Ov[e]);
+        f[j] = fmul(fsub(k, p.out_zp), Ov[e]);
       } else if (EPI == P2V_EPI_GELU) {
         if (POT && !EXACT && gt.entries != nullptr) {
           q[j] = gelu_code_table(y, gt.entries[gelu_segment(y, gt.inv_w, gt.off, gt.n)], slow);
         } else {
           const float g = gelu_erf(y);
-          q[j] = POT ? sat_s8(fmul(g, Rv[e])) : quant_div_s8<EXACT>(g, Ov[e], Rv[e], slow);
+          q[j] = POT ? sat_s8(fmul(g, Rv[e])) : quant_div_s8<EXACT>(g, Ov[e], Rv[e], slow, p.out_zp);
         }
       } else if (EPI == P2V_EPI_RESIDUAL) {
         const float c = quant_div<EXACT>(y, Mv[e], RMv[e], slow);
@@ -186,9 +191,9 @@ __device__ __forceinline__ void epilogue_math(const EpiParams& p, const float* c
         const float z = fadd(fmul(r, RSv[e]), t);
         q[j] = quant_div_s8<EXACT>(z, Ov[e], Rv[e], slow);
       } else if (EPI == P2V_EPI_EMBED) {
-        const float c = quant_div<EXACT>(y, e_sm, e_rsm, slow);
-        const float ecode = quant_div<EXACT>(fmul(c, e_sm), p.aux_scale, e_raux, slow);
-        const float v = fadd(fmul(ecode, p.aux_scale), Pv[e]);
+        const float c = quant_div<EXACT>(y, e_sm, e_rsm, slow, p.mid_zp);
+        const float ecode = quant_div<EXACT>(fmul(fsub(c, p.mid_zp), e_sm), p.aux_scale, e_raux, slow, p.aux_zp);
+        const float v = fadd(fmul(fsub(ecode, p.aux_zp), p.aux_scale), Pv[e]);
         q[j] = quant_div_s8<EXACT>(v, Ov[e], Rv[e], slow);
       }
     }

@@ -629,6 +629,7 @@ bool gemm_pair_supported(const p2v_gemm_args& a) {
   const int e = a.epilogue;
   if (e != P2V_EPI_REQUANT && e != P2V_EPI_GELU && e != P2V_EPI_RESIDUAL) return false;
   if (a.row_map || a.zp_corr || !a.out_i8) return false;
+  if (a.out_zp != 0.f || a.mid_zp != 0.f || a.aux_zp != 0.f) return false;     // asymmetric quantizers: csrc/gemm_tc.cu
   if (a.N % 16 || a.K % 16) return false;
   if (reinterpret_cast<uintptr_t>(a.out_i8) & 15) return false;
   if (e == P2V_EPI_RESIDUAL && (reinterpret_cast<uintptr_t>(a.res) & 15)) return false;

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
           const float deq = fmul(yq, os[e]);                                                       // :337
           yf[e] = deq;
           const float mid = a.clamp_mid ? fmul(fminf(fmaxf(yq, -128.f), 127.f), os[e]) : deq;       // QAct at the LN's own scale
-          q[e] = sat_s8(div_by<POT>(div_by<POT>(mid, pd[e]), a.next_scale));
+          q[e] = sat_s8(fadd(div_by<POT>(div_by<POT>(mid, pd[e]), a.next_scale), a.next_zp));   // next_zp: 0 unless the next QAct is asymmetric
         }
         if (a.out_i8) reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(a.out_row_map ? __ldg(a.out_row_map + row) : row) * a.C)[w] = pack4_s8(q[0], q[1], q[2], q[3]);
         if (a.out_f32) reinterpret_cast<float4*>(a.out_f32 + int64_t(row) * a.C)[w] = make_float4(yf[0], yf[1], yf[2], yf[3]);
@@ -603,26 +603,23 @@ __global__ void minmax_final_kernel(const float* __restrict__ part, float* __res
   }
 }
 
-static float* g_scratch = nullptr;
-static size_t g_scratch_bytes = 0;
-static float* scratch(size_t bytes) {
-  if (bytes > g_scratch_bytes) {
-    if (g_scratch) cudaFree(g_scratch);
-    g_scratch = nullptr;
-    if (cudaMalloc(&g_scratch, bytes) != cudaSuccess) { g_scratch_bytes = 0; return nullptr; }
-    g_scratch_bytes = bytes;
-  }
-  return g_scratch;
-}
-
-int launch_minmax(const float* x, float* minmax, int64_t n, int C, int64_t inner, cudaStream_t stream) {
-  const int64_t outer = n / (int64_t(C) * inner);
+static int minmax_blocks(int64_t outer, int64_t& opb) {
   int nblocks = int(std::min<int64_t>(outer, int64_t(num_sms()) * 4));
   if (nblocks < 1) nblocks = 1;
-  const int64_t opb = (outer + nblocks - 1) / nblocks;
-  nblocks = int((outer + opb - 1) / opb);
-  float* part = scratch(size_t(nblocks) * 2 * C * sizeof(float));
-  P2V_REQUIRE(part != nullptr, "minmax: scratch allocation failed");
+  opb = (outer + nblocks - 1) / nblocks;
+  return int((outer + opb - 1) / opb);
+}
+// bytes of caller-owned scratch (block partials): the library keeps no device memory of its own, so concurrent streams /
+// devices cannot share a buffer by accident
+int64_t minmax_scratch_bytes(int64_t n, int C, int64_t inner) {
+  int64_t opb;
+  return int64_t(minmax_blocks(n / (int64_t(C) * inner), opb)) * 2 * C * int64_t(sizeof(float));
+}
+
+int launch_minmax(const float* x, float* minmax, int64_t n, int C, int64_t inner, float* part, cudaStream_t stream) {
+  const int64_t outer = n / (int64_t(C) * inner);
+  int64_t opb;
+  const int nblocks = minmax_blocks(outer, opb);
   minmax_partial_kernel<<<nblocks, 256, 0, stream>>>(x, part, outer, C, inner, opb);
   minmax_final_kernel<<<(C + 255) / 256, 256, 0, stream>>>(part, minmax, nblocks, C);
   count_launch(2);
@@ -635,7 +632,9 @@ constexpr int MSE_KG = 8;
 __global__ void __launch_bounds__(256) mse_scores_kernel(const float* __restrict__ x, int64_t outer, int C, int64_t inner,
                                                          const float* __restrict__ scales, const float* __restrict__ zps, int K,
                                                          int n_scale, int per_channel_out, float lo, float hi,
-                                                         double* __restrict__ out, int64_t outer_per_block) {
+                                                         double* __restrict__ part, int64_t outer_per_block) {
+  // part: [gridDim.x, K, n_out] block partials, folded in block order by mse_final_kernel: the scores (and so the argmin of
+  // near-tied candidates) are bit-reproducible run to run, unlike floating-point atomics
   const int k0 = blockIdx.y * MSE_KG;
   const int kn = min(MSE_KG, K - k0);
   const int64_t o0 = int64_t(blockIdx.x) * outer_per_block;
@@ -665,7 +664,7 @@ __global__ void __launch_bounds__(256) mse_scores_kernel(const float* __restrict
     }
     if (per_channel_out) {
 #pragma unroll
-      for (int k = 0; k < MSE_KG; ++k) if (k < kn) atomicAdd(out + size_t(k0 + k) * n_out + c, double(acc[k]));
+      for (int k = 0; k < MSE_KG; ++k) if (k < kn) part[(size_t(blockIdx.x) * K + k0 + k) * n_out + c] = double(acc[k]);   // inner == 1: e == c, every (block, k, c) is written exactly once
     } else {
 #pragma unroll
       for (int k = 0; k < MSE_KG; ++k) tot[k] += double(acc[k]);
@@ -677,25 +676,93 @@ __global__ void __launch_bounds__(256) mse_scores_kernel(const float* __restrict
       sh[threadIdx.x] = tot[k];
       __syncthreads();
       for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s]; __syncthreads(); }
-      if (threadIdx.x == 0) atomicAdd(out + (k0 + k), sh[0]);
+      if (threadIdx.x == 0) part[size_t(blockIdx.x) * K + k0 + k] = sh[0];
       __syncthreads();
     }
   }
 }
 
-int launch_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales, const float* zps, int K, int n_scale,
-                      int per_channel_out, int lo, int hi, double* out, cudaStream_t stream) {
-  const int64_t outer = n / (int64_t(C) * inner);
-  const int n_out = per_channel_out ? C : 1;
-  cudaMemsetAsync(out, 0, size_t(K) * n_out * sizeof(double), stream);
+__global__ void mse_final_kernel(const double* __restrict__ part, double* __restrict__ out, int nblocks, int64_t per_block) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < per_block; i += int64_t(gridDim.x) * blockDim.x) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += part[size_t(b) * per_block + i];
+    out[i] = t;
+  }
+}
+
+static int mse_blocks(int64_t outer, int64_t& opb) {
   int nblocks = int(std::min<int64_t>(outer, int64_t(num_sms()) * 2));
   if (nblocks < 1) nblocks = 1;
-  const int64_t opb = (outer + nblocks - 1) / nblocks;
-  nblocks = int((outer + opb - 1) / opb);
+  opb = (outer + nblocks - 1) / nblocks;
+  return int((outer + opb - 1) / opb);
+}
+int64_t mse_scratch_bytes(int64_t n, int C, int64_t inner, int K, int per_channel_out) {
+  int64_t opb;
+  return int64_t(mse_blocks(n / (int64_t(C) * inner), opb)) * K * (per_channel_out ? C : 1) * int64_t(sizeof(double));
+}
+
+int launch_mse_scores(const float* x, int64_t n, int C, int64_t inner, const float* scales, const float* zps, int K, int n_scale,
+                      int per_channel_out, int lo, int hi, double* out, double* part, cudaStream_t stream) {
+  const int64_t outer = n / (int64_t(C) * inner);
+  const int n_out = per_channel_out ? C : 1;
+  int64_t opb;
+  const int nblocks = mse_blocks(outer, opb);
+  P2V_REQUIRE(!(per_channel_out && inner != 1), "mse_scores: per-channel scores need channels-last data (inner == 1)");
   dim3 grid(nblocks, (K + MSE_KG - 1) / MSE_KG);
-  mse_scores_kernel<<<grid, 256, 0, stream>>>(x, outer, C, inner, scales, zps, K, n_scale, per_channel_out, float(lo), float(hi), out, opb);
-  count_launch();
+  mse_scores_kernel<<<grid, 256, 0, stream>>>(x, outer, C, inner, scales, zps, K, n_scale, per_channel_out, float(lo), float(hi), part, opb);
+  const int64_t per_block = int64_t(K) * n_out;
+  mse_final_kernel<<<int(std::min<int64_t>((per_block + 255) / 256, 1024)), 256, 0, stream>>>(part, out, nblocks, per_block);
+  count_launch(2);
   return check_launch("quant_mse_scores");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Order statistics for the percentile observer (observer/percentile.py:26-55): one pass of a most-significant-digit radix
+// select.  Keys are the floats' bit patterns mapped monotonically to unsigned integers; the pass counts, among the elements
+// whose key matches `prefix_value` under `prefix_mask`, the digit (key >> shift) & (2^nbits - 1).  Counts are integers, so the
+// histograms of the ranks of a data-parallel calibration add up exactly (all-reduce SUM) and three passes (12 + 12 + 8 bits)
+// pin down the global k-th smallest element - the same value a single process would find on the concatenated batch.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_order_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(512) radix_hist_kernel(const float* __restrict__ x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value,
+                                                         int shift, int nbits, unsigned long long* __restrict__ hist) {
+  extern __shared__ uint32_t sh_hist[];
+  const int nb = 1 << nbits;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) sh_hist[i] = 0u;
+  __syncthreads();
+  const uint32_t dmask = uint32_t(nb - 1);
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int64_t n4 = n >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += stride) {       // 16-byte loads
+    const float4 v = __ldg(x4 + i);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t k = float_order_key(vv[e]);
+      if ((k & prefix_mask) == prefix_value) atomicAdd(&sh_hist[(k >> shift) & dmask], 1u);
+    }
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const uint32_t k = float_order_key(__ldg(x + i));
+    if ((k & prefix_mask) == prefix_value) atomicAdd(&sh_hist[(k >> shift) & dmask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nb; i += blockDim.x)
+    if (sh_hist[i]) atomicAdd(hist + i, static_cast<unsigned long long>(sh_hist[i]));
+}
+
+int launch_radix_hist(const float* x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value, int shift, int nbits,
+                      unsigned long long* hist, cudaStream_t stream) {
+  const int64_t per_block = 512 * 4 * 8;        // a block's smem counters are 32 bit: 16 K elements per block and grid-stride pass stay far below 2^32
+  int grid = int(std::min<int64_t>((n + per_block - 1) / per_block, int64_t(num_sms()) * 4));
+  if (grid < 1) grid = 1;
+  radix_hist_kernel<<<grid, 512, size_t(4) << nbits, stream>>>(x, n, prefix_mask, prefix_value, shift, nbits, hist);
+  count_launch();
+  return check_launch("radix_hist_f32");
 }
 
 }  // namespace p2v

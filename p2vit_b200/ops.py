@@ -79,7 +79,7 @@ def patchify_u8(img_u8, lut, patch, out=None):
     return out
 
 
-def pixel_code_table(mean, std, patch_scale, device):
+def pixel_code_table(mean, std, patch_scale, device, zero_point=0.0):
     """[Cin,256] int8: qact_input code of ToTensor + Normalize of every byte value (x/255, then (x - mean)/std in fp32, the order
     torchvision applies; reference test_quant.py:565-597), produced by the fp32 quantizer kernel itself."""
     mean = torch.as_tensor(mean, dtype=torch.float32, device=device).reshape(-1, 1)
@@ -87,11 +87,12 @@ def pixel_code_table(mean, std, patch_scale, device):
     v = torch.arange(256, dtype=torch.float32, device=device).div(255).reshape(1, 256)
     x = v.sub(mean).div(std)                                     # [Cin, 256]
     Cin = x.shape[0]
-    return quantize_patchify(x.reshape(1, Cin, 16, 16).contiguous(), 16, patch_scale).reshape(Cin, 256).contiguous()
+    return quantize_patchify(x.reshape(1, Cin, 16, 16).contiguous(), 16, patch_scale, zero_point).reshape(Cin, 256).contiguous()
 
 
 def gemm_args(A, W, epilogue, acc_scale, bias=None, out_scale=None, mid_scale=None, res_scale=None, res=None, pos=None,
-              aux_scale=0.0, tokens_per_image=0, out_i8=None, out_f32=None, pot=False, zp_corr=None, row_map=None, gelu_table=None):
+              aux_scale=0.0, tokens_per_image=0, out_i8=None, out_f32=None, pot=False, zp_corr=None, row_map=None, gelu_table=None,
+              out_zp=0.0, mid_zp=0.0, aux_zp=0.0):
     M, K = A.shape
     N = W.shape[0]
     assert W.shape[1] == K
@@ -107,6 +108,9 @@ def gemm_args(A, W, epilogue, acc_scale, bias=None, out_scale=None, mid_scale=No
     a.row_map = ptr(row_map)
     a.gelu_table = ptr(gelu_table)
     a.pot_scales = 1 if pot else 0
+    a.out_zp, a.mid_zp, a.aux_zp = float(out_zp), float(mid_zp), float(aux_zp)
+    if (a.out_zp or a.mid_zp or a.aux_zp) and pot:
+        raise ValueError("gemm: zero points go with the general (non power-of-two) epilogues")
     return a
 
 
@@ -142,7 +146,7 @@ def fill_cls_rows(out, cls_row, B, T, N):
 
 
 def layernorm_args(x, rows, Cn, row_stride, in_mult, in_scale_min, gamma, beta, out_scale, post_div, next_scale, pot,
-                   out_i8=None, out_f32=None, out_row_map=None, clamp_mid=False):
+                   out_i8=None, out_f32=None, out_row_map=None, clamp_mid=False, next_zp=0.0):
     a = LayerNormArgs()
     a.rows, a.C = rows, Cn
     a.x, a.x_row_stride = ptr(x), row_stride
@@ -152,6 +156,9 @@ def layernorm_args(x, rows, Cn, row_stride, in_mult, in_scale_min, gamma, beta, 
     a.next_scale, a.pot_scales = float(next_scale), 1 if pot else 0
     a.out_i8, a.out_f32 = ptr(out_i8), ptr(out_f32)
     a.out_row_map, a.clamp_mid = ptr(out_row_map), 1 if clamp_mid else 0
+    a.next_zp = float(next_zp)
+    if a.next_zp and pot:
+        raise ValueError("layernorm: a zero point goes with the general (non power-of-two) kernel")
     return a
 
 
@@ -168,13 +175,14 @@ def int_softmax_log2(scores_i8, lut_dev):
     return out
 
 
-def attention_args(qkv, out, B, T, H, dh, score_mult, out_mult, lut_dev, probs=None, scores=None):
+def attention_args(qkv, out, B, T, H, dh, score_mult, out_mult, lut_dev, probs=None, scores=None, zp_qkv=0, zp_score=0.0, zp_out=0.0):
     a = AttentionArgs()
     a.B, a.T, a.H, a.dh = B, T, H, dh
     a.qkv, a.out = ptr(qkv), ptr(out)
     a.score_mult, a.out_mult = float(score_mult), float(out_mult)
     a.lut_dev = ptr(lut_dev)
     a.probs_or_null, a.scores_or_null = ptr(probs), ptr(scores)
+    a.zp_qkv, a.zp_score, a.zp_out = int(zp_qkv), float(zp_score), float(zp_out)
     return a
 
 
@@ -211,22 +219,36 @@ def minmax_per_channel(x):
     """[2,C] tensor: row 0 per-channel min, row 1 per-channel max (observer/base.py:16-29 layout rule)."""
     x = x.detach().contiguous().float()
     Cn, inner = _channel_geometry(x)
+    lib = _lib.load()
     out = torch.empty((2, Cn), dtype=torch.float32, device=x.device)
-    check(_lib.load().p2v_minmax_per_channel(ptr(x), ptr(out), x.numel(), Cn, inner, stream()), "minmax_per_channel")
+    scratch = torch.empty(max(1, lib.p2v_minmax_scratch_bytes(x.numel(), Cn, inner) // 4), dtype=torch.float32, device=x.device)
+    check(lib.p2v_minmax_per_channel(ptr(x), ptr(out), x.numel(), Cn, inner, ptr(scratch), stream()), "minmax_per_channel")
     return out
 
 
 def quant_mse_scores(x, scales, lo, hi, zero_points=None, per_channel_out=False):
-    """sum((x - fq_k(x))^2) for K candidate scales [K, 1 or C] -> float64 [K, 1 or C]."""
+    """sum((x - fq_k(x))^2) for K candidate scales [K, 1 or C] -> float64 [K, 1 or C] (bit-reproducible: fixed reduction order)."""
     x = x.detach().contiguous().float()
     Cn, inner = _channel_geometry(x)
     scales = scales.detach().to(device=x.device, dtype=torch.float32).contiguous()
     K, n_scale = scales.shape
     zps = None if zero_points is None else zero_points.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    lib = _lib.load()
+    pco = 1 if per_channel_out else 0
     out = torch.empty((K, Cn if per_channel_out else 1), dtype=torch.float64, device=x.device)
-    check(_lib.load().p2v_quant_mse_scores(ptr(x), x.numel(), Cn, inner, ptr(scales), ptr(zps), K, n_scale, 1 if per_channel_out else 0,
-                                           lo, hi, ptr(out), stream()), "quant_mse_scores")
+    scratch = torch.empty(max(1, lib.p2v_quant_mse_scratch_bytes(x.numel(), Cn, inner, K, pco) // 8), dtype=torch.float64, device=x.device)
+    check(lib.p2v_quant_mse_scores(ptr(x), x.numel(), Cn, inner, ptr(scales), ptr(zps), K, n_scale, pco, lo, hi, ptr(out), ptr(scratch),
+                                   stream()), "quant_mse_scores")
     return out
+
+
+def radix_hist(flat, prefix_mask, prefix_value, shift, nbits):
+    """one radix-select pass over a flat fp32 CUDA tensor: int64 [2^nbits] counts of the digit (key >> shift) among the elements
+    whose order key matches the prefix (include/p2vit_b200.h: p2v_radix_hist_f32)"""
+    hist = torch.zeros(1 << nbits, dtype=torch.int64, device=flat.device)
+    check(_lib.load().p2v_radix_hist_f32(ptr(flat), flat.numel(), int(prefix_mask), int(prefix_value), int(shift), int(nbits), ptr(hist),
+                                         stream()), "radix_hist_f32")
+    return hist
 
 
 def launch_count(reset=False):

@@ -447,7 +447,17 @@ class VisionTransformer(nn.Module, QuantModelMixin):
                              "(vit_fquant.py:335: bit_pool.index(None) fails)")
         if self._engine is None:
             self._engine = VitEngine(self)
-        return self._engine(x, bit_config), self.flops_list(), []
+        if self._engine is not False:
+            from .engine import EngineNotApplicable
+            try:
+                return self._engine(x, bit_config), self.flops_list(), []
+            except EngineNotApplicable as e:
+                # configurations outside the integer program (Config(ptf=False), Config(lis=False), non-int8 activations): the
+                # reference evaluates them through the same call, so does this model - module by module, same kernels
+                import warnings
+                warnings.warn("p2vit_b200: integer engine not applicable (%s); evaluating module by module (forward_eager)" % e)
+                self._engine = False
+        return self.forward_eager(x, bit_config, plot, hessian_statistic)
 
 
 

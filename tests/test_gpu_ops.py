@@ -663,3 +663,52 @@ def test_patchify_u8_rejects_bad_arguments():
         ops.patchify_u8(torch.zeros((1, 3, 32, 32), dtype=torch.uint8, device=DEV), lut[:2], 16)  # table of another channel count
     with pytest.raises(RuntimeError):
         ops.patchify_u8(torch.zeros((1, 3, 30, 32), dtype=torch.uint8, device=DEV), lut, 16)      # H not a multiple of P
+
+
+# ------------------------------------------------------------------------------------------------ percentile observer kernels
+def test_radix_hist_kernel_vs_numpy():
+    """p2v_radix_hist_f32: digit counts under a key prefix equal numpy's on the same order keys (odd length, negative values)"""
+    from test_host_logic import _np_hist_fn          # tests/ is on sys.path (rootdir conftest, no package)
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(1_000_003) * 5).astype(np.float32)
+    x[::11] = -0.0
+    fn = _np_hist_fn(x)
+    xd = torch.from_numpy(x).cuda()
+    key0 = int(np.sort(x.view(np.uint32))[1234])
+    for mask, value, shift, nbits in ((0, 0, 20, 12), (0xFFF00000, 0xC0000000, 8, 12), (0xFFFFFF00, (key0 | 0x80000000) & 0xFFFFFF00, 0, 8)):
+        got = ops.radix_hist(xd, mask, value, shift, nbits).cpu()
+        assert torch.equal(got, fn(mask, value, shift, nbits)), (hex(mask), shift)
+    assert int(ops.radix_hist(xd, 0, 0, 20, 12).sum()) == x.size
+
+
+@pytest.mark.parametrize("n", [4099, 2_400_000, 16_900_000])
+def test_percentile_observer_equals_reference_quantile(n):
+    """PercentileObserver.update on the GPU (radix select, no sort) against the reference's own calls on the same data:
+    torch.quantile, and np.percentile above 2^24 elements (observer/percentile.py:26-43) - bit for bit"""
+    from p2vit_b200.ptq.bit_type import BIT_TYPE_DICT
+    from p2vit_b200.ptq.observer.percentile import PercentileObserver
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, generator=g) * 2.5
+    obs = PercentileObserver("activation", BIT_TYPE_DICT["int8"], "layer_wise")
+    obs.update(x.cuda().reshape(1, -1, 1))
+    if n <= 16_777_216:
+        hi, lo = torch.quantile(x, 0.99999), torch.quantile(x, 1.0 - 0.99999)
+    else:
+        hi = torch.tensor(np.percentile(x.numpy(), 0.99999 * 100), dtype=torch.float32)
+        lo = torch.tensor(np.percentile(x.numpy(), (1 - 0.99999) * 100), dtype=torch.float32)
+    assert float(obs.max_val) == float(hi) and float(obs.min_val) == float(lo)
+
+
+def test_mse_scores_are_bit_reproducible():
+    """candidate scores are folded in a fixed order (no floating-point atomics), so repeated launches agree bit for bit"""
+    torch.manual_seed(0)
+    x = torch.randn(64, 197, 384, device="cuda")
+    cand = (2.0 ** torch.arange(-8, -4).float()).reshape(4, 1).cuda()
+    a = ops.quant_mse_scores(x, cand, -128, 127)
+    pc = ops.quant_mse_scores(x, cand.expand(4, 384).contiguous(), -128, 127, per_channel_out=True)
+    for _ in range(3):
+        assert torch.equal(a, ops.quant_mse_scores(x, cand, -128, 127))
+        assert torch.equal(pc, ops.quant_mse_scores(x, cand.expand(4, 384).contiguous(), -128, 127, per_channel_out=True))
+    ref = torch.stack([((x - (x / s).round().clamp(-128, 127) * s) ** 2).double().sum() for s in cand.reshape(-1)])
+    assert torch.allclose(a.reshape(-1), ref, rtol=1e-6)
+    assert torch.allclose(pc.sum(1), ref, rtol=1e-6)

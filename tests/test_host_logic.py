@@ -141,6 +141,79 @@ def test_statistics_allreduce_world2_gloo(tmp_path):
     assert r.stdout.count("ok") == 2
 
 
+# ------------------------------------------------------------------------------------------------ percentile observer (host logic)
+def _np_hist_fn(x):
+    """numpy stand-in for ops.radix_hist (the CUDA kernel; tests/test_gpu_ops.py checks the kernel against this very function)"""
+    import numpy as np
+    u = x.view(np.uint32)
+    key = np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.uint32)
+
+    def fn(mask, value, shift, nbits):
+        sel = key[(key & np.uint32(mask)) == np.uint32(value)]
+        return torch.from_numpy(np.bincount((sel >> np.uint32(shift)) & np.uint32((1 << nbits) - 1), minlength=1 << nbits).astype(np.int64))
+    return fn
+
+
+def test_percentile_select_and_interpolation_equal_the_reference_libraries():
+    """observer/percentile.py:26-55 sorts (torch.quantile; np.percentile above 2^24 elements).  The radix select + the restated
+    interpolation arithmetic return the same fp32 value, bit for bit, in both size classes - ties, negative values, both tails."""
+    import numpy as np
+    from p2vit_b200.ptq.observer.percentile import quantile_from_order_statistics, select_kth
+    rng = np.random.default_rng(0)
+    local = lambda t, op: t
+    for n in (1000, 123457, 2_400_000):
+        x = (rng.standard_normal(n) * 3).astype(np.float32)
+        x[::7] = x[3]
+        fn, srt = _np_hist_fn(x), np.sort(x)
+        for k in (0, n // 3, n - 2, n - 1):
+            assert select_kth(fn, k, allreduce=local) == srt[k]
+        kth = lambda k: select_kth(fn, k, allreduce=local)
+        for q in (0.99999, 1 - 0.99999, 0.5):
+            assert quantile_from_order_statistics(kth, n, q) == float(torch.quantile(torch.from_numpy(x), q)), (n, q)
+    n = 16_777_300                                  # torch.quantile refuses: the reference's numpy branch (percentile.py:36-43)
+    x = rng.standard_normal(n).astype(np.float32)
+    with pytest.raises(RuntimeError):
+        torch.quantile(torch.from_numpy(x), 0.5)
+    srt = np.sort(x)
+    for q in (0.99999, 1 - 0.99999):
+        want = float(torch.tensor(np.percentile(x, q * 100), dtype=torch.float32))
+        assert quantile_from_order_statistics(lambda k: srt[k], n, q) == want, q
+
+
+_PCT_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+sys.path.insert(0, os.path.join(%r, "tests"))
+from test_host_logic import _np_hist_fn
+from p2vit_b200.ptq.observer.percentile import quantile_from_order_statistics, select_kth
+from p2vit_b200.ptq.observer.utils import allreduce_
+from p2vit_b200.runner import shard_range
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+full = (np.random.default_rng(5).standard_normal(300007) * 2).astype(np.float32)
+a, b = shard_range(full.size, r, w)
+fn = _np_hist_fn(full[a:b].copy())                       # this rank's shard only
+n = int(allreduce_(torch.tensor([b - a]), "sum"))
+kth = lambda k: select_kth(fn, k)                        # histograms all-reduced (SUM) pass by pass
+for q in (0.99999, 1 - 0.99999):
+    got = quantile_from_order_statistics(kth, n, q)
+    want = float(torch.quantile(torch.from_numpy(full), q))      # one process on the concatenated batch
+    assert got == want, (r, q, got, want)
+print("rank", r, "ok")
+dist.destroy_process_group()
+'''
+
+
+def test_percentile_world2_gloo_equals_single_process(tmp_path):
+    """every rank of a data-parallel percentile calibration freezes the quantile of the WHOLE batch (SURVEY 5; ADVICE r1)"""
+    script = tmp_path / "p.py"
+    script.write_text(_PCT_WORKER % (ROOT, ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29643", str(script)], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
+
+
 # ------------------------------------------------------------------------------------------------ mixed-precision search
 def _vit_flops(depth=12, D=192, T=197):
     f = [196 * 768 * D]
