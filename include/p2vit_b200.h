@@ -168,6 +168,11 @@ typedef struct {
                                LayerNorm and the smoothing divide (Swin: norm2 -> qact3 -> Mlp, swin_quant.py:439-446) */
   float next_zp;            /* zero point of the QAct after the LN (0 unless its observer is asymmetric; needs pot_scales = 0):
                                out_i8 = sat(RNE(fl(fl(fl(y_q*out_scale[c]) / post_div[c]) / next_scale) + next_zp)) */
+  const int32_t* in_gather; /* [rows * gather_segs] or NULL.  Swin patch merging (swin_quant.py:512-519) as the LayerNorm's input
+                               row map: row r is the concatenation of gather_segs source rows of C / gather_segs channels,
+                               segment k = x[in_gather[r * gather_segs + k]] (x_row_stride = bytes of one SOURCE row), so the 2x2
+                               neighbourhood gather costs no kernel and no [rows, 4C] buffer of its own */
+  int gather_segs;          /* 4 for patch merging; C / gather_segs must be a multiple of 4 */
 } p2v_layernorm_args;
 
 int p2v_layernorm_int(const p2v_layernorm_args* args_host, void* stream);

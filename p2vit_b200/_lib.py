@@ -41,6 +41,7 @@ class LayerNormArgs(C.Structure):
         ("next_scale", C.c_float), ("pot_scales", C.c_int),
         ("out_i8", C.c_void_p), ("out_f32", C.c_void_p),
         ("out_row_map", C.c_void_p), ("clamp_mid", C.c_int), ("next_zp", C.c_float),
+        ("in_gather", C.c_void_p), ("gather_segs", C.c_int),
     ]
 
 

@@ -172,6 +172,8 @@ int p2v_layernorm_int(const p2v_layernorm_args* a, void* stream) {
   P2V_REQUIRE(a->out_i8 || a->out_f32, "layernorm: no output");
   P2V_REQUIRE(a->x_row_stride % 4 == 0, "layernorm: row stride must be a multiple of 4 bytes");
   P2V_REQUIRE(a->next_zp == 0.f || !a->pot_scales, "layernorm: a zero point needs the general kernel (pot_scales = 0)");
+  if (a->in_gather) P2V_REQUIRE(a->gather_segs > 0 && a->C % (4 * a->gather_segs) == 0 && !a->out_f32,
+                                "layernorm: gathered input needs C %% (4 * gather_segs) == 0 and int8 output");
   return launch_layernorm(*a, (cudaStream_t)stream);
 }
 int p2v_int_softmax_log2(const int8_t* scores, uint8_t* out, int64_t rows, int n, const p2v_softmax_lut* lut, void* stream) {

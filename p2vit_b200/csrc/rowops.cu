@@ -229,6 +229,15 @@ int launch_fill_cls(int8_t* out, const int8_t* cls_row, int B, int T, int N, cud
 template <bool POT>
 __device__ __forceinline__ float div_by(float x, float s) { return POT ? fmul(x, fdiv(1.f, s)) : fdiv(x, s); }
 
+// word w (4 channels) of input row `row`: plain rows, or - Swin patch merging fused into the LayerNorm (p2v_layernorm_args.in_gather) -
+// the concatenation of gather_segs source rows
+__device__ __forceinline__ const uint32_t* ln_word_ptr(const p2v_layernorm_args& a, int row, int w) {
+  if (a.in_gather == nullptr) return reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride) + w;
+  const int seg_words = a.C / (4 * a.gather_segs);
+  const int seg = w / seg_words;
+  return reinterpret_cast<const uint32_t*>(a.x + int64_t(__ldg(a.in_gather + int64_t(row) * a.gather_segs + seg)) * a.x_row_stride) + (w - seg * seg_words);
+}
+
 template <int WPL, bool POT>
 __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
   pdl_wait();
@@ -239,14 +248,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(p2v_layernorm_args a) {
   const float Cf = float(a.C);
   const float s1 = a.in_scale_min;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.rows; row += gridDim.x * warps_per_block) {
-    const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
     int xv[WPL][4];
     int S1 = 0, S2 = 0;
 #pragma unroll
     for (int i = 0; i < WPL; ++i) {
       const int w = lane + 32 * i;
       if (w < nwords) {
-        const uint32_t u = __ldg(xr + w);
+        const uint32_t u = __ldg(ln_word_ptr(a, row, w));
         const float4 m = __ldg(reinterpret_cast<const float4*>(a.in_mult) + w);
         xv[i][0] = int(int8_t(u & 0xff)) * int(m.x);
         xv[i][1] = int(int8_t((u >> 8) & 0xff)) * int(m.y);
@@ -326,7 +334,7 @@ __device__ __forceinline__ uint32_t ln_pot_word(float t, float mos, const float 
 }
 
 // one lane's words of a row through ln_pot_word<true>, every constant re-derived from global memory as the kernel prologue does
-__device__ __noinline__ void ln_pot_row_slow(const p2v_layernorm_args& a, const uint32_t* __restrict__ xr, uint32_t* __restrict__ orow, int sub,
+__device__ __noinline__ void ln_pot_row_slow(const p2v_layernorm_args& a, int row, uint32_t* __restrict__ orow, int sub,
                                              int lpr, int wpln, float t, float mos, float clamp_hi) {
   const float rnext = fdiv(1.f, a.next_scale);
   for (int i = 0; i < wpln; ++i) {
@@ -336,7 +344,7 @@ __device__ __noinline__ void ln_pot_row_slow(const p2v_layernorm_args& a, const 
     const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.in_mult) + w);
     const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, oo[4] = {o4.x, o4.y, o4.z, o4.w};
     const float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
-    const uint32_t u = __ldg(xr + w);
+    const uint32_t u = __ldg(ln_word_ptr(a, row, w));
     const int cx[4] = {int(int8_t(u & 0xff)), int(int8_t((u >> 8) & 0xff)), int(int8_t((u >> 16) & 0xff)), int(int8_t(u >> 24))};
     float g[4], bt[4], f[4];
     int xv[4];
@@ -428,13 +436,22 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
   }
   pdl_wait();          // the channel constants above are plan-time data; the rows are the previous kernel's output (common.cuh)
   pdl_trigger();
+  // gathered input (patch merging): segment and offset of each of the lane's words are row independent
+  int gseg[WPLN], goff[WPLN];
+  const bool gathered = a.in_gather != nullptr;
+  if (gathered) {
+    const int seg_words = a.C / (4 * a.gather_segs);
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) { gseg[i] = (sub + LPR * i) / seg_words; goff[i] = (sub + LPR * i) - gseg[i] * seg_words; }
+  }
   for (int row = warp_global * GPW + grp; row < a.rows; row += row_stride) {
     const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
     int xv[WPLN][4];
     int S1 = 0, S2 = 0;
 #pragma unroll
     for (int i = 0; i < WPLN; ++i) {
-      const uint32_t u = __ldg(xr + sub + LPR * i);
+      const uint32_t u = gathered ? __ldg(reinterpret_cast<const uint32_t*>(a.x + int64_t(__ldg(a.in_gather + int64_t(row) * a.gather_segs + gseg[i])) * a.x_row_stride) + goff[i])
+                                  : __ldg(xr + sub + LPR * i);
       xv[i][0] = int(int8_t(u & 0xff)) * sh[i][0];
       xv[i][1] = int(int8_t((u >> 8) & 0xff)) * sh[i][1];
       xv[i][2] = int(int8_t((u >> 16) & 0xff)) * sh[i][2];
@@ -462,7 +479,7 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
       for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_fast_word<CLAMP_MID>(t, mos, g[i], bt[i], f[i], xv[i], mant_max);
     }
     if (!in_range || mant_max >= 0x007ffff0u) {
-      ln_pot_row_slow(a, xr, orow, sub, LPR, WPLN, t, mos, clamp_hi);     // rare: out of line, constants re-read from memory
+      ln_pot_row_slow(a, row, orow, sub, LPR, WPLN, t, mos, clamp_hi);     // rare: out of line, constants re-read from memory
     } else {
 #pragma unroll
       for (int i = 0; i < WPLN; ++i) orow[sub + LPR * i] = qw[i];

@@ -146,7 +146,7 @@ def fill_cls_rows(out, cls_row, B, T, N):
 
 
 def layernorm_args(x, rows, Cn, row_stride, in_mult, in_scale_min, gamma, beta, out_scale, post_div, next_scale, pot,
-                   out_i8=None, out_f32=None, out_row_map=None, clamp_mid=False, next_zp=0.0):
+                   out_i8=None, out_f32=None, out_row_map=None, clamp_mid=False, next_zp=0.0, in_gather=None, gather_segs=0):
     a = LayerNormArgs()
     a.rows, a.C = rows, Cn
     a.x, a.x_row_stride = ptr(x), row_stride
@@ -157,6 +157,7 @@ def layernorm_args(x, rows, Cn, row_stride, in_mult, in_scale_min, gamma, beta, 
     a.out_i8, a.out_f32 = ptr(out_i8), ptr(out_f32)
     a.out_row_map, a.clamp_mid = ptr(out_row_map), 1 if clamp_mid else 0
     a.next_zp = float(next_zp)
+    a.in_gather, a.gather_segs = ptr(in_gather), int(gather_segs)
     if a.next_zp and pot:
         raise ValueError("layernorm: a zero point goes with the general (non power-of-two) kernel")
     return a

@@ -10,7 +10,7 @@ workspace, and the launch sequence captured into a CUDA graph:
                [q k^T -> qact_attn1 -> + bias -> qact2 -> (+ mask) -> log2 softmax -> P v -> qact3]
                -> GEMM[proj -> attn.qact4 -> + shortcut -> qact2(PTF), stored back in token order]
                -> LN2[-> qact3 -> / cs -> mlp.qact0] -> GEMM[fc1 -> GELU -> qact1] -> GEMM[fc2 -> qact2(PTF) -> + x -> qact4(PTF)]
-    per stage end: gather 2x2 -> LN[4C -> qact1] -> GEMM[reduction -> qact2(PTF)]
+    per stage end: LN[2x2 gather as its input row map, 4C -> qact1] -> GEMM[reduction -> qact2(PTF)]
     LN[norm -> qact2] -> average pool + qact3 -> GEMM[head -> act_out]
 
 Window partition, cyclic shift and their inverses never move data on their own: LN1 scatters its rows through a
@@ -193,15 +193,17 @@ class SwinEngine:
         n0 = B * L0 * pl.C0                                                # bytes of one [rows, C] activation (constant over stages / 2)
         flat = lambda n: torch.empty(n, dtype=torch.int8, device=dev)
         ws = dict(img=torch.empty((B, 3, side, side), dtype=torch.float32, device=dev), cols=flat(B * L0 * 3 * pl.P * pl.P),
-                  ra=flat(n0), rb=flat(n0), ln=flat(n0), ao=flat(n0), gat=flat(n0), qkv=flat(3 * n0), hid=flat(4 * n0),
+                  ra=flat(n0), rb=flat(n0), ln=flat(n0), ao=flat(n0), qkv=flat(3 * n0), hid=flat(4 * n0),
                   pool=flat(B * pl.Cf), logits=torch.empty((B, pl.head.N), dtype=torch.float32, device=dev), logit_codes=flat(B * pl.head.N))
         view = lambda name, rows, C: ws[name][: rows * C].view(rows, C)
         steps = []
         gemm = lambda args: (lambda: ops.gemm(args))
 
-        def ln(p, x, rows, C, out, row_map=None, clamp_mid=False):
-            a = ops.layernorm_args(x, rows, C, C, p["in_mult"], p["s1"], p["gamma"], p["beta"], p["out_scale"], p["post_div"], p["next_scale"],
-                                   p["pot"], out_i8=out, out_row_map=row_map, clamp_mid=clamp_mid)
+        def ln(p, x, rows, C, out, row_map=None, clamp_mid=False, gather=None):
+            # gather: patch merging - the row is the concatenation of four source rows of C / 4 channels (row stride = source row)
+            a = ops.layernorm_args(x, rows, C, C // 4 if gather is not None else C, p["in_mult"], p["s1"], p["gamma"], p["beta"], p["out_scale"],
+                                   p["post_div"], p["next_scale"], p["pot"], out_i8=out, out_row_map=row_map, clamp_mid=clamp_mid,
+                                   in_gather=gather, gather_segs=4 if gather is not None else 0)
             return lambda: ops.layernorm(a)
 
         R = B * L0
@@ -256,13 +258,13 @@ class SwinEngine:
                 src = _merge_map(B, H, H, dev)
                 keep.append(src)
                 R4 = R // 4
-                gat, ln4 = view("gat", R4, 4 * C), view("ln", R4, 4 * C)
-                steps.append((pre + "gather", (lambda src=src, ra=ra, gat=gat, R4=R4, C=C: ops.gather_rows(ra, gat, src, R4, 4, C))))
-                steps.append((pre + "qact1", ln(mg["ln"], gat, R4, 4 * C, ln4)))
+                ln4 = view("ln", R4, 4 * C)
+                # the 2x2 neighbourhood gather (swin_quant.py:512-519) is the merge LayerNorm's input row map: no gather kernel, no [R/4, 4C] copy
+                steps.append((pre + "qact1", ln(mg["ln"], ra, R4, 4 * C, ln4, gather=src)))
                 gr = mg["red"]
                 steps.append((pre + "qact2", gemm(ops.gemm_args(ln4, gr.W, ops.EPI_REQUANT, gr.acc_scale, bias=None, out_scale=mg["out"],
                                                                 out_i8=view("ra", R4, 2 * C)))))
-                outs.update({pre + "gather": ("gat", R4, 4 * C), pre + "qact1": ("ln", R4, 4 * C), pre + "qact2": ("ra", R4, 2 * C)})
+                outs.update({pre + "qact1": ("ln", R4, 4 * C), pre + "qact2": ("ra", R4, 2 * C)})
         Cf, Tl = pl.Cf, pl.stages[-1]["H"] ** 2
         Rl = B * Tl
         steps.append(("qact2", ln(pl.ln_f, view("ra", Rl, Cf), Rl, Cf, view("ln", Rl, Cf))))
