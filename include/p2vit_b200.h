@@ -252,9 +252,21 @@ typedef struct {
   const int32_t* out_row_map;   /* optional [n_windows * T]: row (window order) -> destination row of `out`; NULL = same row.
                                    window_reverse + roll (swin_quant.py:426-436) applied by the store, so the proj GEMM that
                                    follows reads and writes token order and needs no scatter */
+  /* The same two tables in the form the tensor-core kernel stages (both optional; without them the dp4a kernel runs):
+   *   bias_codes  int8 [H, T, 80]: qact_table codes gathered through relative_position_index, rows padded to 80 bytes,
+   *               16-byte aligned;  bias[h,i,j] == fl(bias_codes[h,i,j] * bias_scale) (bias_scale = qact_table.scale)
+   *   mask_bits   uint64 [windows_per_image, T]: bit j of word (w, i) = [label_i != label_j]; required with `labels` */
+  const int8_t* bias_codes;
+  float bias_scale;
+  const uint64_t* mask_bits;
 } p2v_window_attention_args;
 
+/* Head dim 32, T <= 64, bias_codes (and mask_bits when labels are given): tcgen05 kernel (csrc/swin_attention_tc.cu: two
+ * windows per 128-row tile, S = q k^T and O = P v on the tensor cores, softmax per TMEM row); otherwise the dp4a kernel
+ * (csrc/swin_ops.cu). */
 int p2v_window_attention_i8(const p2v_window_attention_args* args_host, void* stream);
+/* same contract, always on CUDA cores (dp4a); used by tests to cross-check the tcgen05 kernel */
+int p2v_window_attention_i8_simt(const p2v_window_attention_args* args_host, void* stream);
 
 /* Patch merging gather (swin_quant.py:512-519): out[r, k*C:(k+1)*C] = in[src_rows[r*segs + k], :]  (int8 rows of C bytes) */
 int p2v_gather_rows_i8(const int8_t* in, int8_t* out, const int32_t* src_rows, int rows_out, int segs, int C, void* stream);

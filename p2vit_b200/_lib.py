@@ -52,6 +52,7 @@ class WindowAttentionArgs(C.Structure):
         ("score_mult", C.c_float), ("s_attn1", C.c_float), ("s_attn2", C.c_float),
         ("bias", C.c_void_p), ("labels", C.c_void_p), ("mask_code", C.c_int), ("mask_exp_int", C.c_uint32),
         ("out_mult", C.c_float), ("lut_dev", C.c_void_p), ("out_row_map", C.c_void_p),
+        ("bias_codes", C.c_void_p), ("bias_scale", C.c_float), ("mask_bits", C.c_void_p),
     ]
 
 
@@ -88,6 +89,7 @@ SYMBOLS = {
     "p2v_attention_i8": (_I, [C.POINTER(AttentionArgs), _P]),
     "p2v_attention_i8_simt": (_I, [C.POINTER(AttentionArgs), _P]),
     "p2v_window_attention_i8": (_I, [C.POINTER(WindowAttentionArgs), _P]),
+    "p2v_window_attention_i8_simt": (_I, [C.POINTER(WindowAttentionArgs), _P]),
     "p2v_gather_rows_i8": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "p2v_avgpool_quant_i8": (_I, [_P, _P, _I, _I, _I, _F, _F, _P]),
     "p2v_minmax_scratch_bytes": (_I64, [_I64, _I, _I64]),

@@ -75,6 +75,8 @@ int launch_attention(const p2v_attention_args& a, cudaStream_t stream);
 int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream);
 bool attention_tc_supported(const p2v_attention_args& a);
 int launch_window_attention(const p2v_window_attention_args& a, uint32_t e_mask, cudaStream_t stream);
+int launch_window_attention_tc(const p2v_window_attention_args& a, uint32_t e_mask, cudaStream_t stream);
+bool window_attention_tc_supported(const p2v_window_attention_args& a);
 int launch_gather_rows(const int8_t* in, int8_t* out, const int32_t* src, int rows_out, int segs, int C, cudaStream_t stream);
 int launch_avgpool_quant(const int8_t* in, int8_t* out, int B, int T, int C, float s_in, float s_out, cudaStream_t stream);
 int launch_minmax(const float* x, float* minmax, int64_t n, int C, int64_t inner, float* part, cudaStream_t stream);
@@ -195,12 +197,21 @@ int p2v_attention_i8_simt(const p2v_attention_args* a, void* stream) {
   if (int r = validate_attention(a)) return r;
   return launch_attention(*a, (cudaStream_t)stream);
 }
-int p2v_window_attention_i8(const p2v_window_attention_args* a, void* stream) {
+static int validate_window_attention(const p2v_window_attention_args* a) {
   P2V_REQUIRE(a && a->qkv && a->out && a->bias && a->lut_dev, "window_attention: missing pointers");
   P2V_REQUIRE(a->n_windows > 0 && a->H > 0 && a->T > 0 && a->T <= 64, "window_attention: T=%d unsupported (1..64)", a->T);
   P2V_REQUIRE(a->dh == 32 || a->dh == 64, "window_attention: head dim %d unsupported (32 or 64)", a->dh);
   P2V_REQUIRE(a->windows_per_image > 0 && a->mask_code <= 0, "window_attention: bad mask arguments");
   P2V_REQUIRE((reinterpret_cast<uintptr_t>(a->qkv) & 15) == 0, "window_attention: qkv must be 16-byte aligned");
+  return 0;
+}
+int p2v_window_attention_i8(const p2v_window_attention_args* a, void* stream) {
+  if (int r = validate_window_attention(a)) return r;
+  if (window_attention_tc_supported(*a)) return launch_window_attention_tc(*a, a->mask_exp_int, (cudaStream_t)stream);
+  return launch_window_attention(*a, a->mask_exp_int, (cudaStream_t)stream);
+}
+int p2v_window_attention_i8_simt(const p2v_window_attention_args* a, void* stream) {
+  if (int r = validate_window_attention(a)) return r;
   return launch_window_attention(*a, a->mask_exp_int, (cudaStream_t)stream);
 }
 int p2v_gather_rows_i8(const int8_t* in, int8_t* out, const int32_t* src_rows, int rows_out, int segs, int C, void* stream) {

@@ -193,19 +193,41 @@ def attention(args, simt=False):
     check(fn(C.byref(args), stream()), "attention_i8_simt" if simt else "attention_i8")
 
 
+BIAS_PITCH = 80      # row pitch of WindowAttentionArgs.bias_codes (include/p2vit_b200.h)
+
+
+def window_bias_codes(codes):
+    """int8 [H, T, T] qact_table codes gathered through relative_position_index -> the padded [H, T, 80] layout of the ABI"""
+    H, T, _ = codes.shape
+    out = torch.zeros((H, T, BIAS_PITCH), dtype=torch.int8, device=codes.device)
+    out[:, :, :T] = codes
+    return out.contiguous()
+
+
+def window_mask_bits(labels):
+    """SW-MSA region labels int8 [windows_per_image, T] -> int64 [windows_per_image, T]: bit j of word (w, i) = [label_i != label_j]"""
+    lab = labels.long()
+    ne = (lab.unsqueeze(2) != lab.unsqueeze(1)).long()                      # [wpi, T(i), T(j)]
+    sh = torch.arange(lab.shape[1], device=lab.device, dtype=torch.int64)
+    return (ne << sh.reshape(1, 1, -1)).sum(dim=2).contiguous()              # T <= 63 bits set: no sign issue below bit 63
+
+
 def window_attention_args(qkv, out, n_windows, T, H, dh, windows_per_image, score_mult, s_attn1, s_attn2, bias, labels, mask_code,
-                          mask_exp_int, out_mult, lut_dev, out_row_map=None):
+                          mask_exp_int, out_mult, lut_dev, out_row_map=None, bias_codes=None, bias_scale=0.0, mask_bits=None):
     a = WindowAttentionArgs()
     a.n_windows, a.T, a.H, a.dh, a.windows_per_image = n_windows, T, H, dh, windows_per_image
     a.qkv, a.out = ptr(qkv), ptr(out)
     a.score_mult, a.s_attn1, a.s_attn2 = float(score_mult), float(s_attn1), float(s_attn2)
     a.bias, a.labels, a.mask_code, a.mask_exp_int = ptr(bias), ptr(labels), int(mask_code), int(mask_exp_int)
     a.out_mult, a.lut_dev, a.out_row_map = float(out_mult), ptr(lut_dev), ptr(out_row_map)
+    a.bias_codes, a.bias_scale, a.mask_bits = ptr(bias_codes), float(bias_scale), ptr(mask_bits)
     return a
 
 
-def window_attention(args):
-    check(_lib.load().p2v_window_attention_i8(C.byref(args), stream()), "window_attention_i8")
+def window_attention(args, simt=False):
+    lib = _lib.load()
+    fn = lib.p2v_window_attention_i8_simt if simt else lib.p2v_window_attention_i8
+    check(fn(C.byref(args), stream()), "window_attention_i8")
 
 
 def gather_rows(x, out, src_rows, rows_out, segs, Cn):

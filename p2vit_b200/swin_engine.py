@@ -117,11 +117,15 @@ class SwinPlan:
                 p["score_mult"] = float(sq.double() * sq.double() * a.scale / sa1.double())
                 p["s_attn1"], p["s_attn2"] = float(sa1), float(sa2)
                 table = a.relative_position_bias_table.detach().float()
-                table_hat = (table / st_).round().clamp(-128, 127) * st_
+                table_codes = (table / st_).round().clamp(-128, 127)
+                table_hat = table_codes * st_
                 p["bias"] = a.relative_position_bias(table_hat).contiguous()
+                # the same table as int8 codes for the tensor-core kernel: bias[h,i,j] == fl(code * s_table)
+                p["bias_codes"] = ops.window_bias_codes(a.relative_position_bias(table_codes).to(torch.int8))
+                p["bias_scale"] = float(st_)
                 p["out_mult"] = float(sq.double() / sa3.double() / 32768.0)
                 p["lut"] = intmath.lut_to_device(intmath.build_softmax_lut(sa2), dev)
-                p["mask_code"], p["mask_exp"], p["labels"] = 0, 0, None
+                p["mask_code"], p["mask_exp"], p["labels"], p["mask_bits"] = 0, 0, None, None
                 if blk.shift_size > 0:
                     sf = sa2.float().cpu().reshape(())
                     x0 = torch.floor(-0.6931 / sf)
@@ -137,6 +141,7 @@ class SwinPlan:
                             lab[:, hs, wsl, :] = cnt
                             cnt += 1
                     p["labels"] = window_partition(lab, blk.window_size).reshape(-1, T).to(torch.int8).to(dev).contiguous()
+                    p["mask_bits"] = ops.window_mask_bits(p["labels"])
                 p["proj"] = _Gemm(a.proj, a.proj.weight, 8, sa3, dev)
                 p["proj_mid"] = _vec(sa4, C, dev)
                 p["res1_scale"] = _vec(last, C, dev)
@@ -176,8 +181,9 @@ class SwinPlan:
 
 
 class SwinEngine:
-    def __init__(self, model, use_graph=True):
+    def __init__(self, model, use_graph=True, simt=False):
         self.model, self.use_graph = model, use_graph
+        self.simt = simt                # tests only: window attention on the dp4a cross-check kernel
         self.plan, self.programs, self.graphs = None, {}, {}
         self._pixel_luts = {}
 
@@ -235,8 +241,9 @@ class SwinEngine:
                 T = p["T"]
                 wa = ops.window_attention_args(qkv, ao, R // T, T, st["heads"], p["dh"], (H // p["ws"]) ** 2, p["score_mult"], p["s_attn1"],
                                                p["s_attn2"], p["bias"], p["labels"], p["mask_code"], p["mask_exp"], p["out_mult"], p["lut"],
-                                               out_row_map=to_tok)      # window_reverse + roll in the store: `ao` is in token order
-                steps.append((pre + "attn.qact3", (lambda wa=wa: ops.window_attention(wa))))
+                                               out_row_map=to_tok,      # window_reverse + roll in the store: `ao` is in token order
+                                               bias_codes=p["bias_codes"], bias_scale=p["bias_scale"], mask_bits=p["mask_bits"])
+                steps.append((pre + "attn.qact3", (lambda wa=wa, simt=self.simt: ops.window_attention(wa, simt=simt))))
                 gp = p["proj"]
                 steps.append((pre + "qact2", gemm(ops.gemm_args(ao, gp.W, ops.EPI_RESIDUAL, gp.acc_scale, bias=gp.bias, out_scale=p["proj_out"],
                                                                 mid_scale=p["proj_mid"], res_scale=p["res1_scale"], res=ra, out_i8=rb,
