@@ -307,6 +307,24 @@ int p2v_quant_mse_scores(const float* x, int64_t n, int C, int64_t inner, const 
 int p2v_radix_hist_f32(const float* x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value, int shift, int nbits,
                        unsigned long long* hist, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * fp32 GEMMs on the CUDA cores (csrc/sgemm.cu) - the two places whose operands are genuinely fp32.
+ *
+ * Weight power-of-two search of MinmaxObserver (observer/minmax.py:145-207): the reference's score of candidate k for output
+ * channel j is  sum_rows (layer(x; W)[., j] - layer(x; fq_k(W))[., j])^2  =  sum_rows (x . D[j, :])^2  with D = W - fq_k(W).
+ * D: fp32 [n, K] (the difference rows of every candidate stacked); out: double [n] = per-row-of-D sums over the M calibration
+ * rows.  x: fp32 [M, K], or (patch > 0) an NCHW image [B, Cin, H, W] whose k = stride = patch patches are the rows (QConv2d).
+ * scratch: >= p2v_linear_sqerr_scratch_bytes(M, n) bytes; row blocks are folded in a fixed order (bit-reproducible).
+ * ------------------------------------------------------------------------------------------- */
+int64_t p2v_linear_sqerr_scratch_bytes(int M, int n);
+int p2v_linear_sqerr_scores(const float* x, int M, int K, int patch, int Cin, int H, int W, const float* D, int n, double* out,
+                            double* scratch, void* stream);
+/* ViT-Large stem (vit_fquant.py:1063 input_quant=False; layers_quant.py:486-489): fp32 pixels x dequantized weights w_hat [N, K]
+ * + bias, then the P2V_EPI_EMBED chain (patch_embed.qact -> qact_embed -> + pos -> qact1) with IEEE divisions;
+ * out: int8 [B*(T+1), N], rows b*(T+1) + tok + 1 (the class rows are p2v_fill_cls_rows'). */
+int p2v_embed_f32(const float* img, int B, int Cin, int H, int W, int P, const float* w_hat, const float* bias, int N, float mid_scale,
+                  float mid_zp, float aux_scale, float aux_zp, const float* pos, const float* out_scale, int8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

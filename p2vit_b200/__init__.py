@@ -13,7 +13,7 @@ from .vit import (VisionTransformer, deit_base_patch16_224, deit_small_patch16_2
 from .swin import (SwinTransformer, swin_base_patch4_window7_224, swin_small_patch4_window7_224,  # noqa: F401
                    swin_tiny_patch4_window7_224)
 from .runner import build_model, calibrate_model, str2model, validate  # noqa: F401
-from . import checkpoint, data, search, synth  # noqa: F401
+from . import checkpoint, data, hessian, search, synth  # noqa: F401
 from .checkpoint import load_checkpoint, load_weights_from_npz  # noqa: F401
 
 __version__ = "0.1.0"

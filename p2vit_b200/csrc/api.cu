@@ -87,6 +87,12 @@ int64_t mse_scratch_bytes(int64_t n, int C, int64_t inner, int K, int per_channe
 int launch_radix_hist(const float* x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value, int shift, int nbits,
                       unsigned long long* hist, cudaStream_t stream);
 
+struct SgemmEmbed { const float* bias; const float* pos; const float* out_scale; float mid_scale, mid_zp, aux_scale, aux_zp; int tokens_per_image; int8_t* out; };
+int64_t linear_sqerr_scratch_bytes(int M, int n);
+int launch_linear_sqerr(const float* x, int M, int K, int patch, int Cin, int H, int W, const float* D, int n, double* out, double* scratch,
+                        cudaStream_t stream);
+int launch_embed_f32(const float* img, int B, int Cin, int H, int W, int P, const float* w_hat, int N, const SgemmEmbed& ep, cudaStream_t stream);
+
 static int validate_gemm(const p2v_gemm_args* a) {
   P2V_REQUIRE(a != nullptr, "gemm: null args");
   P2V_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
@@ -240,6 +246,24 @@ int p2v_quant_mse_scores(const float* x, int64_t n, int C, int64_t inner, const 
   P2V_REQUIRE(x && scales && out && scratch && n > 0 && C > 0 && inner > 0 && K > 0 && K <= 96, "mse_scores: bad arguments (K <= 96)");
   P2V_REQUIRE(n_scale == 1 || n_scale == C, "mse_scores: n_scale must be 1 or C");
   return launch_mse_scores(x, n, C, inner, scales, zps, K, n_scale, per_channel_out, lo, hi, out, scratch, (cudaStream_t)stream);
+}
+int64_t p2v_linear_sqerr_scratch_bytes(int M, int n) { return (M > 0 && n > 0) ? linear_sqerr_scratch_bytes(M, n) : 0; }
+int p2v_linear_sqerr_scores(const float* x, int M, int K, int patch, int Cin, int H, int W, const float* D, int n, double* out,
+                            double* scratch, void* stream) {
+  P2V_REQUIRE(x && D && out && scratch && M > 0 && K > 0 && n > 0 && K % 4 == 0, "linear_sqerr: bad arguments (K %% 4 == 0)");
+  P2V_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(D)) & 15) == 0, "linear_sqerr: 16-byte alignment");
+  if (patch > 0) P2V_REQUIRE(patch % 4 == 0 && Cin > 0 && H % patch == 0 && W % patch == 0 && K == Cin * patch * patch &&
+                             M % ((H / patch) * (W / patch)) == 0, "linear_sqerr: bad patch geometry");
+  return launch_linear_sqerr(x, M, K, patch, Cin, H, W, D, n, out, scratch, (cudaStream_t)stream);
+}
+int p2v_embed_f32(const float* img, int B, int Cin, int H, int W, int P, const float* w_hat, const float* bias, int N, float mid_scale,
+                  float mid_zp, float aux_scale, float aux_zp, const float* pos, const float* out_scale, int8_t* out, void* stream) {
+  P2V_REQUIRE(img && w_hat && bias && pos && out_scale && out && B > 0 && Cin > 0 && P > 0 && P % 4 == 0 && H % P == 0 && W % P == 0 && N % 4 == 0,
+              "embed_f32: bad arguments (P %% 4 == 0, N %% 4 == 0)");
+  P2V_REQUIRE(((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(w_hat)) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+              "embed_f32: alignment");
+  SgemmEmbed ep{bias, pos, out_scale, mid_scale, mid_zp, aux_scale, aux_zp, (H / P) * (W / P), out};
+  return launch_embed_f32(img, B, Cin, H, W, P, w_hat, N, ep, (cudaStream_t)stream);
 }
 int p2v_radix_hist_f32(const float* x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value, int shift, int nbits,
                        unsigned long long* hist, void* stream) {

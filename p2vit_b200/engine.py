@@ -96,6 +96,7 @@ class VitPlan:
             self.w_embed_hat = (codes.float() * ws.reshape(-1, 1)).contiguous()
             self.b_embed = pe.proj.bias.detach().float().contiguous()
         self.s_pe = _vec(s_pe, 1, dev)
+        self.s_pe_f = float(s_pe)
         self.s_e = float(s_e)
         self.s_e_vec = _vec(s_e, 1, dev)
         s0 = _vec(_sym_scale(m.qact1, "qact1"), D, dev)
@@ -243,16 +244,11 @@ class VitEngine:
                                                             mid_scale=pl.s_pe, pos=pl.pos_hat, aux_scale=pl.s_e, tokens_per_image=T,
                                                             out_i8=ws["ra"], zp_corr=g.zp_corr, mid_zp=pl.z_pe, aux_zp=pl.z_e))))
         else:
-            def embed_fp32():
-                P, gs = pl.P, int(round(T ** 0.5))
-                rows = ws["img"].reshape(B, 3, gs, P, gs, P).permute(0, 2, 4, 1, 3, 5).reshape(B * T, 3 * P * P)
-                y = torch.nn.functional.linear(rows, pl.w_embed_hat, pl.b_embed).reshape(B, T, D)
-                y = ops.fake_quant(y, pl.s_pe, pl.z_pe)                             # patch_embed.qact
-                y = ops.fake_quant(y, pl.s_e_vec, pl.z_e)                           # qact_embed (class row handled by `cls`)
-                y = y + pl.pos_hat[1:].reshape(1, T, D)
-                ws["ra"].reshape(B, T + 1, D)[:, 1:].copy_(ops.quantize(y.contiguous(), pl.s_r0))   # qact1 (PTF)
+            # ViT-L: fp32 pixels x dequantized weights on the CUDA cores (csrc/sgemm.cu), patch gather and the whole
+            # patch_embed.qact -> qact_embed -> + pos -> qact1 chain fused; the graph holds no library kernel
             steps.append(("patchify", lambda: None))
-            steps.append(("embed", embed_fp32))
+            steps.append(("embed", lambda: ops.embed_f32(ws["img"], pl.P, pl.w_embed_hat, pl.b_embed, pl.s_pe_f, pl.z_pe, pl.s_e, pl.z_e,
+                                                         pl.pos_hat, pl.s_r0, ws["ra"])))
         steps.append(("cls", lambda: ops.fill_cls_rows(ws["ra"], pl.cls_row, B, T, D)))
         for i, p in enumerate(pl.blocks):
             pre = "blocks.%d." % i
@@ -304,7 +300,7 @@ class VitEngine:
         return lambda: ops.layernorm(a)
 
     def launches_per_forward(self, bit_config):
-        return 5 + 7 * self.model.depth
+        return (5 if self.model.input_quant else 4) + 7 * self.model.depth
 
     def static_input(self, B, bit_config):
         """the fp32 image buffer the program reads; copy a batch into it (e.g. straight from pinned host memory) and call

@@ -265,6 +265,32 @@ def quant_mse_scores(x, scales, lo, hi, zero_points=None, per_channel_out=False)
     return out
 
 
+def linear_sqerr_scores(x, D, patch=0):
+    """double [n]: sum over the rows of x of (x . D[j, :])^2 for every row j of D (fp32 [n, K]).  x: fp32 [M, K], or with patch > 0
+    an NCHW image whose k = stride = patch patches are the rows.  (csrc/sgemm.cu; observer/minmax.py:145-207)"""
+    x = x.detach().contiguous().float()
+    D = D.detach().contiguous().float()
+    n, K = D.shape
+    if patch:
+        B, Cin, H, W = x.shape
+        M = B * (H // patch) * (W // patch)
+    else:
+        Cin = H = W = 0
+        M = x.numel() // K
+    lib = _lib.load()
+    out = torch.empty(n, dtype=torch.float64, device=x.device)
+    scratch = torch.empty(max(1, lib.p2v_linear_sqerr_scratch_bytes(M, n) // 8), dtype=torch.float64, device=x.device)
+    check(lib.p2v_linear_sqerr_scores(ptr(x), M, K, int(patch), Cin, H, W, ptr(D), n, ptr(out), ptr(scratch), stream()), "linear_sqerr_scores")
+    return out
+
+
+def embed_f32(img, patch, w_hat, bias, mid_scale, mid_zp, aux_scale, aux_zp, pos, out_scale, out):
+    """ViT-L stem: fp32 image -> int8 residual rows (class rows excluded), see include/p2vit_b200.h: p2v_embed_f32"""
+    B, Cin, H, W = img.shape
+    check(_lib.load().p2v_embed_f32(ptr(img), B, Cin, H, W, int(patch), ptr(w_hat), ptr(bias), w_hat.shape[0], float(mid_scale), float(mid_zp),
+                                    float(aux_scale), float(aux_zp), ptr(pos), ptr(out_scale), ptr(out), stream()), "embed_f32")
+
+
 def radix_hist(flat, prefix_mask, prefix_value, shift, nbits):
     """one radix-select pass over a flat fp32 CUDA tensor: int64 [2^nbits] counts of the digit (key >> shift) among the elements
     whose order key matches the prefix (include/p2vit_b200.h: p2v_radix_hist_f32)"""

@@ -3,11 +3,11 @@
 The reference evaluates, per output channel and in a Python loop, four candidate exponents
 floor(log2 s) + {-1,0,1,2} by fake-quantising and re-running the layer (5 tiny F.linear per channel).
 Here the same scores are produced for all channels at once: activations through the block-reduce kernel
-`p2v_quant_mse_scores`, weights through 5 dense fp32 GEMMs (cuBLAS via torch) + a column reduction.
+`p2v_quant_mse_scores`, weights through one launch of the fp32 GEMM + column-square-sum kernel (csrc/sgemm.cu) on
+the stacked candidate differences W - fq_k(W).
 Scores are all-reduced over ranks before the arg-min so every rank picks identical exponents.
 """
 import torch
-from torch.nn import functional as F
 
 from ... import ops
 from .base import BaseObserver
@@ -50,25 +50,24 @@ class MinmaxObserver(BaseObserver):
         return scale, zero_point
 
     def _weight_scores(self, x, others, cand_scales, zp_f, qmin, qmax):
-        """score[k, j] = sum over calibration rows of (layer(x; W)[., j] - layer(x; fq_k(W))[., j])^2, reduced over j
-        when layer_wise (minmax.py:82-141,165-201)."""
-        w = self.v.detach()
+        """score[k, j] = sum over calibration rows of (layer(x; W)[., j] - layer(x; fq_k(W))[., j])^2, reduced over j when
+        layer_wise (minmax.py:82-141,165-201).  The two layer outputs differ by x . (W - fq_k(W))[j, :] (the bias cancels), so
+        the four candidates' difference rows are stacked and ONE launch of the fp32 GEMM + column-square-sum kernel
+        (csrc/sgemm.cu) returns all scores; the [rows, 4 Cout] product is never written."""
+        w = self.v.detach().float()
         wm = w.reshape(w.shape[0], -1)
-        bias = others[0] if others and others[0] is not None else None
+        patch = 0
         if self.module_type == "conv_weight":
-            stride = others[1]
-            k = w.shape[-1]
+            stride, k = others[1], w.shape[-1]
             assert tuple(stride) == (k, k) and tuple(others[2]) == (0, 0), "QConv2d is the patch-embed conv (kernel == stride)"
-            B, Cin, H, W_ = x.shape
-            xm = x.reshape(B, Cin, H // k, k, W_ // k, k).permute(0, 2, 4, 1, 3, 5).reshape(-1, Cin * k * k)
+            patch, xm = k, x
         else:
             xm = x.reshape(-1, x.shape[-1])
-        ref = F.linear(xm, wm, bias)
         zp = 0.0 if zp_f is None else zp_f.reshape(-1, 1)
-        out = []
-        for kidx in range(cand_scales.shape[0]):
+        K4 = cand_scales.shape[0]
+        diffs = []
+        for kidx in range(K4):
             s = cand_scales[kidx].reshape(-1, 1)
-            wq = ((wm / s + zp).round().clamp(qmin, qmax) - zp) * s
-            d = (ref - F.linear(xm, wq, bias)).double().pow(2)
-            out.append(d.sum(0) if self.calibration_mode == "channel_wise" else d.sum().reshape(1))
-        return torch.stack(out)
+            diffs.append(wm - ((wm / s + zp).round().clamp(qmin, qmax) - zp) * s)
+        sc = ops.linear_sqerr_scores(xm, torch.cat(diffs, dim=0), patch=patch).reshape(K4, wm.shape[0])
+        return sc if self.calibration_mode == "channel_wise" else sc.sum(dim=1, keepdim=True)

@@ -557,6 +557,27 @@ def test_mixed_precision_search_flow():
         assert runner.validate(m, batches, cfg)[1] == acc            # deterministic: the memoised score is reproducible
 
 
+def test_hessian_sensitivity_feeds_the_search():
+    """Hutchinson traces of the FP model on the GPU (fp32 autograd), normalised as test_quant.py:184-201, are
+    the `sensitivity` vector of the mixed-precision ranking (test_quant.py:350-368)"""
+    from p2vit_b200 import hessian, runner, search
+    m = build_model("vit_micro", Config(), seed=0, device="cuda")
+    crit = torch.nn.CrossEntropyLoss()
+    torch.manual_seed(0)
+    traces = []
+    for i in range(2):
+        x = synth.synth_images(4, seed=40 + i).cuda()
+        names, tr = hessian.hessian_traces(m, crit, x, torch.tensor([1, 2, 3, 4], device="cuda"), max_iter=6)
+        traces.append(tr)
+    sens = hessian.mean_normalised_sensitivity(traces)
+    n = 4 * m.depth + 2
+    assert len(sens) == n - 1 and min(sens) >= 0.0 and max(sens) <= 1.0
+    (_, flops, gdist), _ = runner.calibrate_model(m, synth.synth_images(8, seed=3).cuda())
+    cands = [[8] * n, [8] + [4] * (n - 1), [8, 4, 4] + [8] * (n - 3)]
+    ranked = search.rank_by_sensitivity(cands, search.distance_columns(gdist), sens)
+    assert [o for _, o in ranked] == sorted(o for _, o in ranked) and ranked[0][0] == [8] * n
+
+
 def test_uint8_pixels_equal_host_normalised_fp32(golden):
     """`model(x_u8)` after set_pixel_normalization == `model(Normalize(ToTensor(x_u8)))`: logits bit for bit, through the graph
     and the eager engine; without the normalisation constants the byte input is refused"""

@@ -712,3 +712,26 @@ def test_mse_scores_are_bit_reproducible():
     ref = torch.stack([((x - (x / s).round().clamp(-128, 127) * s) ** 2).double().sum() for s in cand.reshape(-1)])
     assert torch.allclose(a.reshape(-1), ref, rtol=1e-6)
     assert torch.allclose(pc.sum(1), ref, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ fp32 GEMM kernels (csrc/sgemm.cu)
+@pytest.mark.parametrize("M,K,n", [(788, 384, 1536), (300, 48, 96), (1000, 1024, 260), (6304, 768, 4 * 768)])
+def test_linear_sqerr_scores_vs_torch(M, K, n):
+    """p2v_linear_sqerr_scores: per-row-of-D column sums of squares of x D^T against torch in float64; bit-reproducible"""
+    torch.manual_seed(M + n)
+    x = torch.randn(M, K, device="cuda")
+    D = torch.randn(n, K, device="cuda") * 0.01
+    got = ops.linear_sqerr_scores(x, D)
+    ref = (x.double() @ D.double().T).pow(2).sum(0)
+    assert torch.allclose(got, ref, rtol=2e-5), float(((got - ref).abs() / ref).max())
+    assert torch.equal(got, ops.linear_sqerr_scores(x, D))
+
+
+def test_linear_sqerr_scores_patch_rows():
+    """patch > 0: the rows are the k = stride = P patches of an NCHW image (QConv2d weight search, layers.py:62-85)"""
+    torch.manual_seed(1)
+    img = torch.randn(3, 3, 224, 224, device="cuda")
+    D = torch.randn(128, 3 * 16 * 16, device="cuda") * 0.01
+    rows = img.reshape(3, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(-1, 768)
+    ref = (rows.double() @ D.double().T).pow(2).sum(0)
+    assert torch.allclose(ops.linear_sqerr_scores(img, D, patch=16), ref, rtol=2e-5)
