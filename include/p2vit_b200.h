@@ -319,6 +319,11 @@ int p2v_radix_hist_f32(const float* x, int64_t n, uint32_t prefix_mask, uint32_t
 int64_t p2v_linear_sqerr_scratch_bytes(int M, int n);
 int p2v_linear_sqerr_scores(const float* x, int M, int K, int patch, int Cin, int H, int W, const float* D, int n, double* out,
                             double* scratch, void* stream);
+/* The FP layer itself, out[M, N] = x W^T + bias (bias may be NULL): QLinear / QConv2d before model_quant() - the calibration
+ * forward (layers.py:87,173; test_quant.py:275-281).  Every output element is one ascending-k FMA chain whatever M is, so the
+ * activations - and with them every observer statistic - do not depend on how the calibration batch is split over GPUs. */
+int p2v_linear_f32(const float* x, int M, int K, int patch, int Cin, int H, int W, const float* Wt, const float* bias, int N, float* out,
+                   void* stream);
 /* ViT-Large stem (vit_fquant.py:1063 input_quant=False; layers_quant.py:486-489): fp32 pixels x dequantized weights w_hat [N, K]
  * + bias, then the P2V_EPI_EMBED chain (patch_embed.qact -> qact_embed -> + pos -> qact1) with IEEE divisions;
  * out: int8 [B*(T+1), N], rows b*(T+1) + tok + 1 (the class rows are p2v_fill_cls_rows'). */

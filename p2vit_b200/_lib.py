@@ -98,6 +98,7 @@ SYMBOLS = {
     "p2v_quant_mse_scores": (_I, [_P, _I64, _I, _I64, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "p2v_linear_sqerr_scratch_bytes": (_I64, [_I, _I]),
     "p2v_linear_sqerr_scores": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "p2v_linear_f32": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "p2v_embed_f32": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _F, _F, _F, _F, _P, _P, _P, _P]),
     "p2v_radix_hist_f32": (_I, [_P, _I64, C.c_uint32, C.c_uint32, _I, _I, _P, _P]),
 }

@@ -87,11 +87,13 @@ int64_t mse_scratch_bytes(int64_t n, int C, int64_t inner, int K, int per_channe
 int launch_radix_hist(const float* x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value, int shift, int nbits,
                       unsigned long long* hist, cudaStream_t stream);
 
-struct SgemmEmbed { const float* bias; const float* pos; const float* out_scale; float mid_scale, mid_zp, aux_scale, aux_zp; int tokens_per_image; int8_t* out; };
+struct SgemmEmbed { const float* bias; float* out_f32; const float* pos; const float* out_scale; float mid_scale, mid_zp, aux_scale, aux_zp; int tokens_per_image; int8_t* out; };
 int64_t linear_sqerr_scratch_bytes(int M, int n);
 int launch_linear_sqerr(const float* x, int M, int K, int patch, int Cin, int H, int W, const float* D, int n, double* out, double* scratch,
                         cudaStream_t stream);
 int launch_embed_f32(const float* img, int B, int Cin, int H, int W, int P, const float* w_hat, int N, const SgemmEmbed& ep, cudaStream_t stream);
+int launch_linear_f32(const float* x, int M, int K, int patch, int Cin, int H, int W, const float* Wt, const float* bias, int N, float* out,
+                      cudaStream_t stream);
 
 static int validate_gemm(const p2v_gemm_args* a) {
   P2V_REQUIRE(a != nullptr, "gemm: null args");
@@ -256,13 +258,21 @@ int p2v_linear_sqerr_scores(const float* x, int M, int K, int patch, int Cin, in
                              M % ((H / patch) * (W / patch)) == 0, "linear_sqerr: bad patch geometry");
   return launch_linear_sqerr(x, M, K, patch, Cin, H, W, D, n, out, scratch, (cudaStream_t)stream);
 }
+int p2v_linear_f32(const float* x, int M, int K, int patch, int Cin, int H, int W, const float* Wt, const float* bias, int N, float* out,
+                   void* stream) {
+  P2V_REQUIRE(x && Wt && out && M > 0 && K > 0 && N > 0 && K % 4 == 0, "linear_f32: bad arguments (K %% 4 == 0)");
+  P2V_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Wt)) & 15) == 0, "linear_f32: 16-byte alignment");
+  if (patch > 0) P2V_REQUIRE(patch % 4 == 0 && Cin > 0 && H % patch == 0 && W % patch == 0 && K == Cin * patch * patch &&
+                             M % ((H / patch) * (W / patch)) == 0, "linear_f32: bad patch geometry");
+  return launch_linear_f32(x, M, K, patch, Cin, H, W, Wt, bias, N, out, (cudaStream_t)stream);
+}
 int p2v_embed_f32(const float* img, int B, int Cin, int H, int W, int P, const float* w_hat, const float* bias, int N, float mid_scale,
                   float mid_zp, float aux_scale, float aux_zp, const float* pos, const float* out_scale, int8_t* out, void* stream) {
   P2V_REQUIRE(img && w_hat && bias && pos && out_scale && out && B > 0 && Cin > 0 && P > 0 && P % 4 == 0 && H % P == 0 && W % P == 0 && N % 4 == 0,
               "embed_f32: bad arguments (P %% 4 == 0, N %% 4 == 0)");
   P2V_REQUIRE(((reinterpret_cast<uintptr_t>(img) | reinterpret_cast<uintptr_t>(w_hat)) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
               "embed_f32: alignment");
-  SgemmEmbed ep{bias, pos, out_scale, mid_scale, mid_zp, aux_scale, aux_zp, (H / P) * (W / P), out};
+  SgemmEmbed ep{bias, nullptr, pos, out_scale, mid_scale, mid_zp, aux_scale, aux_zp, (H / P) * (W / P), out};
   return launch_embed_f32(img, B, Cin, H, W, P, w_hat, N, ep, (cudaStream_t)stream);
 }
 int p2v_radix_hist_f32(const float* x, int64_t n, uint32_t prefix_mask, uint32_t prefix_value, int shift, int nbits,

@@ -36,7 +36,8 @@ __device__ __forceinline__ float4 sg_load_a(const SgemmA& a, int row, int k) {
 }
 
 struct SgemmEmbed {      // EMBED epilogue on an fp32 accumulator (include/p2vit_b200.h: P2V_EPI_EMBED), zero points included
-  const float* bias;
+  const float* bias;         // (MODE 2: bias or NULL, out_f32 the [M, N] result)
+  float* out_f32;
   const float* pos;          // [(T+1), N]
   const float* out_scale;    // [N]
   float mid_scale, mid_zp, aux_scale, aux_zp;
@@ -44,7 +45,7 @@ struct SgemmEmbed {      // EMBED epilogue on an fp32 accumulator (include/p2vit
   int8_t* out;               // [B*(T+1), N]
 };
 
-template <int MODE>      // 0: column sums of squares -> part[blockIdx.y][n];  1: EMBED epilogue
+template <int MODE>      // 0: column sums of squares -> part[blockIdx.y][n];  1: EMBED epilogue;  2: out_f32 = acc + bias
 __global__ void __launch_bounds__(SG_THREADS) sgemm_kernel(SgemmA a, const float* __restrict__ Wt, int N, double* __restrict__ part, SgemmEmbed ep) {
   // operand tiles, and - after the k loop - the MODE 0 reduction buffer over the same bytes
   __shared__ __align__(16) unsigned char sg_smem[2 * 2 * SG_BK * (SG_BM + 4) * 4];
@@ -115,6 +116,19 @@ __global__ void __launch_bounds__(SG_THREADS) sgemm_kernel(SgemmA a, const float
       for (int r = 0; r < 16; ++r) s += red[r][tid];
       if (n0 + tid < N) part[size_t(blockIdx.y) * N + n0 + tid] = s;
     }
+  } else if (MODE == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = m0 + (i < 4 ? 0 : 64) + ty * 4 + (i & 3);
+      if (row >= a.M) continue;
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        const int n = n0 + jh * 64 + tx * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < N) ep.out_f32[size_t(row) * N + n + e] = ep.bias ? fadd(acc[i][jh * 4 + e], __ldg(ep.bias + n + e)) : acc[i][jh * 4 + e];
+      }
+    }
   } else {
     const float e_rsm = fdiv(1.f, ep.mid_scale), e_raux = fdiv(1.f, ep.aux_scale);
     const int T = ep.tokens_per_image;
@@ -164,6 +178,18 @@ int launch_linear_sqerr(const float* x, int M, int K, int patch, int Cin, int H,
   sg_final_kernel<<<std::min((n + 255) / 256, 1024), 256, 0, stream>>>(scratch, out, int(grid.y), n);
   count_launch(2);
   return check_launch("linear_sqerr_scores");
+}
+
+int launch_linear_f32(const float* x, int M, int K, int patch, int Cin, int H, int W, const float* Wt, const float* bias, int N, float* out,
+                      cudaStream_t stream) {
+  SgemmA a{x, M, K, patch, Cin, H, W};
+  SgemmEmbed ep{};
+  ep.bias = bias;
+  ep.out_f32 = out;
+  dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
+  sgemm_kernel<2><<<grid, SG_THREADS, 0, stream>>>(a, Wt, N, nullptr, ep);
+  count_launch();
+  return check_launch("linear_f32");
 }
 
 int launch_embed_f32(const float* img, int B, int Cin, int H, int W, int P, const float* w_hat, int N, const SgemmEmbed& ep, cudaStream_t stream) {

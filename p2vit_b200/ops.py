@@ -284,6 +284,26 @@ def linear_sqerr_scores(x, D, patch=0):
     return out
 
 
+def linear_f32(x, weight, bias=None, patch=0):
+    """x W^T + bias in fp32 on the library's own GEMM (csrc/sgemm.cu): the FP forward of QLinear / QConv2d during calibration.
+    Batch-split invariant (one ascending-k FMA chain per output).  x: [..., K], or with patch > 0 an NCHW image -> [B*T, N]."""
+    x = x.detach().contiguous().float()
+    w = weight.detach().float().reshape(weight.shape[0], -1).contiguous()
+    N, K = w.shape
+    if patch:
+        B, Cin, H, W = x.shape
+        M = B * (H // patch) * (W // patch)
+        shape = (M, N)
+    else:
+        Cin = H = W = 0
+        M = x.numel() // K
+        shape = tuple(x.shape[:-1]) + (N,)
+    b = None if bias is None else bias.detach().float().contiguous()
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    check(_lib.load().p2v_linear_f32(ptr(x), M, K, int(patch), Cin, H, W, ptr(w), ptr(b), N, ptr(out), stream()), "linear_f32")
+    return out.reshape(shape)
+
+
 def embed_f32(img, patch, w_hat, bias, mid_scale, mid_zp, aux_scale, aux_zp, pos, out_scale, out):
     """ViT-L stem: fp32 image -> int8 residual rows (class rows excluded), see include/p2vit_b200.h: p2v_embed_f32"""
     B, Cin, H, W = img.shape

@@ -21,6 +21,15 @@ from .observer.utils import lp_loss
 from .quantizer import build_quantizer
 
 
+def fp_linear(x, weight, bias):
+    """The FP layer.  Calibration / FP evaluation on the GPU (no autograd): the library's own fp32 GEMM - deterministic and
+    batch-split invariant, so a calibration sharded over N GPUs sees exactly the activations one GPU would.  With autograd
+    (Hessian sensitivity pass) or on the CPU (host-logic tests): F.linear."""
+    if x.is_cuda and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)) and weight.shape[-1] % 4 == 0:
+        return ops.linear_f32(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
 def _attach_codes(y, codes, scale, zero_point):
     y._p2v_codes = (codes, scale, zero_point)
     return y
@@ -125,7 +134,10 @@ class QConv2d(nn.Conv2d, _QWeightMixin):
         k = self.kernel_size[0]
         assert self.kernel_size == self.stride and self.padding == (0, 0), "only the patch-embed form is supported"
         B, _, H, W = x.shape
-        y = F.linear(self._patch_rows(x), weight.reshape(weight.shape[0], -1), self.bias)
+        if x.is_cuda and k % 4 == 0 and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)):
+            y = ops.linear_f32(x, weight, self.bias, patch=k)                 # patch gather inside the kernel
+        else:
+            y = F.linear(self._patch_rows(x), weight.reshape(weight.shape[0], -1), self.bias)
         return y.reshape(B, H // k, W // k, -1).permute(0, 3, 1, 2)
 
     def forward(self, x, bit_config):
@@ -160,7 +172,7 @@ class QLinear(nn.Linear, _QWeightMixin):
         if weight_smoothed is None:
             weight_smoothed = self.weight
         if not self.quant:
-            y = F.linear(x, weight_smoothed, self.bias)
+            y = fp_linear(x, weight_smoothed, self.bias)
         if self.calibrate:
             distance = self._calibrate_all_bit_types(weight_smoothed, x, [self.bias], kwargs=dict(attn=attn, attn_para=attn_para))
             global_distance.append(distance)

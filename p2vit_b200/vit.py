@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .ptq import QAct, QConv2d, QIntLayerNorm, QIntSoftmax, QLinear
+from .ptq.layers import fp_linear
 from .ptq.observer.utils import allreduce_, pot_exponent
 
 __all__ = ["deit_tiny_patch16_224", "deit_small_patch16_224", "deit_base_patch16_224", "vit_base_patch16_224",
@@ -65,7 +66,7 @@ class _SmoothedLinear:
             pool.append(cs)
             xs = x / cs.reshape(1, 1, -1)
             ws = lin.weight * cs.reshape(1, -1)
-            gt = F.linear(xs, ws, lin.bias)
+            gt = fp_linear(xs, ws, lin.bias)
             mid = qact0(xs)
             if qact0.last_calibrate:
                 act_scale.append(qact0.quantizer.scale)

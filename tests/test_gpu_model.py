@@ -557,6 +557,18 @@ def test_mixed_precision_search_flow():
         assert runner.validate(m, batches, cfg)[1] == acc            # deterministic: the memoised score is reproducible
 
 
+def test_calibration_forward_is_batch_split_invariant():
+    """The FP forward that feeds the observers (test_quant.py:275-281) gives every image the same activations whatever the
+    batch around it - own fp32 GEMM with a fixed k order instead of a library GEMM whose kernel choice depends on M - so the
+    statistics of a calibration sharded over N GPUs are those of one GPU (raw fp32 scales of ema / percentile / omse included)"""
+    m = build_model("vit_micro", Config(), seed=0, device="cuda")
+    x = synth.synth_images(7, seed=9).cuda()
+    with torch.no_grad():
+        full = m(x)[0]
+        parts = torch.cat([m(x[:3].contiguous())[0], m(x[3:].contiguous())[0]])
+    assert torch.equal(full, parts)
+
+
 def test_hessian_sensitivity_feeds_the_search():
     """Hutchinson traces of the FP model on the GPU (fp32 autograd), normalised as test_quant.py:184-201, are
     the `sensitivity` vector of the mixed-precision ranking (test_quant.py:350-368)"""

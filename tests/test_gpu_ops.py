@@ -735,3 +735,16 @@ def test_linear_sqerr_scores_patch_rows():
     rows = img.reshape(3, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(-1, 768)
     ref = (rows.double() @ D.double().T).pow(2).sum(0)
     assert torch.allclose(ops.linear_sqerr_scores(img, D, patch=16), ref, rtol=2e-5)
+
+
+def test_linear_f32_vs_torch_and_batch_split():
+    """p2v_linear_f32 (the FP layer of the calibration forward): equals torch in fp32 accuracy, and every row's result is
+    independent of how many rows are in the launch (the property that makes an N-GPU calibration see the 1-GPU activations)"""
+    torch.manual_seed(2)
+    x = torch.randn(777, 384, device="cuda")
+    w, b = torch.randn(1000, 384, device="cuda") * 0.05, torch.randn(1000, device="cuda")
+    y = ops.linear_f32(x, w, b)
+    ref = (x.double() @ w.double().T + b.double())
+    assert float((y.double() - ref).abs().max()) < 1e-4
+    assert torch.equal(y[:130], ops.linear_f32(x[:130].contiguous(), w, b)) and torch.equal(y[130:], ops.linear_f32(x[130:].contiguous(), w, b))
+    assert torch.equal(ops.linear_f32(x, w), ops.linear_f32(x, w, torch.zeros_like(b)))
