@@ -35,7 +35,7 @@ constexpr uint32_t WT_P_PLANE = 128 * 128;
 constexpr uint32_t WT_OFF_LUT = WT_OFF_P + 2 * WT_P_PLANE;   // 256 x {hi, lo, exp_f32, 1 / exp_f32}
 constexpr uint32_t WT_BIAS_PITCH = 80;                       // bias-code row pitch (p2v_window_attention_args.bias_codes): 16-byte row reads of 8 lanes hit 8 distinct bank groups
 constexpr uint32_t WT_BIAS_SLOT = 64 * WT_BIAS_PITCH;        // int8 bias codes of one head (T <= 64 rows)
-constexpr uint32_t WT_OFF_BIAS = WT_OFF_LUT + 4096;
+constexpr uint32_t WT_OFF_BIAS = WT_OFF_LUT + 4224;             // 257 table entries of 16 bytes, padded
 constexpr uint32_t WT_OFF_BARS = WT_OFF_BIAS + 2 * WT_BIAS_SLOT;
 constexpr uint32_t WT_SMEM = WT_OFF_BARS + 64;
 constexpr size_t WT_SMEM_ALLOC = WT_SMEM + 1024;             // + alignment slack
@@ -53,7 +53,7 @@ struct WinTcParams {
   int8_t* out;
 };
 
-template <bool POT2>
+template <bool POT2, bool MASK>
 __global__ void __launch_bounds__(WT_THREADS, 3)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, WinTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -72,9 +72,13 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, WinTcParam
     fence_mbar_init();
   }
   if (warp == 4) tmem_alloc<WT_TMEM_COLS>(base + WT_OFF_BARS + 48);
-  for (int i = threadIdx.x; i < 256; i += WT_THREADS) {
-    const float e = p.lut->exp_f32[i];
-    s_lut[i] = make_uint4(p.lut->hi[i], p.lut->lo[i], __float_as_uint(e), __float_as_uint(fdiv(1.0f, e)));
+  // table entry d = max - x: {exp_int hi, lo, exp_int as fp32, its reciprocal}; entry 256 = the clamped tail of int_exp that
+  // every masked score lands on (the host checks mask_code reaches it), so the lookup needs no branch: d = min(max - x, 256)
+  for (int i = threadIdx.x; i < 257; i += WT_THREADS) {
+    const bool tail = i == 256 && MASK;            // (without a mask entry 256 only serves the padding keys of a partial chunk: a copy of 255)
+    const int k = min(i, 255);
+    const float e = tail ? float(p.e_mask) : p.lut->exp_f32[k];
+    s_lut[i] = make_uint4(tail ? 0u : p.lut->hi[k], tail ? p.e_mask : p.lut->lo[k], __float_as_uint(e), __float_as_uint(fdiv(1.0f, e)));
   }
   for (uint32_t i = threadIdx.x; i < 2 * WT_P_PLANE / 16; i += WT_THREADS)       // off-diagonal blocks and key padding of P stay zero
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + WT_OFF_P + i * 16u), "r"(0u) : "memory");
@@ -141,23 +145,31 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, WinTcParam
     const uint32_t tlane = tmem_base + ((uint32_t(warp) * 32u) << 16);
     const uint32_t lut32 = base + WT_OFF_LUT;
     const float r2 = fdiv(1.0f, p.s_attn2);
-    const float e_mask_f = float(p.e_mask), r_mask = fdiv(1.0f, e_mask_f);
     constexpr float LO = RMAGIC - 128.f, HI = RMAGIC + 127.f;
     const uint32_t prow = base + WT_OFF_P + uint32_t(r) * 128u;
     const uint32_t sw = uint32_t(r & 7);
+    const int nfull = T >> 4, rem = T & 15;          // key chunks of 16: nfull complete ones, then one with `rem` valid keys
     uint32_t n = 0;
     for (int unit = blockIdx.x; unit < p.units; unit += gridDim.x, ++n) {
       const int pair = unit / H, h = unit % H;
       const int win = 2 * pair + w;
       const bool live = i < T && win < p.n_windows;
-      // ---- this head's bias codes into the slot of this unit (row pitch 64); slot n&1 was last read two units ago
+      // ---- this head's bias codes into the slot of this unit, as code + 128 (unsigned bytes decode with one PRMT + FADD);
+      //      slot n&1 was last read two units ago
       {
         uint4* slot = reinterpret_cast<uint4*>(gbase + WT_OFF_BIAS + (n & 1u) * WT_BIAS_SLOT);
         const uint4* src = reinterpret_cast<const uint4*>(p.bias_codes + size_t(h) * T * WT_BIAS_PITCH);
-        for (int e = threadIdx.x; e < T * int(WT_BIAS_PITCH / 16); e += 128) slot[e] = __ldg(src + e);
+        for (int e = threadIdx.x; e < T * int(WT_BIAS_PITCH / 16); e += 128) {
+          uint4 v = __ldg(src + e);
+          v.x ^= 0x80808080u; v.y ^= 0x80808080u; v.z ^= 0x80808080u; v.w ^= 0x80808080u;
+          slot[e] = v;
+        }
       }
-      unsigned long long mbits = 0ull;
-      if (p.mask_bits != nullptr && live) mbits = __ldg(p.mask_bits + size_t(win % p.wpi) * T + i);
+      uint32_t mlo = 0u, mhi = 0u;
+      if (MASK && live) {
+        const unsigned long long mb = __ldg(p.mask_bits + size_t(win % p.wpi) * T + i);
+        mlo = uint32_t(mb); mhi = uint32_t(mb >> 32);
+      }
       named_barrier(1, 128);                        // bias slot complete; every row is done with the unit before the last
       const uint8_t* brow = gbase + WT_OFF_BIAS + (n & 1u) * WT_BIAS_SLOT + i * WT_BIAS_PITCH;
       mbar_wait(bar_s, n & 1u);
@@ -167,93 +179,91 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, WinTcParam
       for (int c = 0; c < 4; ++c) tmem_ld16_async(tlane + uint32_t(w) * 64u + c * 16, x[c]);
       tmem_wait_ld();
       if (live) {
-        // ---- pass A: scores -> qact_attn1 -> + bias -> qact2 -> + mask; row max
+        // ---- pass A: scores -> qact_attn1 -> + bias -> qact2 -> + mask; row max.  Straight-line code per chunk: a complete chunk
+        //      has no per-element tests at all, the last one replaces its padding keys after the fact.
         int mx = INT_MIN;
+        auto pass_a = [&](auto partial, auto cc) {
+          constexpr int c = decltype(cc)::value;
+          const uint4 b16 = *reinterpret_cast<const uint4*>(brow + c * 16);
+          const uint32_t bw[4] = {b16.x, b16.y, b16.z, b16.w};
+          const uint32_t mword = c < 2 ? mlo : mhi;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c * 16 < T) {
-            const uint4 b16 = *reinterpret_cast<const uint4*>(brow + c * 16);
-            const uint32_t bw[4] = {b16.x, b16.y, b16.z, b16.w};
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int j = c * 16 + e;
-              // float(sat_s8(s * m)) without leaving fp32 (the biased sum is monotone in its argument)
-              const float c1 = fsub(fminf(fmaxf(fadd(fmul(__int2float_rn(x[c][e]), p.score_mult), RMAGIC), LO), HI), RMAGIC);
-              const float bc = __int2float_rn(int(int8_t((bw[e >> 2] >> (8 * (e & 3))) & 0xffu)));
-              const float v = fadd(fmul(c1, p.s_attn1), fmul(bc, p.bias_scale));            // + dequantized relative position bias
-              const float q2 = POT2 ? fmul(v, r2) : fdiv(v, p.s_attn2);                      // qact2
-              const int c2 = __float_as_int(fminf(fmaxf(fadd(q2, RMAGIC), LO), HI)) - 0x4B400000;
-              const int xv = c2 + (((mbits >> j) & 1ull) ? p.mask_code : 0);                 // + mask (after the quantizer)
-              x[c][e] = j < T ? xv : INT_MIN;
-              mx = max(mx, x[c][e]);
-            }
+          for (int e = 0; e < 16; ++e) {
+            // float(sat_s8(s * m)) without leaving fp32 (the biased sum is monotone in its argument)
+            const float c1 = fsub(fminf(fmaxf(fadd(fmul(__int2float_rn(x[c][e]), p.score_mult), RMAGIC), LO), HI), RMAGIC);
+            // bias code: byte e of the row (stored + 128) -> 2^23 + (code + 128) -> code, exactly
+            const float bc = fsub(__uint_as_float(__byte_perm(bw[e >> 2], 0x4B000000u, 0x7540 + (e & 3))), 8388736.f);
+            const float v = fadd(fmul(c1, p.s_attn1), fmul(bc, p.bias_scale));              // + dequantized relative position bias
+            const float q2 = POT2 ? fmul(v, r2) : fdiv(v, p.s_attn2);                        // qact2
+            int xv = __float_as_int(fminf(fmaxf(fadd(q2, RMAGIC), LO), HI)) - 0x4B400000;
+            if (MASK) xv += int(((mword >> ((c & 1) * 16 + e)) & 1u) * uint32_t(p.mask_code));   // + mask (after the quantizer)
+            if (decltype(partial)::value) xv = e < rem ? xv : -(1 << 30);      // padding key: far below every score, lands on table entry 256
+            x[c][e] = xv;
+            mx = max(mx, xv);
           }
-        }
-        // ---- pass B: exact row sum of exp_int(max - x); x[] becomes the shared-memory address of the table entry (0 = masked tail)
+        };
+        // ---- pass B: exact row sum of exp_int(max - x); x[] becomes the shared-memory address of the table entry
         unsigned long long sum = 0;
+        auto pass_b = [&](auto partial, auto cc) {
+          constexpr int c = decltype(cc)::value;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c * 16 < T) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const int j = c * 16 + e;
-              if (j < T) {
-                const int d = mx - x[c][e];
-                if (d > 255) {            // masked entry beyond the table: the clamped tail of int_exp (host checks mask_code reaches it)
-                  sum += p.e_mask;
-                  x[c][e] = 0;
-                } else {
-                  const uint32_t addr = lut32 + uint32_t(d) * 16u;
-                  uint32_t vh, vl;
-                  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vh), "=r"(vl) : "r"(addr));
-                  sum += (static_cast<unsigned long long>(vh) << 32) | vl;
-                  x[c][e] = int(addr);
-                }
-              }
-            }
+          for (int e = 0; e < 16; ++e) {
+            const uint32_t d = uint32_t(min(mx - x[c][e], 256));
+            const uint32_t addr = lut32 + (d << 4);
+            uint32_t vh, vl;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vh), "=r"(vl) : "r"(addr));
+            unsigned long long ev = (static_cast<unsigned long long>(vh) << 32) | vl;
+            if (decltype(partial)::value) ev = e < rem ? ev : 0ull;
+            sum += ev;
+            x[c][e] = int(addr);
           }
-        }
+        };
+#define P2V_WT_CHUNKS(fn)                                                                                                   \
+        if (nfull > 0) fn(std::false_type{}, std::integral_constant<int, 0>{}); else if (rem) fn(std::true_type{}, std::integral_constant<int, 0>{}); \
+        if (nfull > 1) fn(std::false_type{}, std::integral_constant<int, 1>{}); else if (nfull == 1 && rem) fn(std::true_type{}, std::integral_constant<int, 1>{}); \
+        if (nfull > 2) fn(std::false_type{}, std::integral_constant<int, 2>{}); else if (nfull == 2 && rem) fn(std::true_type{}, std::integral_constant<int, 2>{}); \
+        if (nfull > 3) fn(std::false_type{}, std::integral_constant<int, 3>{}); else if (nfull == 3 && rem) fn(std::true_type{}, std::integral_constant<int, 3>{});
+        P2V_WT_CHUNKS(pass_a)
+        P2V_WT_CHUNKS(pass_b)
         const float tot = __ull2float_rn(sum);      // <= 64 entries below 2^55: exact in 64 bits, rounded once
         const float tot2 = fmul(tot, 2.0f), tot43 = fmul(tot, 1.33333337306976318359375f);
         // ---- pass C: 2^(15-code) as hi / lo byte planes, this row's 64 key bytes of each plane
+        auto pass_c = [&](auto partial, auto cc) {
+          constexpr int c = decltype(cc)::value;
+          uint32_t pv[16];
+          float gmax = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
-          if (c * 16 < T) {
-            uint32_t pv[16];
-            float gmax = 0.f;
+          for (int e = 0; e < 16; ++e) {
+            float rcp;
+            asm volatile("ld.shared.f32 %0, [%1+12];" : "=f"(rcp) : "r"(uint32_t(x[c][e])));
+            pv[e] = prob_bits_fast(tot2, tot43, rcp, gmax);
+          }
+          if (!(gmax < PROB_GUARD)) {             // next to a rounding / log2 boundary (or not finite): IEEE division for the chunk
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              const int j = c * 16 + e;
-              pv[e] = 0u;
-              if (j < T) {
-                float rcp = r_mask;
-                if (x[c][e] != 0) asm volatile("ld.shared.f32 %0, [%1+12];" : "=f"(rcp) : "r"(uint32_t(x[c][e])));
-                pv[e] = prob_bits_fast(tot2, tot43, rcp, gmax) & 0xffffu;
-              }
+              float ef;
+              asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(ef) : "r"(uint32_t(x[c][e])));
+              pv[e] = shr_clamp(0x8000u, log2_code(tot, ef));
             }
-            if (!(gmax < PROB_GUARD)) {             // next to a rounding / log2 boundary (or not finite): IEEE division for the chunk
+          }
+          if (decltype(partial)::value) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int j = c * 16 + e;
-                if (j < T) {
-                  float ef = e_mask_f;
-                  if (x[c][e] != 0) asm volatile("ld.shared.f32 %0, [%1+8];" : "=f"(ef) : "r"(uint32_t(x[c][e])));
-                  pv[e] = shr_clamp(0x8000u, log2_code(tot, ef));
-                }
-              }
-            }
+            for (int e = 0; e < 16; ++e) pv[e] = e < rem ? pv[e] : 0u;
+          }
+          uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int e4 = 0; e4 < 4; ++e4) {
-              const uint32_t p01 = __byte_perm(pv[e4 * 4], pv[e4 * 4 + 1], 0x5410), p23 = __byte_perm(pv[e4 * 4 + 2], pv[e4 * 4 + 3], 0x5410);
-              lo[e4] = __byte_perm(p01, p23, 0x6420);
-              hi[e4] = __byte_perm(p01, p23, 0x7531);
-            }
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const uint32_t p01 = __byte_perm(pv[e4 * 4], pv[e4 * 4 + 1], 0x5410), p23 = __byte_perm(pv[e4 * 4 + 2], pv[e4 * 4 + 3], 0x5410);
+            lo[e4] = __byte_perm(p01, p23, 0x6420);
+            hi[e4] = __byte_perm(p01, p23, 0x7531);
           }
           const uint32_t dst = prow + ((uint32_t(4 * w + c) ^ sw) << 4);
           asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
           asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(dst + WT_P_PLANE), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
-        }
+        };
+        P2V_WT_CHUNKS(pass_c)
+#undef P2V_WT_CHUNKS
+        // (key chunks beyond T are never written: they stay zero from the prologue)
       } else if (i < T) {
         // the missing partner of an odd window count: its P rows must not carry the previous unit's values (token-padding rows
         // are never written and stay zero from the prologue)
@@ -338,16 +348,21 @@ int launch_window_attention_tc(const p2v_window_attention_args& a, uint32_t e_ma
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WT_SMEM_ALLOC));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WT_SMEM_ALLOC));
+    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WT_SMEM_ALLOC));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WT_SMEM_ALLOC));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WT_SMEM_ALLOC));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(window_attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(WT_SMEM_ALLOC));
     P2V_REQUIRE(e == cudaSuccess, "window_attention_tc: cannot set %zu bytes of dynamic shared memory: %s", WT_SMEM_ALLOC, cudaGetErrorString(e));
   }
   const int grid = std::min(p.units, 3 * sms);
   int ex = 0;
   const bool pot2 = std::frexp(a.s_attn2, &ex) == 0.5f;
   pdl_next_kind(PDL_OTHER);
-  if (pot2) launch_pdl(window_attention_tc_kernel<true>, dim3(grid), dim3(WT_THREADS), WT_SMEM_ALLOC, stream, tm, p);
-  else launch_pdl(window_attention_tc_kernel<false>, dim3(grid), dim3(WT_THREADS), WT_SMEM_ALLOC, stream, tm, p);
+  const bool mask = p.mask_bits != nullptr;
+  if (pot2 && mask) launch_pdl(window_attention_tc_kernel<true, true>, dim3(grid), dim3(WT_THREADS), WT_SMEM_ALLOC, stream, tm, p);
+  else if (pot2) launch_pdl(window_attention_tc_kernel<true, false>, dim3(grid), dim3(WT_THREADS), WT_SMEM_ALLOC, stream, tm, p);
+  else if (mask) launch_pdl(window_attention_tc_kernel<false, true>, dim3(grid), dim3(WT_THREADS), WT_SMEM_ALLOC, stream, tm, p);
+  else launch_pdl(window_attention_tc_kernel<false, false>, dim3(grid), dim3(WT_THREADS), WT_SMEM_ALLOC, stream, tm, p);
   count_launch();
   return check_launch("window_attention_tc");
 }
