@@ -395,7 +395,7 @@ __device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const f
 //   Bv = RNE(fl(fl(b - fl(m*g))*ros)*2^N) == RNE(fl(b' - fl(m*g'))*2^N),  b' = b*ros
 //   q  = sat(RNE(((yq*os)/pd)/next))  == sat(RNE(yq*f))
 // (scaling by a power of two commutes with rounding), so the codes equal the generic kernel's bit for bit.
-template <int LPR, int WPLN, bool CLAMP_MID>
+template <int LPR, int WPLN, bool CLAMP_MID, bool GATHER>
 __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_args a) {
   constexpr int GPW = 32 / LPR;                       // rows per warp iteration
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
@@ -436,10 +436,10 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
   }
   pdl_wait();          // the channel constants above are plan-time data; the rows are the previous kernel's output (common.cuh)
   pdl_trigger();
-  // gathered input (patch merging): segment and offset of each of the lane's words are row independent
-  int gseg[WPLN], goff[WPLN];
-  const bool gathered = a.in_gather != nullptr;
-  if (gathered) {
+  // gathered input (patch merging; its own instantiation - the plain kernel carries none of this): segment and offset of each
+  // of the lane's words are row independent
+  int gseg[GATHER ? WPLN : 1], goff[GATHER ? WPLN : 1];
+  if (GATHER) {
     const int seg_words = a.C / (4 * a.gather_segs);
 #pragma unroll
     for (int i = 0; i < WPLN; ++i) { gseg[i] = (sub + LPR * i) / seg_words; goff[i] = (sub + LPR * i) - gseg[i] * seg_words; }
@@ -450,8 +450,8 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
     int S1 = 0, S2 = 0;
 #pragma unroll
     for (int i = 0; i < WPLN; ++i) {
-      const uint32_t u = gathered ? __ldg(reinterpret_cast<const uint32_t*>(a.x + int64_t(__ldg(a.in_gather + int64_t(row) * a.gather_segs + gseg[i])) * a.x_row_stride) + goff[i])
-                                  : __ldg(xr + sub + LPR * i);
+      const uint32_t u = GATHER ? __ldg(reinterpret_cast<const uint32_t*>(a.x + int64_t(__ldg(a.in_gather + int64_t(row) * a.gather_segs + gseg[GATHER ? i : 0])) * a.x_row_stride) + goff[GATHER ? i : 0])
+                                : __ldg(xr + sub + LPR * i);
       xv[i][0] = int(int8_t(u & 0xff)) * sh[i][0];
       xv[i][1] = int(int8_t((u >> 8) & 0xff)) * sh[i][1];
       xv[i][2] = int(int8_t((u >> 16) & 0xff)) * sh[i][2];
@@ -487,18 +487,18 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
   }
 }
 
-template <int LPR, int WPLN, bool CLAMP_MID>
+template <int LPR, int WPLN, bool CLAMP_MID, bool GATHER = false>
 static void launch_ln_pot_c(const p2v_layernorm_args& a, cudaStream_t stream) {
   constexpr int GPW = 32 / LPR;
   const int rows_per_block = 4 * GPW;
   // persistent: several rows per lane group so the register-resident channel constants are amortised; one wave of resident blocks
   static int occ = 0;
   if (!occ) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_pot_kernel<LPR, WPLN, CLAMP_MID>, 128, 0) != cudaSuccess || occ < 1) occ = 3;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layernorm_pot_kernel<LPR, WPLN, CLAMP_MID, GATHER>, 128, 0) != cudaSuccess || occ < 1) occ = 3;
   }
   const int blocks = std::max(1, std::min((a.rows + rows_per_block - 1) / rows_per_block, num_sms() * occ));
   pdl_next_kind(PDL_LAYERNORM);
-  launch_pdl(layernorm_pot_kernel<LPR, WPLN, CLAMP_MID>, dim3(blocks), dim3(128), 0, stream, a);
+  launch_pdl(layernorm_pot_kernel<LPR, WPLN, CLAMP_MID, GATHER>, dim3(blocks), dim3(128), 0, stream, a);
 }
 template <int LPR, int WPLN>
 static void launch_ln_pot(const p2v_layernorm_args& a, cudaStream_t stream) {
@@ -508,7 +508,23 @@ static void launch_ln_pot(const p2v_layernorm_args& a, cudaStream_t stream) {
 
 int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
   const int nwords = a.C / 4;
-  if (a.pot_scales && a.out_i8 && !a.out_f32) {
+  if (a.in_gather && a.pot_scales && a.out_i8 && !a.clamp_mid && nwords % 32 == 0 && nwords / 32 >= 3 && nwords / 32 <= 12) {
+    // patch-merging LayerNorm (4C = 384 / 768 / 1536 for Swin-T/S, 512 / 1024 / 2048 for Swin-B): gathered instantiations
+    bool done = true;
+    switch (nwords / 32) {
+      case 3: launch_ln_pot_c<32, 3, false, true>(a, stream); break;
+      case 4: launch_ln_pot_c<32, 4, false, true>(a, stream); break;
+      case 6: launch_ln_pot_c<32, 6, false, true>(a, stream); break;
+      case 8: launch_ln_pot_c<32, 8, false, true>(a, stream); break;
+      case 12: launch_ln_pot_c<32, 12, false, true>(a, stream); break;
+      default: done = false;
+    }
+    if (done) {
+      count_launch();
+      return check_launch("layernorm_int");
+    }
+  }
+  if (a.pot_scales && a.out_i8 && !a.out_f32 && !a.in_gather) {
     bool done = true;
     // lanes per row: as many as leave a lane >= 12 channels (3 words) - more rows in flight per SM beat the amortisation of
     // the per-row scalar work (C = 384: 32 lanes x 3 words 26.8 us vs 16 x 6 32.9 us for 50 k rows, tools/ln_bench.py)
