@@ -127,8 +127,10 @@ struct GeluStepsHeader {   // 64 bytes, then float2 seg[P2V_GELU_STEPS_MAX_SEG],
   int nseg, nr, nl, k1, rep_log2, ok;
   float seg_scale;         // nseg - 1 + 0.49: segment = RNE(sat((y * inv_w + soff) / seg_scale) * seg_scale)
   float f_scale;           // 126 - f0 + 0.49 (f0 = -k1): f = f0 + RNE(sat(A' y + B') * f_scale), seg = (A', B') = (A, B - f0) / f_scale
-  int pad[3];
+  int clean;               // 1: the step code equals the direct evaluation also within 8 ulps of every threshold (no distance test needed)
+  int pad[2];
 };
+bool gelu_table_is_clean(const void* table_dev);     // host (gelu_table.cu): verdict of the table's self-check, by device address
 constexpr int P2V_GELU_STEPS_MAX_SEG = 64, P2V_GELU_STEPS_MAX_THR = 512;
 constexpr int P2V_GELU_STEPS_OFFSET = 16 + 8 * P2V_GELU_TABLE_MAX_ENTRIES;                 // byte offset inside a p2v gelu table buffer
 constexpr int P2V_GELU_STEPS_SMEM_MAX = 256 * P2V_GELU_STEPS_MAX_SEG + 26 * 1024;          // replicated tables: segments + thresholds
@@ -182,6 +184,9 @@ __device__ __forceinline__ GeluSteps gelu_steps_view(const void* table, uint32_t
 // (B - f0) / f_scale), the indices leave an FFMA already biased and become addresses with one IMAD each.
 // near_min collects min(bits(y) - bits(threshold) + 8) as unsigned: a value <= 16 means some y was within 8 ulps of the
 // threshold consulted and the caller must evaluate erf directly.
+// GUARD = false: the table's self-check found every threshold a clean step of the direct evaluation (GeluStepsHeader.clean), so
+// the distance test - three ALU-pipe instructions per output - is not needed.
+template <bool GUARD = true>
 __device__ __forceinline__ uint32_t gelu_steps_code(float y, const GeluSteps& t, uint32_t& near_min) {
   const float yc = fmaxf(y, t.ymin);                     // left of ymin the code is constant; right of ymax the SATs hold the indices
   const uint32_t sb = __float_as_uint(__fmaf_rn(fma_sat(yc, t.sa, t.sb), t.seg_scale, RMAGIC));      // 0x4B400000 + segment
@@ -191,7 +196,7 @@ __device__ __forceinline__ uint32_t gelu_steps_code(float y, const GeluSteps& t,
   const bool left = yc < t.ystar;
   float thr;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(thr) : "r"(fb * t.thr_mul + (left ? t.thr_l : t.thr_r)));
-  near_min = min(near_min, __float_as_uint(yc) - __float_as_uint(thr) + 8u);
+  if (GUARD) near_min = min(near_min, __float_as_uint(yc) - __float_as_uint(thr) + 8u);
   return fb + (((yc >= thr) != left) ? 1u : 0u);
 }
 // low bytes of four words -> one word
@@ -255,7 +260,7 @@ constexpr float PROB_GUARD = 16384.f - 0.0625f;     // 16 ulps of [2^15, 2^16)
 __device__ __forceinline__ uint32_t prob_bits_fast(float tot2, float tot43, float rcp, float& gmax) {
   const float g = fminf(__fmaf_rn(tot2, rcp, -1.0f), __fmaf_rn(tot43, rcp, 0.666666686534881591796875f));
   const float pf = __uint_as_float(0x86800000u - (__float_as_uint(g) & 0x7F800000u));     // 2^(15 - E), E = floor(log2 g)
-  gmax = fmaxf(gmax, fabsf(fadd(fmul(g, pf), -49152.f)));
+  gmax = fmaxf(gmax, fabsf(__fmaf_rn(g, pf, -49152.f)));       // g * pf is exact (pf is a power of two), and so is the difference
   return __float_as_uint(fadd(pf, 8388608.f));      // low 16 bits: 2^(15-E)
 }
 // exactly rounded (RNE) fp32 of the 128-bit integer hi*2^32 + lo  (hi, lo < 2^63)

@@ -4,6 +4,9 @@
 // neighbourhood of the threshold is probed so that a segment whose code is not a clean step is flagged `slow`
 // (the epilogue then evaluates erf directly for every y that lands in it).
 #include <cmath>
+#include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 #include "common.cuh"
 
@@ -114,8 +117,10 @@ __global__ void __launch_bounds__(128) build_gelu_steps_kernel(GeluStepsHeader h
 
 // Self-check with the epilogue's own code path (replicated shared-memory tables, gelu_steps_code): +-256 ulps around every
 // threshold, a uniform grid over the active range and beyond, and a sweep of magnitudes; any y that is not sent to the direct
-// evaluation (near_min > 16) must get exactly the direct code.  A mismatch clears *ok.
-__global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __restrict__ table, float ro, int* __restrict__ ok) {
+// evaluation (near_min > 16) must get exactly the direct code.  A mismatch clears *ok.  A y inside the band whose step code
+// differs from the direct one clears *clean: the band around every threshold is scanned exhaustively, so a table that keeps
+// `clean` needs no distance test in the epilogue.
+__global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __restrict__ table, float ro, int* __restrict__ ok, int* __restrict__ clean) {
   extern __shared__ uint8_t vsm[];
   const uint32_t base = (uint32_t(__cvta_generic_to_shared(vsm)) + 255u) & ~255u;
   gelu_steps_fill_smem(table, base, int(threadIdx.x), int(blockDim.x));
@@ -124,11 +129,13 @@ __global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __re
   const GeluStepsHeader h = *reinterpret_cast<const GeluStepsHeader*>(reinterpret_cast<const char*>(table) + P2V_GELU_STEPS_OFFSET);
   const float* thr = reinterpret_cast<const float*>(reinterpret_cast<const char*>(table) + P2V_GELU_STEPS_OFFSET + sizeof(GeluStepsHeader) +
                                                     8 * P2V_GELU_STEPS_MAX_SEG);
-  bool bad = false;
+  bool bad = false, unclean = false;
   auto check = [&](float y) {
     uint32_t nm = 0xffffffffu;
     const int c = int(int8_t(gelu_steps_code(y, t, nm) & 0xffu));
-    if (nm > 16u && c != gelu_code_direct(y, ro)) bad = true;
+    if (c != gelu_code_direct(y, ro)) {
+      if (nm > 16u) bad = true; else unclean = true;
+    }
   };
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
   const long long n1 = (long long)(h.nr + h.nl) * 513;
@@ -145,6 +152,17 @@ __global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __re
   }
   if (gid == 0) { check(0.0f); check(-0.0f); check(h.ymin); check(h.ymax); check(h.ystar); }
   if (bad) atomicExch(ok, 0);
+  if (unclean) atomicExch(clean, 0);
+}
+
+// tables whose self-check found them clean, by device address (the table itself lives in device memory; the GEMM launcher
+// picks the epilogue variant on the host)
+static std::mutex g_clean_mu;
+static std::unordered_map<const void*, bool> g_clean;
+bool gelu_table_is_clean(const void* table_dev) {
+  std::lock_guard<std::mutex> lk(g_clean_mu);
+  auto it = g_clean.find(table_dev);
+  return it != g_clean.end() && it->second;
 }
 
 static double gelu_f64(double y) { return 0.5 * y * (1.0 + erf(y * 0.70710678118654752440)); }
@@ -163,8 +181,8 @@ static bool plan_gelu_steps(float out_scale, GeluStepsHeader& h, std::vector<flo
   const double ymin = lo;
   cr0 = int(floor(gmin * ro + 0.5)) - 2;
   h.ymin = float(ymin); h.ymax = float(ymax); h.ystar = ystar;
-  h.nr = 131 - cr0; h.nl = 3 - cr0; h.k1 = 1 - cr0; h.ok = 1;
-  for (int k = 0; k < 3; ++k) h.pad[k] = 0;
+  h.nr = 131 - cr0; h.nl = 3 - cr0; h.k1 = 1 - cr0; h.ok = 1; h.clean = 1;
+  for (int k = 0; k < 2; ++k) h.pad[k] = 0;
   const double f0 = double(cr0 - 1);
   h.f_scale = float(126.0 - f0 + 0.49);
   const int entries = h.nr + h.nl;
@@ -217,13 +235,19 @@ static int build_gelu_steps(float out_scale, void* table_dev, cudaStream_t strea
     cudaFuncSetAttribute(verify_gelu_steps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P2V_GELU_STEPS_SMEM_MAX + 256));
     attr = true;
   }
-  verify_gelu_steps_kernel<<<64, 256, smem, stream>>>(table_dev, 1.0f / out_scale, ok_dev);
+  int* clean_dev = &reinterpret_cast<GeluStepsHeader*>(base)->clean;
+  verify_gelu_steps_kernel<<<64, 256, smem, stream>>>(table_dev, 1.0f / out_scale, ok_dev, clean_dev);
   count_launch(2);
   if (int r = check_launch("build_gelu_steps")) return r;
-  int ok = 0;
-  cudaMemcpyAsync(&ok, ok_dev, sizeof(int), cudaMemcpyDeviceToHost, stream);
+  GeluStepsHeader back;
+  cudaMemcpyAsync(&back, base, sizeof(back), cudaMemcpyDeviceToHost, stream);
   if (cudaStreamSynchronize(stream) != cudaSuccess) { set_error("build_gelu_steps: %s", cudaGetErrorString(cudaGetLastError())); return 2; }
-  return ok ? 0 : 3;
+  static const bool no_clean = getenv("P2V_GELU_GUARD") && atoi(getenv("P2V_GELU_GUARD")) != 0;     // triage: keep the distance test
+  {
+    std::lock_guard<std::mutex> lk(g_clean_mu);
+    g_clean[table_dev] = back.ok && back.clean && !no_clean;
+  }
+  return back.ok ? 0 : 3;
 }
 
 int launch_build_gelu_table(float out_scale, void* table_dev, cudaStream_t stream) {

@@ -199,7 +199,8 @@ __device__ __forceinline__ float4 prm_ld4(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-template <int EPI, bool POT, bool GST>
+// GST: 0 = no GELU step tables, 1 = step tables with the near-threshold distance test, 2 = clean tables (gelu_table.cu), no test
+template <int EPI, bool POT, int GST>
 __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const uint32_t prm, const int (&acc)[16], const uint4 resx, uint4& out,
                                            const GeluSteps& gst) {
   uint32_t ow[4];
@@ -251,7 +252,7 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
       // taken once per chunk, after the loop.
       uint32_t q[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) q[e] = gelu_steps_code(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]), gst, gst_near);
+      for (int e = 0; e < 4; ++e) q[e] = gelu_steps_code<GST == 1>(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]), gst, gst_near);
       ow[j4 >> 2] = pack4_low_bytes(q[0], q[1], q[2], q[3]);
       continue;
     } else if (POT && EPI == P2V_EPI_GELU) {
@@ -283,7 +284,7 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
     }
     ow[j4 >> 2] = pack4_sat(t[0], t[1], t[2], t[3]);
   }
-  if (POT && EPI == P2V_EPI_GELU && GST) {
+  if (POT && EPI == P2V_EPI_GELU && GST == 1) {
     if (gst_near <= 16u) {     // some y within 8 ulps of the threshold it consulted: the chunk takes the direct evaluation
 #pragma unroll 1
       for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -337,7 +338,7 @@ __device__ __forceinline__ void store_col(float* prm, int c, const RawCol& r) {
   }
 }
 
-template <int EPI, bool POT, bool GST>
+template <int EPI, bool POT, int GST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                  const __grid_constant__ CUtensorMap tmR, EpiParams p, PairGeom g) {
@@ -711,7 +712,7 @@ static double pair_cost(const p2v_gemm_args& a, const PairGeom& g, bool gst) {
   return waves * (std::max(load, std::max(mma, g.BN * per_col)) + 1500.0) * handicap;
 }
 
-template <int EPI, bool POT, bool GST = false>
+template <int EPI, bool POT, int GST = 0>
 static int launch_pair(const p2v_gemm_args& a, const PairGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                        const CUtensorMap& tmR, cudaStream_t stream) {
   auto kern = gemm_pair_kernel<EPI, POT, GST>;
@@ -760,7 +761,8 @@ int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
       return pot ? launch_pair<P2V_EPI_REQUANT, true>(a, g, tmA, tmB, tmO, tmR, stream)
                  : launch_pair<P2V_EPI_REQUANT, false>(a, g, tmA, tmB, tmO, tmR, stream);
     case P2V_EPI_GELU:
-      if (gst) return launch_pair<P2V_EPI_GELU, true, true>(a, g, tmA, tmB, tmO, tmR, stream);
+      if (gst) return gelu_table_is_clean(a.gelu_table) ? launch_pair<P2V_EPI_GELU, true, 2>(a, g, tmA, tmB, tmO, tmR, stream)
+                                                        : launch_pair<P2V_EPI_GELU, true, 1>(a, g, tmA, tmB, tmO, tmR, stream);
       return pot ? launch_pair<P2V_EPI_GELU, true>(a, g, tmA, tmB, tmO, tmR, stream)
                  : launch_pair<P2V_EPI_GELU, false>(a, g, tmA, tmB, tmO, tmR, stream);
     default:

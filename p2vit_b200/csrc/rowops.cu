@@ -396,7 +396,7 @@ __device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const f
 //   q  = sat(RNE(((yq*os)/pd)/next))  == sat(RNE(yq*f))
 // (scaling by a power of two commutes with rounding), so the codes equal the generic kernel's bit for bit.
 template <int LPR, int WPLN, bool CLAMP_MID, bool GATHER>
-__global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_args a) {
+__global__ void __launch_bounds__(128, (WPLN <= 3 && !GATHER) ? 4 : 3) layernorm_pot_kernel(p2v_layernorm_args a) {
   constexpr int GPW = 32 / LPR;                       // rows per warp iteration
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
@@ -444,18 +444,24 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
 #pragma unroll
     for (int i = 0; i < WPLN; ++i) { gseg[i] = (sub + LPR * i) / seg_words; goff[i] = (sub + LPR * i) - gseg[i] * seg_words; }
   }
-  for (int row = warp_global * GPW + grp; row < a.rows; row += row_stride) {
+  // The row's words are loaded one iteration ahead: with three warps per scheduler the wait for them was a third of the
+  // kernel's stall samples (ncu r2: long scoreboard on the first unpack).
+  auto load_row = [&](int row, uint32_t (&u)[WPLN]) {
     const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
-    int xv[WPLN][4];
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i)
+      u[i] = GATHER ? __ldg(reinterpret_cast<const uint32_t*>(a.x + int64_t(__ldg(a.in_gather + int64_t(row) * a.gather_segs + gseg[GATHER ? i : 0])) * a.x_row_stride) + goff[GATHER ? i : 0])
+                    : __ldg(xr + sub + LPR * i);
+  };
+  // unpack (x * in_mult), exact integer sums over the row, the row scalars t = s1 / std and mos = mean / std (layers.py:316-323)
+  auto row_stats = [&](const uint32_t (&u)[WPLN], int (&xv)[WPLN][4], float& t, float& mos) {
     int S1 = 0, S2 = 0;
 #pragma unroll
     for (int i = 0; i < WPLN; ++i) {
-      const uint32_t u = GATHER ? __ldg(reinterpret_cast<const uint32_t*>(a.x + int64_t(__ldg(a.in_gather + int64_t(row) * a.gather_segs + gseg[GATHER ? i : 0])) * a.x_row_stride) + goff[GATHER ? i : 0])
-                                : __ldg(xr + sub + LPR * i);
-      xv[i][0] = int(int8_t(u & 0xff)) * sh[i][0];
-      xv[i][1] = int(int8_t((u >> 8) & 0xff)) * sh[i][1];
-      xv[i][2] = int(int8_t((u >> 16) & 0xff)) * sh[i][2];
-      xv[i][3] = int(int8_t(u >> 24)) * sh[i][3];
+      xv[i][0] = int(int8_t(u[i] & 0xff)) * sh[i][0];
+      xv[i][1] = int(int8_t((u[i] >> 8) & 0xff)) * sh[i][1];
+      xv[i][2] = int(int8_t((u[i] >> 16) & 0xff)) * sh[i][2];
+      xv[i][3] = int(int8_t(u[i] >> 24)) * sh[i][3];
 #pragma unroll
       for (int e = 0; e < 4; ++e) { S1 += xv[i][e]; S2 += xv[i][e] * xv[i][e]; }
     }
@@ -464,26 +470,43 @@ __global__ void __launch_bounds__(128, 3) layernorm_pot_kernel(p2v_layernorm_arg
     const float S1f = float(S1), S2f = float(S2);
     const float mean = fmul(fdiv(S1f, Cf), s1);
     const float stdv = fmul(s1c, __fsqrt_rn(fsub(fmul(Cf, S2f), fmul(S1f, S1f))));
-    const float t = fdiv(s1, stdv);
-    const float mos = fdiv(mean, stdv);
+    t = fdiv(s1, stdv);
+    mos = fdiv(mean, stdv);
+  };
+  // Fast element loop (ln_pot_fast_word): no conversion / rounding instruction except one FRND.  It needs every |A| = |t*g'| in
+  // [2^-24, 2^8) (N = 7 - floor(log2|A|) unclamped) - checked per row against the row-independent bounds of |g'| - and no
+  // mantissa of A within 16 ulps below a power of two (floor_log2_as_fp32's corner) - collected by the loop itself.  Rows that
+  // fail either test (or have std == 0 / non-finite statistics) are redone with the reference-order code.
+  auto finish_row = [&](int row, float t, float mos, const uint32_t (&qw)[WPLN], uint32_t mant_max) {
     uint32_t* orow = reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(a.out_row_map ? __ldg(a.out_row_map + row) : row) * a.C);
-    // Fast element loop (ln_pot_fast_word): no conversion / rounding instruction except one FRND.  It needs every |A| = |t*g'| in
-    // [2^-24, 2^8) (N = 7 - floor(log2|A|) unclamped) - checked per row against the row-independent bounds of |g'| - and no
-    // mantissa of A within 16 ulps below a power of two (floor_log2_as_fp32's corner) - collected by the loop itself.  Rows that
-    // fail either test (or have std == 0 / non-finite statistics) are redone with the reference-order code.
     const bool in_range = fmul(t, gmax) < 256.f && fmul(t, gmin) >= 0x1p-24f;
-    uint32_t qw[WPLN];
-    uint32_t mant_max = 0;
-    if (in_range) {
-#pragma unroll
-      for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_fast_word<CLAMP_MID>(t, mos, g[i], bt[i], f[i], xv[i], mant_max);
-    }
     if (!in_range || mant_max >= 0x007ffff0u) {
       ln_pot_row_slow(a, row, orow, sub, LPR, WPLN, t, mos, clamp_hi);     // rare: out of line, constants re-read from memory
     } else {
 #pragma unroll
       for (int i = 0; i < WPLN; ++i) orow[sub + LPR * i] = qw[i];
     }
+  };
+  const int row0 = warp_global * GPW + grp;
+  if (row0 >= a.rows) return;
+  // (Measured and rejected, r2: two rows in flight - the statistics chain of row n + 1 in the same straight-line block as the
+  // element loop of row n, 143 registers - 23.3 vs 22.5 us at C = 384 stand-alone, 0.74 vs 0.71 ms per DeiT-S step.)
+  uint32_t ucur[WPLN], unext[WPLN];
+  load_row(row0, ucur);
+  for (int row = row0; row < a.rows; row += row_stride) {
+    if (row + row_stride < a.rows) load_row(row + row_stride, unext);
+    int xv[WPLN][4];
+    float t, mos;
+    row_stats(ucur, xv, t, mos);
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) ucur[i] = unext[i];
+    uint32_t qw[WPLN];
+    uint32_t mant_max = 0;
+    if (fmul(t, gmax) < 256.f && fmul(t, gmin) >= 0x1p-24f) {
+#pragma unroll
+      for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_fast_word<CLAMP_MID>(t, mos, g[i], bt[i], f[i], xv[i], mant_max);
+    }
+    finish_row(row, t, mos, qw, mant_max);
   }
 }
 
