@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define P2V_ABI_VERSION 3
+#define P2V_ABI_VERSION 2
 
 int p2v_abi_version(void);
 const char* p2v_last_error(void);
@@ -217,10 +217,6 @@ typedef struct {
    * out_i8 = sat(RNE(fl(O*out_mult) + zp_out)).  All integer valued; 0 for symmetric observers. */
   int zp_qkv;
   float zp_score, zp_out;
-  /* largest entry of the table behind lut_dev (exp_f32[0..255]); 0 = not stated.  Entries below 2^48 (score scales down to
-   * about 2^-7) let the tcgen05 kernel sum them as two 24-bit-split words without a carry chain (attention_tc.cu SPLIT);
-   * the result does not depend on it. */
-  float lut_exp_max;
 } p2v_attention_args;
 
 /* Head dim 64, T <= 224 and no debug dumps: tcgen05 kernel (csrc/attention_tc.cu: TMA-fed S = q k^T and O = P v on

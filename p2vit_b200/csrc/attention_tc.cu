@@ -26,7 +26,6 @@
 // instead of 6 + 2 and 10 + 4.
 #include <climits>
 #include <cmath>
-#include <cstdlib>
 #include <type_traits>
 #include "tc_common.cuh"
 
@@ -57,7 +56,6 @@ constexpr size_t AT_SMEM_ALLOC = AT_SMEM + 128;
 // so the softmax warps only add the scalar dh z^2.  The tile costs 14 KB: one CTA per SM for that variant.
 constexpr uint32_t AT_OFF_ZC = (AT_SMEM + 1023u) & ~1023u;
 constexpr size_t AT_SMEM_ALLOC_ZP = AT_OFF_ZC + AT_KV_ROWS * AT_DH + 128;
-constexpr float SPLIT_EXP_MAX = 281474976710656.f;         // 2^48: bound on the table entries the SPLIT variant accepts
 static_assert(AT_OFF_K % 1024 == 0 && AT_OFF_V % 1024 == 0 && AT_OFF_P % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 struct AttTcParams {
@@ -96,10 +94,14 @@ __device__ __forceinline__ void quarter_exchange_sync(uint32_t quarter) {
 
 // POTM: score_mult is a power of two (minmax observers), so S * mult is exact and one FFMA on the magic-biased integer does
 // the conversion, the scaling and the RNE together; otherwise the reference's separately rounded product is kept.
-// SPLIT (every exp_int entry below 2^48, i.e. score scales down to ~2^-7): the table holds the entries as {e >> 24, e & 0xFFFFFF},
-// a row's word sums stay below 2^32 each, so pass 2 adds two entries per IADD3 and word instead of an IADD3 / IADD3.X carry
-// chain per entry.
-template <bool POTM, bool ZP, bool SPLIT>
+// Measured and rejected on passes 2 / 3 (r2, all at 97-98 us for B = 256, H = 6, against 97.2 us as it stands): table entries split
+// at 24 bits so that the row sum needs no IADD3.X carry chain; the reciprocal parked in TMEM over S by pass 2 (entry = {exp_int as
+// fp32, 1 / exp_int}, sums through two exact float splits) so that pass 3 has no shared-memory lookup - 35 % fewer shared-memory
+// wavefronts (the table lookups run at 2.3-3.1 wavefronts per ideal one, random indices in 32 lanes), three FADDs more per score.
+// Neither the instruction count of pass 2 (146 -> 95 per 16-score unit with the subnormal-address FFMA below: 101 -> 97 us) nor
+// the wavefront count is what bounds the kernel: with 4.5 warps per scheduler it issues one instruction per warp every 7 cycles,
+// and no single stall reason exceeds 15 % of the samples (profiles/r2_attention_stalls.txt).
+template <bool POTM, bool ZP>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttTcParams p) {
   static_assert(!(POTM && ZP), "zero points come with raw fp32 scales");
@@ -123,8 +125,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == AT_SM_WARPS) tmem_alloc<AT_TMEM_COLS>(base + AT_OFF_BARS + 48);
   for (int i = threadIdx.x; i < 257; i += AT_THREADS) {
     const int d = max(i - 1, 0);
-    const uint32_t ehi = p.lut->hi[d], elo = p.lut->lo[d];
-    s_lut[i] = SPLIT ? make_uint2((ehi << 8) | (elo >> 24), elo & 0xFFFFFFu) : make_uint2(ehi, elo);
+    s_lut[i] = make_uint2(p.lut->hi[d], p.lut->lo[d]);
     s_rcp[i] = make_float2(fdiv(1.0f, p.lut->exp_f32[d]), 0.f);
   }
   // -z as an int8 byte; z = -128 has no int8 negative: the tile then holds 64 and the correction MMAs are issued twice
@@ -282,12 +283,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           //      code_sat = 128 only when mx = 127: entry -1.
           const float rowk_f = __uint_as_float(lut32 + uint32_t(mx + 128) * 8u);      // &exp_int[mx + 128] (< 2^23: a subnormal)
           unsigned long long sum = 0;
-          uint32_t sum_h = 0, sum_l = 0;              // SPLIT: sums of the 24-bit-split words
           auto sum_unit = [&](auto masked, int u) {
             int acc[16];
             tmem_ld16(tlane + u * 16, acc);
             const int nv = T - u * 16;
-            uint32_t wh[16], wl[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const float uq = POTM ? __fmaf_rn(__int_as_float(acc[e] + 0x4B400000), mult, potm_c)
@@ -299,20 +298,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               acc[e] = int(addr);
               uint32_t vx, vy;
               asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "r"(addr));
-              if (SPLIT) {
-                const bool live = !decltype(masked)::value || e < nv;
-                wh[e] = live ? vx : 0u;
-                wl[e] = live ? vy : 0u;
-              } else if (!decltype(masked)::value || e < nv) {
-                sum += (static_cast<unsigned long long>(vx) << 32) | vy;
-              }
-            }
-            if (SPLIT) {
-#pragma unroll
-              for (int e = 0; e < 16; e += 2) {
-                sum_h += wh[e] + wh[e + 1];
-                sum_l += wl[e] + wl[e + 1];
-              }
+              if (!decltype(masked)::value || e < nv) sum += (static_cast<unsigned long long>(vx) << 32) | vy;
             }
             tmem_st16(tlane + u * 16, acc);
           };
@@ -321,7 +307,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (u_full < u_send) sum_unit(std::true_type{}, u_full);
           {
             uint32_t o0, o1;
-            if (SPLIT) sum = (static_cast<unsigned long long>(sum_h) << 24) + sum_l;
             tmem_st2(tlane + AT_XSUM + 2 * half, uint32_t(sum), uint32_t(sum >> 32));
             quarter_exchange_sync(quarter);           // also orders the address write-back before pass 3's loads
             tmem_ld2(tlane + AT_XSUM + 2 * (half ^ 1u), o0, o1);
@@ -354,7 +339,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               for (int e = 0; e < 16; ++e) {
                 uint32_t vx, vy;
                 asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "r"(uint32_t(aa[e])));
-                const uint32_t big = log2_code(tot, __ull2float_rn((static_cast<unsigned long long>(vx) << (SPLIT ? 24 : 32)) + vy));
+                const uint32_t big = log2_code(tot, __ull2float_rn((static_cast<unsigned long long>(vx) << 32) | vy));
                 pv[e] = shr_clamp(0x8000u, big);
               }
             }
@@ -467,25 +452,14 @@ int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaSuccess;
-    auto set_smem = [&](auto kernel, size_t bytes) {
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
-    };
-    set_smem(attention_tc_kernel<true, false, false>, AT_SMEM_ALLOC);
-    set_smem(attention_tc_kernel<true, false, true>, AT_SMEM_ALLOC);
-    set_smem(attention_tc_kernel<false, false, false>, AT_SMEM_ALLOC);
-    set_smem(attention_tc_kernel<false, false, true>, AT_SMEM_ALLOC);
-    set_smem(attention_tc_kernel<false, true, false>, AT_SMEM_ALLOC_ZP);
-    set_smem(attention_tc_kernel<false, true, true>, AT_SMEM_ALLOC_ZP);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC_ZP));
     P2V_REQUIRE(e == cudaSuccess, "attention_tc: cannot set %zu bytes of dynamic shared memory: %s", AT_SMEM_ALLOC_ZP, cudaGetErrorString(e));
   }
-  // the caller states the largest table entry (0 = not stated): below 2^48 the 24-bit-split sums apply
-  static const int split_mode = [] { const char* v = getenv("P2V_ATT_SPLIT"); return v ? atoi(v) : 1; }();
-  const bool split = split_mode != 0 && a.lut_exp_max > 0.f && a.lut_exp_max < SPLIT_EXP_MAX;
   if (zp) {      // asymmetric quantizers: constant-tile variant, one CTA per SM
     pdl_next_kind(PDL_ATTENTION);
-    if (split) launch_pdl(attention_tc_kernel<false, true, true>, dim3(std::min(p.total_heads, sms)), dim3(AT_THREADS), AT_SMEM_ALLOC_ZP, stream, tmQ, tmKV, p);
-    else launch_pdl(attention_tc_kernel<false, true, false>, dim3(std::min(p.total_heads, sms)), dim3(AT_THREADS), AT_SMEM_ALLOC_ZP, stream, tmQ, tmKV, p);
+    launch_pdl(attention_tc_kernel<false, true>, dim3(std::min(p.total_heads, sms)), dim3(AT_THREADS), AT_SMEM_ALLOC_ZP, stream, tmQ, tmKV, p);
     count_launch();
     return check_launch("attention_tc");
   }
@@ -494,13 +468,8 @@ int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
   int mexp = 0;
   const bool potm = std::frexp(a.score_mult, &mexp) == 0.5f && mexp >= -19 && mexp <= 9;
   pdl_next_kind(PDL_ATTENTION);
-  if (potm) {
-    if (split) launch_pdl(attention_tc_kernel<true, false, true>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
-    else launch_pdl(attention_tc_kernel<true, false, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
-  } else {
-    if (split) launch_pdl(attention_tc_kernel<false, false, true>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
-    else launch_pdl(attention_tc_kernel<false, false, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
-  }
+  if (potm) launch_pdl(attention_tc_kernel<true, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
+  else launch_pdl(attention_tc_kernel<false, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
   count_launch();
   return check_launch("attention_tc");
 }

@@ -47,9 +47,7 @@ def build_softmax_lut(scale, max_row_len=1024):
 
 
 def lut_to_device(lut, device):
-    t = torch.from_numpy(np.frombuffer(lut.tobytes(), dtype=np.uint8).copy()).to(device)
-    t.exp_max = float(lut["exp_f32"].max())     # ops.attention_args passes it on (p2v_attention_args.lut_exp_max)
-    return t
+    return torch.from_numpy(np.frombuffer(lut.tobytes(), dtype=np.uint8).copy()).to(device)
 
 
 def is_pot(t):

@@ -184,7 +184,6 @@ def attention_args(qkv, out, B, T, H, dh, score_mult, out_mult, lut_dev, probs=N
     a.lut_dev = ptr(lut_dev)
     a.probs_or_null, a.scores_or_null = ptr(probs), ptr(scores)
     a.zp_qkv, a.zp_score, a.zp_out = int(zp_qkv), float(zp_score), float(zp_out)
-    a.lut_exp_max = float(getattr(lut_dev, "exp_max", 0.0))      # intmath.lut_to_device records it on the tensor
     return a
 
 
