@@ -510,6 +510,190 @@ __global__ void __launch_bounds__(128, (WPLN <= 3 && !GATHER) ? 4 : 3) layernorm
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same row-persistent kernel for arbitrary fp32 scales (ema / percentile / omse observers): the reference divides by the
+// LayerNorm's output scale twice and by the next QAct's scale once per element (layers.py:320-337 and the following QAct,
+// uniform.py:83-86).  Each of them is an exactly rounded IEEE quotient here too, but from the divisor's reciprocal, computed once
+// per channel: q0 = a * rb, two residual corrections q <- q + (a - b q) * rb with the residual exact in one FFMA.  The first
+// correction leaves q within half an ulp (+ 2^-40) of a / b, the second then rounds correctly (Markstein's theorem: rb = RN(1 / b),
+// b's significand not all ones; the operands here are far from the exponent range's ends, zero operands give zero).  A channel whose
+// scale has an all-ones significand, a post-divisor that is not a power of two, a row outside the fast loop's range (see
+// layernorm_pot_kernel) take the reference-order code.  Constants sit in shared memory ([6][C] floats, one LDS.128 per word and
+// row): the register-resident form of the power-of-two kernel would need 6 x 24 registers at C = 768.
+// ViT-B percentile: 6.8 ms of LayerNorm per 256 images with the generic kernel (r2).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float div_rb(float a, float b, float rb) {
+  const float q0 = fmul(a, rb);
+  const float q1 = __fmaf_rn(__fmaf_rn(-b, q0, a), rb, q0);
+  return __fmaf_rn(__fmaf_rn(-b, q1, a), rb, q1);
+}
+// one lane's words of a row in the reference's operation order (the generic kernel's element code)
+__device__ __noinline__ void ln_np_row_slow(const p2v_layernorm_args& a, int row, uint32_t* __restrict__ orow, int sub, int lpr, int wpln,
+                                            float t, float mos) {
+  for (int i = 0; i < wpln; ++i) {
+    const int w = sub + lpr * i;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma) + w), b4 = __ldg(reinterpret_cast<const float4*>(a.beta) + w);
+    const float4 o4 = __ldg(reinterpret_cast<const float4*>(a.out_scale) + w), p4 = __ldg(reinterpret_cast<const float4*>(a.post_div) + w);
+    const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.in_mult) + w);
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w}, os[4] = {o4.x, o4.y, o4.z, o4.w};
+    const float pd[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+    const uint32_t u = __ldg(ln_word_ptr(a, row, w));
+    const int cx[4] = {int(int8_t(u & 0xff)), int(int8_t((u >> 8) & 0xff)), int(int8_t((u >> 16) & 0xff)), int(int8_t(u >> 24))};
+    int q[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float A = fdiv(fmul(t, g[e]), os[e]);
+      const float aA = fabsf(A);
+      int N;
+      if (aA == 0.f) N = 31;
+      else if (!(aA < __int_as_float(0x7f800000))) N = 0;
+      else N = min(max(7 - floor_log2_as_fp32(aA), 0), 31);
+      const float twoN = pow2i(N);
+      const float M = fminf(fmaxf(floorf(fmul(aA, twoN)), 0.f), 255.f);
+      const float sgn = A > 0.f ? 1.f : (A < 0.f ? -1.f : 0.f);
+      const float Bv = rintf(fmul(fdiv(fsub(be[e], fmul(mos, g[e])), os[e]), twoN));
+      const float yq = rintf(fmul(fadd(fmul(fmul(sgn, M), float(cx[e] * int(mm[e]))), Bv), pow2i(-N)));
+      const float mid = a.clamp_mid ? fmul(fminf(fmaxf(yq, -128.f), 127.f), os[e]) : fmul(yq, os[e]);
+      q[e] = sat_s8(fadd(fdiv(fdiv(mid, pd[e]), a.next_scale), a.next_zp));
+    }
+    orow[w] = pack4_s8(q[0], q[1], q[2], q[3]);
+  }
+}
+
+template <int LPR, int WPLN, bool CLAMP_MID>
+__global__ void __launch_bounds__(128, 4) layernorm_np_kernel(p2v_layernorm_args a) {
+  extern __shared__ float4 ln_np_sm[];                 // [6][C / 4]: gamma, beta, out_scale, 1 / out_scale, 1 / post_div, in_mult
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
+  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row_stride = gridDim.x * (blockDim.x >> 5) * GPW;
+  const int nw = a.C >> 2;
+  bool bad = false;
+  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma) + w), o4 = __ldg(reinterpret_cast<const float4*>(a.out_scale) + w);
+    const float4 p4 = __ldg(reinterpret_cast<const float4*>(a.post_div) + w);
+    const float oo[4] = {o4.x, o4.y, o4.z, o4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+    float ro[4], rp[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ro[e] = fdiv(1.f, oo[e]);
+      rp[e] = fdiv(1.f, pp[e]);
+      bad |= (__float_as_uint(oo[e]) & 0x007fffffu) == 0x007fffffu || !(oo[e] > 0x1p-60f && oo[e] < 0x1p60f);
+      bad |= (__float_as_uint(pp[e]) & 0x007fffffu) != 0u || !(pp[e] > 0x1p-60f && pp[e] < 0x1p60f);
+    }
+    ln_np_sm[w] = g4;
+    ln_np_sm[nw + w] = __ldg(reinterpret_cast<const float4*>(a.beta) + w);
+    ln_np_sm[2 * nw + w] = o4;
+    ln_np_sm[3 * nw + w] = make_float4(ro[0], ro[1], ro[2], ro[3]);
+    ln_np_sm[4 * nw + w] = make_float4(rp[0], rp[1], rp[2], rp[3]);
+    ln_np_sm[5 * nw + w] = __ldg(reinterpret_cast<const float4*>(a.in_mult) + w);
+  }
+  const float next = a.next_scale, rnext = fdiv(1.f, next), zp = a.next_zp;
+  bad |= (__float_as_uint(next) & 0x007fffffu) == 0x007fffffu || !(next > 0x1p-60f && next < 0x1p60f);
+  bad = __syncthreads_or(bad);
+  // row-independent bounds of |g / out_scale| over the lane group's channels, and the integer input multipliers in registers
+  int sh[WPLN][4];
+  float gmin = __int_as_float(0x7f800000), gmax = 0.f;
+#pragma unroll
+  for (int i = 0; i < WPLN; ++i) {
+    const float4 g4 = ln_np_sm[sub + LPR * i], r4 = ln_np_sm[3 * nw + sub + LPR * i], m4 = ln_np_sm[5 * nw + sub + LPR * i];
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float q = fabsf(fmul(gg[e], rr[e]));
+      gmin = fminf(gmin, q); gmax = fmaxf(gmax, q);
+      sh[i][e] = int(mm[e]);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  }
+  const float Cf = float(a.C), s1 = a.in_scale_min, s1c = fdiv(s1, Cf);
+  pdl_wait();
+  pdl_trigger();
+  const int row0 = warp_global * GPW + grp;
+  if (row0 >= a.rows) return;
+  auto load_row = [&](int row, uint32_t (&u)[WPLN]) {
+    const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) u[i] = __ldg(xr + sub + LPR * i);
+  };
+  uint32_t ucur[WPLN], unext[WPLN];
+  load_row(row0, ucur);
+  for (int row = row0; row < a.rows; row += row_stride) {
+    if (row + row_stride < a.rows) load_row(row + row_stride, unext);
+    int xv[WPLN][4];
+    int S1 = 0, S2 = 0;
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) {
+      xv[i][0] = int(int8_t(ucur[i] & 0xff)) * sh[i][0];
+      xv[i][1] = int(int8_t((ucur[i] >> 8) & 0xff)) * sh[i][1];
+      xv[i][2] = int(int8_t((ucur[i] >> 16) & 0xff)) * sh[i][2];
+      xv[i][3] = int(int8_t(ucur[i] >> 24)) * sh[i][3];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { S1 += xv[i][e]; S2 += xv[i][e] * xv[i][e]; }
+      ucur[i] = unext[i];
+    }
+    S1 = __reduce_add_sync(gmask, S1);
+    S2 = __reduce_add_sync(gmask, S2);
+    const float S1f = float(S1), S2f = float(S2);
+    const float mean = fmul(fdiv(S1f, Cf), s1);
+    const float stdv = fmul(s1c, __fsqrt_rn(fsub(fmul(Cf, S2f), fmul(S1f, S1f))));
+    const float t = fdiv(s1, stdv);
+    const float mos = fdiv(mean, stdv);
+    uint32_t* orow = reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(a.out_row_map ? __ldg(a.out_row_map + row) : row) * a.C);
+    // |A| = |fl(fl(t g) / os)| within [2^-24, 2^8) for every channel, with a margin for the two roundings
+    const bool in_range = !bad && fmul(t, gmax) < 255.99f && fmul(t, gmin) >= 0x1.0002p-24f;
+    uint32_t qw[WPLN];
+    uint32_t mant_max = 0;
+    if (in_range) {
+#pragma unroll
+      for (int i = 0; i < WPLN; ++i) {
+        const int w = sub + LPR * i;
+        const float4 g4 = ln_np_sm[w], b4 = ln_np_sm[nw + w], o4 = ln_np_sm[2 * nw + w], r4 = ln_np_sm[3 * nw + w], p4 = ln_np_sm[4 * nw + w];
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w}, os[4] = {o4.x, o4.y, o4.z, o4.w};
+        const float ro[4] = {r4.x, r4.y, r4.z, r4.w}, rp[4] = {p4.x, p4.y, p4.z, p4.w};
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t Ab = __float_as_uint(div_rb(fmul(t, g[e]), os[e], ro[e]));
+          const uint32_t Ef = Ab & 0x7f800000u;
+          mant_max = max(mant_max, Ab & 0x007fffffu);
+          const float twoN = __uint_as_float(0x82800000u - Ef);            // 2^(134 - E)
+          const float rtwoN = __uint_as_float(Ef - 0x03800000u);           // 2^(E - 134)
+          const float sM = __uint_as_float((Ab & 0x807f0000u) | 0x43000000u);
+          const float Bv = rintf(fmul(div_rb(fsub(be[e], fmul(mos, g[e])), os[e], ro[e]), twoN));
+          const float sum = __fmaf_rn(sM, __int2float_rn(xv[i][e]), Bv);  // sM * x is exact (8 x 11 bits)
+          float yq = fsub(__fmaf_rn(sum, rtwoN, RMAGIC), RMAGIC);          // RNE(sum / 2^N)
+          if (CLAMP_MID) yq = fminf(fmaxf(yq, -128.f), 127.f);
+          const float v = fmul(fmul(yq, os[e]), rp[e]);                    // (yq * os) / post_div, the second factor a power of two
+          r[e] = fadd(fadd(div_rb(v, next, rnext), zp), RMAGIC);           // RNE(v / next + zp) + RMAGIC, saturated below
+        }
+        qw[i] = pack4_sat(r[0], r[1], r[2], r[3]);
+      }
+    }
+    if (!in_range || mant_max >= 0x007ffff0u) {
+      ln_np_row_slow(a, row, orow, sub, LPR, WPLN, t, mos);
+    } else {
+#pragma unroll
+      for (int i = 0; i < WPLN; ++i) orow[sub + LPR * i] = qw[i];
+    }
+  }
+}
+template <int LPR, int WPLN>
+static void launch_ln_np(const p2v_layernorm_args& a, cudaStream_t stream) {
+  constexpr int GPW = 32 / LPR;
+  const int rows_per_block = 4 * GPW;
+  const size_t smem = size_t(a.C) * 24;
+  const int blocks = std::max(1, std::min((a.rows + rows_per_block - 1) / rows_per_block, num_sms() * 4));
+  pdl_next_kind(PDL_LAYERNORM);
+  if (a.clamp_mid) launch_pdl(layernorm_np_kernel<LPR, WPLN, true>, dim3(blocks), dim3(128), smem, stream, a);
+  else launch_pdl(layernorm_np_kernel<LPR, WPLN, false>, dim3(blocks), dim3(128), smem, stream, a);
+}
+
 template <int LPR, int WPLN, bool CLAMP_MID, bool GATHER = false>
 static void launch_ln_pot_c(const p2v_layernorm_args& a, cudaStream_t stream) {
   constexpr int GPW = 32 / LPR;
@@ -561,6 +745,27 @@ int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
     } else if (nwords % 32 == 0 && nwords / 32 <= 2) {
       switch (nwords / 32) { P2V_LN_POT(32, 1) P2V_LN_POT(32, 2) }
 #undef P2V_LN_POT
+    } else {
+      done = false;
+    }
+    if (done) {
+      count_launch();
+      return check_launch("layernorm_int");
+    }
+  }
+  static const bool np_off = getenv("P2V_LN_NP") && atoi(getenv("P2V_LN_NP")) == 0;     // triage: generic kernel for non-power-of-two scales
+  if (!a.pot_scales && a.out_i8 && !a.out_f32 && !a.in_gather && a.C <= 2048 && !np_off) {
+    bool done = true;
+#define P2V_LN_NP(LPR_, N_) case N_: launch_ln_np<LPR_, N_>(a, stream); break;
+    if (nwords % 32 == 0 && nwords / 32 >= 3 && nwords / 32 <= 8) {
+      switch (nwords / 32) { P2V_LN_NP(32, 3) P2V_LN_NP(32, 4) P2V_LN_NP(32, 5) P2V_LN_NP(32, 6) P2V_LN_NP(32, 7) P2V_LN_NP(32, 8) }
+    } else if (nwords % 16 == 0 && nwords / 16 >= 3 && nwords / 16 <= 6 && a.rows >= 2) {
+      switch (nwords / 16) { P2V_LN_NP(16, 3) P2V_LN_NP(16, 4) P2V_LN_NP(16, 5) P2V_LN_NP(16, 6) }
+    } else if (nwords % 8 == 0 && nwords / 8 >= 3 && nwords / 8 <= 6 && a.rows >= 4) {
+      switch (nwords / 8) { P2V_LN_NP(8, 3) P2V_LN_NP(8, 4) P2V_LN_NP(8, 5) P2V_LN_NP(8, 6) }
+    } else if (nwords % 32 == 0 && nwords / 32 <= 2) {
+      switch (nwords / 32) { P2V_LN_NP(32, 1) P2V_LN_NP(32, 2) }
+#undef P2V_LN_NP
     } else {
       done = false;
     }
