@@ -68,6 +68,16 @@ __device__ __forceinline__ int quant_s8(float x, float s, float rs) {
   return sat_s8(POT ? fmul(x, rs) : fdiv(x, s));
 }
 
+// Exactly rounded a / b from rb = RN(1 / b) without the division sequence: q0 = a * rb, then two residual corrections
+// q <- q + (a - b q) * rb with the residual exact in one FFMA.  The first leaves q within half an ulp (+ 2^-40) of a / b, the
+// second then rounds correctly (Markstein's theorem for a correctly rounded reciprocal and a faithful quotient).  Zero numerators
+// give zero; the operands must be far from the ends of the exponent range (scales and activations are).
+__device__ __forceinline__ float div_rb(float a, float b, float rb) {
+  const float q0 = fmul(a, rb);
+  const float q1 = __fmaf_rn(__fmaf_rn(-b, q0, a), rb, q0);
+  return __fmaf_rn(__fmaf_rn(-b, q1, a), rb, q1);
+}
+
 __device__ __forceinline__ uint32_t pack4_s8(int a, int b, int c, int d) {
   return (uint32_t(a) & 0xffu) | ((uint32_t(b) & 0xffu) << 8) | ((uint32_t(c) & 0xffu) << 16) | (uint32_t(d) << 24);
 }

@@ -95,13 +95,17 @@ struct TileIter {
 };
 
 // ---- parameter rows (warp-private table: rows of 64 floats)
-template <int EPI, bool POT>
+// ZP (asymmetric quantizers, omse; raw fp32 scales only): the accumulator loses zp_corr[n] = zp_in * sum_k W[n,k] first, and the
+// output code of REQUANT / GELU is sat(RNE(fl(fl(y / scale) + out_zp))) - the exactly rounded quotient itself is needed, so it
+// comes from the scale's reciprocal with two residual corrections (div_rb) instead of the reciprocal-bounds test.
+template <int EPI, bool POT, bool ZP = false>
 __host__ __device__ constexpr int prm_rows() {
-  return EPI == P2V_EPI_RESIDUAL ? 9 : (POT ? (EPI == P2V_EPI_GELU ? 3 : 2) : 5);
+  return EPI == P2V_EPI_RESIDUAL ? (ZP ? 10 : 9) : (POT ? (EPI == P2V_EPI_GELU ? 3 : 2) : 5);
 }
 enum { PR_S = 0, PR_B = 1, PR_RO = 2,                 // POT GELU: 1/out_scale
        PR_OLO = 2, PR_OHI = 3, PR_O = 4,              // general REQUANT / GELU
-       PR_MLO = 2, PR_MHI = 3, PR_M = 4, PR_RS = 5, PR_ROLO = 6, PR_ROHI = 7, PR_RO_ = 8 };   // RESIDUAL
+       PR_ZRO = 2, PR_ZC = 3,                         // ZP REQUANT / GELU: 1/out_scale, zp_corr (int32 bits); PR_O as above
+       PR_MLO = 2, PR_MHI = 3, PR_M = 4, PR_RS = 5, PR_ROLO = 6, PR_ROHI = 7, PR_RO_ = 8, PR_RZC = 9 };   // RESIDUAL (+ zp_corr)
 
 // ---- cluster / 2-SM primitives
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -200,9 +204,9 @@ __device__ __forceinline__ float4 prm_ld4(uint32_t addr) {
   return v;
 }
 // GST: 0 = no GELU step tables, 1 = step tables with the near-threshold distance test, 2 = clean tables (gelu_table.cu), no test
-template <int EPI, bool POT, int GST>
+template <int EPI, bool POT, int GST, bool ZP>
 __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const uint32_t prm, const int (&acc)[16], const uint4 resx, uint4& out,
-                                           const GeluSteps& gst) {
+                                           const GeluSteps& gst, const float out_zp) {
   uint32_t ow[4];
   const uint32_t rw[4] = {resx.x, resx.y, resx.z, resx.w};
   uint32_t gst_near = 0xffffffffu;
@@ -223,11 +227,16 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
       const float4 f4 = prm_ld4(prm + (PR_ROHI * 64 + j4) * 4);
       const float MLv[4] = {a4.x, a4.y, a4.z, a4.w}, MHv[4] = {b4.x, b4.y, b4.z, b4.w}, Mv[4] = {c4.x, c4.y, c4.z, c4.w};
       const float RSv[4] = {d4.x, d4.y, d4.z, d4.w}, OLv[4] = {e4.x, e4.y, e4.z, e4.w}, OHv[4] = {f4.x, f4.y, f4.z, f4.w};
+      int zc[4] = {0, 0, 0, 0};
+      if (ZP) {
+        const float4 z4 = prm_ld4(prm + (PR_RZC * 64 + j4) * 4);
+        zc[0] = __float_as_int(z4.x); zc[1] = __float_as_int(z4.y); zc[2] = __float_as_int(z4.z); zc[3] = __float_as_int(z4.w);
+      }
       float y[4], r[4];
       uint32_t flag = 0;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float af = __int2float_rn(acc[j4 + e]);
+        const float af = __int2float_rn(acc[j4 + e] - zc[e]);
         y[e] = POT ? __fmaf_rn(af, Sv[e], Bv[e]) : fadd(fmul(af, Sv[e]), Bv[e]);
         const float k = fsub(quant_iv<false, true>(y[e], MLv[e], MHv[e], Mv[e], flag), RMAGIC);        // qact after the GEMM (code)
         // residual code: byte e of the word (sign already flipped) -> 2^23 + (code + 128) -> code, exactly
@@ -262,6 +271,18 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
       for (int e = 0; e < 4; ++e) {
         const float y = __fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]);
         t[e] = __fmaf_rn(gelu_erf(y), Rv[e], RMAGIC);      // g * 2^k is exact
+      }
+    } else if (ZP) {
+      const float4 r4 = *reinterpret_cast<const float4*>(prmg + PR_ZRO * 64 + j4);
+      const float4 z4 = *reinterpret_cast<const float4*>(prmg + PR_ZC * 64 + j4);
+      const float4 o4 = *reinterpret_cast<const float4*>(prmg + PR_O * 64 + j4);
+      const float ROv[4] = {r4.x, r4.y, r4.z, r4.w}, Ov[4] = {o4.x, o4.y, o4.z, o4.w};
+      const int zc[4] = {__float_as_int(z4.x), __float_as_int(z4.y), __float_as_int(z4.z), __float_as_int(z4.w)};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float y = fadd(fmul(__int2float_rn(acc[j4 + e] - zc[e]), Sv[e]), Bv[e]);
+        if (EPI == P2V_EPI_GELU) y = gelu_erf(y);
+        t[e] = fadd(fadd(div_rb(y, Ov[e], ROv[e]), out_zp), RMAGIC);
       }
     } else {
       const float4 a4 = *reinterpret_cast<const float4*>(prmg + PR_OLO * 64 + j4);
@@ -307,11 +328,12 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
 }
 
 // per-column constants of columns n (lane's first) and n + 32 (second, if < W): raw values, fetched one tile ahead
-struct RawCol { float s, b, o, m, rs; };
-template <int EPI>
+struct RawCol { float s, b, o, m, rs, zc; };
+template <int EPI, bool ZP>
 __device__ __forceinline__ RawCol load_raw_col(const EpiParams& p, int n, bool ok) {
   RawCol r;
   ok = ok && n < p.N;
+  r.zc = (ZP && ok && p.zp_corr) ? __int_as_float(__ldg(p.zp_corr + n)) : 0.f;
   r.s = ok ? __ldg(p.acc_scale + n) : 0.f;
   r.b = (ok && p.bias) ? __ldg(p.bias + n) : 0.f;
   r.o = ok ? __ldg(p.out_scale + n) : 1.f;
@@ -319,9 +341,15 @@ __device__ __forceinline__ RawCol load_raw_col(const EpiParams& p, int n, bool o
   r.rs = (EPI == P2V_EPI_RESIDUAL && ok) ? __ldg(p.res_scale + n) : 0.f;
   return r;
 }
-template <int EPI, bool POT>
+template <int EPI, bool POT, bool ZP>
 __device__ __forceinline__ void store_col(float* prm, int c, const RawCol& r) {
   const float ro = __frcp_rn(r.o);     // == fdiv(1, o): both correctly rounded
+  if (ZP && EPI != P2V_EPI_RESIDUAL) {
+    prm[PR_S * 64 + c] = r.s; prm[PR_B * 64 + c] = r.b;
+    prm[PR_ZRO * 64 + c] = ro; prm[PR_ZC * 64 + c] = r.zc; prm[PR_O * 64 + c] = r.o;
+    return;
+  }
+  if (ZP) prm[PR_RZC * 64 + c] = r.zc;
   if (EPI == P2V_EPI_RESIDUAL) {
     const float rm = __frcp_rn(r.m);
     prm[PR_S * 64 + c] = r.s; prm[PR_B * 64 + c] = r.b;
@@ -338,12 +366,12 @@ __device__ __forceinline__ void store_col(float* prm, int c, const RawCol& r) {
   }
 }
 
-template <int EPI, bool POT, int GST>
+template <int EPI, bool POT, int GST, bool ZP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                  const __grid_constant__ CUtensorMap tmR, EpiParams p, PairGeom g) {
   constexpr bool RESID = EPI == P2V_EPI_RESIDUAL;
-  constexpr int ROWS = prm_rows<EPI, POT>();
+  constexpr int ROWS = prm_rows<EPI, POT, ZP>();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * P_MAX_STAGES + 13];
   __shared__ uint32_t tmem_slot;
@@ -518,8 +546,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     TileIter ti(g, pair, npairs);
     {
       const int n0 = ti.nt * g.BN + cg * W;
-      nx0 = load_raw_col<EPI>(p, n0 + lane, ti.left > 0 && quarter == 0);          // the quarter-0 warp fills the group's table
-      nx1 = load_raw_col<EPI>(p, n0 + 32 + lane, ti.left > 0 && quarter == 0 && 32 + lane < W);
+      nx0 = load_raw_col<EPI, ZP>(p, n0 + lane, ti.left > 0 && quarter == 0);          // the quarter-0 warp fills the group's table
+      nx1 = load_raw_col<EPI, ZP>(p, n0 + 32 + lane, ti.left > 0 && quarter == 0 && 32 + lane < W);
     }
     pdl_wait();                // everything above read constants; the residual codes and the output buffer come after the dependency
     uint32_t it = 0;
@@ -536,16 +564,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (nt != prm_nt) {       // the four warps of the group walk the same tile sequence: they all take this branch together
         named_barrier(1 + uint32_t(cg), 128);       // every warp of the group is done reading the previous column tile's constants
         if (quarter == 0) {
-          store_col<EPI, POT>(prm, lane, nx0);
-          if (32 + lane < W) store_col<EPI, POT>(prm, 32 + lane, nx1);
+          store_col<EPI, POT, ZP>(prm, lane, nx0);
+          if (32 + lane < W) store_col<EPI, POT, ZP>(prm, 32 + lane, nx1);
         }
         named_barrier(1 + uint32_t(cg), 128);       // ... and sees the new ones
         prm_nt = nt;
       }
       if (ti.left > 0 && ti.nt != nt) {
         const int nn0 = ti.nt * g.BN + cg * W;
-        nx0 = load_raw_col<EPI>(p, nn0 + lane, quarter == 0);
-        nx1 = load_raw_col<EPI>(p, nn0 + 32 + lane, quarter == 0 && 32 + lane < W);
+        nx0 = load_raw_col<EPI, ZP>(p, nn0 + lane, quarter == 0);
+        nx1 = load_raw_col<EPI, ZP>(p, nn0 + 32 + lane, quarter == 0 && 32 + lane < W);
       }
       if (lane == 0) PTRACE(3 + e, it, 0);
       if (RESID) mbar_wait(bar_rfull + 8 * slot, ruse & 1u);
@@ -574,7 +602,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           resx.x ^= 0x80808080u; resx.y ^= 0x80808080u; resx.z ^= 0x80808080u; resx.w ^= 0x80808080u;
         }
         uint4 o;
-        pair_chunk<EPI, POT, GST>(prm + c * 16, prm32 + uint32_t(c) * 64u, cur, resx, o, gst);
+        pair_chunk<EPI, POT, GST, ZP>(prm + c * 16, prm32 + uint32_t(c) * 64u, cur, resx, o, gst, p.out_zp);
         if (c == 0) {
           if (!RESID) {                     // the previous tile's store must have finished reading this block
             if (lane == 0) bulk_wait_read0();
@@ -629,8 +657,10 @@ static int make_tmap_rows(CUtensorMap* m, const void* ptr, int rows, int cols, i
 bool gemm_pair_supported(const p2v_gemm_args& a) {
   const int e = a.epilogue;
   if (e != P2V_EPI_REQUANT && e != P2V_EPI_GELU && e != P2V_EPI_RESIDUAL) return false;
-  if (a.row_map || a.zp_corr || !a.out_i8) return false;
-  if (a.out_zp != 0.f || a.mid_zp != 0.f || a.aux_zp != 0.f) return false;     // asymmetric quantizers: csrc/gemm_tc.cu
+  if (a.row_map || !a.out_i8) return false;
+  if (a.mid_zp != 0.f || a.aux_zp != 0.f) return false;                          // EMBED's zero points: csrc/gemm_tc.cu
+  if ((a.zp_corr || a.out_zp != 0.f) && a.pot_scales) return false;              // zero points come with raw fp32 scales (ZP variants)
+  if (a.out_zp != 0.f && e == P2V_EPI_RESIDUAL) return false;
   if (a.N % 16 || a.K % 16) return false;
   if (reinterpret_cast<uintptr_t>(a.out_i8) & 15) return false;
   if (e == P2V_EPI_RESIDUAL && (reinterpret_cast<uintptr_t>(a.res) & 15)) return false;
@@ -712,10 +742,10 @@ static double pair_cost(const p2v_gemm_args& a, const PairGeom& g, bool gst) {
   return waves * (std::max(load, std::max(mma, g.BN * per_col)) + 1500.0) * handicap;
 }
 
-template <int EPI, bool POT, int GST = 0>
+template <int EPI, bool POT, int GST = 0, bool ZP = false>
 static int launch_pair(const p2v_gemm_args& a, const PairGeom& g, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                        const CUtensorMap& tmR, cudaStream_t stream) {
-  auto kern = gemm_pair_kernel<EPI, POT, GST>;
+  auto kern = gemm_pair_kernel<EPI, POT, GST, ZP>;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(P_SMEM_BUDGET));
@@ -734,7 +764,8 @@ int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
   P2V_REQUIRE(gemm_pair_supported(a), "gemm_pair: unsupported arguments");
   const bool pot = a.pot_scales != 0;
   const bool gst = a.epilogue == P2V_EPI_GELU && pot && a.gelu_table;
-  const int rows = a.epilogue == P2V_EPI_RESIDUAL ? prm_rows<P2V_EPI_RESIDUAL, true>()
+  const bool zpv = !pot && (a.zp_corr != nullptr || a.out_zp != 0.f);
+  const int rows = a.epilogue == P2V_EPI_RESIDUAL ? (zpv ? prm_rows<P2V_EPI_RESIDUAL, false, true>() : prm_rows<P2V_EPI_RESIDUAL, true>())
                    : a.epilogue == P2V_EPI_GELU   ? (pot ? prm_rows<P2V_EPI_GELU, true>() : prm_rows<P2V_EPI_GELU, false>())
                                                   : (pot ? prm_rows<P2V_EPI_REQUANT, true>() : prm_rows<P2V_EPI_REQUANT, false>());
   static const int force_bn = getenv("P2V_PAIR_BN") ? atoi(getenv("P2V_PAIR_BN")) : 0;    // perf triage only
@@ -756,6 +787,13 @@ int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
   tmR = tmO;
   if (a.epilogue == P2V_EPI_RESIDUAL)
     if (int r = make_tmap_rows(&tmR, a.res, a.M, a.N, g.W, 32, oswz)) return r;
+  if (zpv) {
+    switch (a.epilogue) {
+      case P2V_EPI_REQUANT: return launch_pair<P2V_EPI_REQUANT, false, 0, true>(a, g, tmA, tmB, tmO, tmR, stream);
+      case P2V_EPI_GELU: return launch_pair<P2V_EPI_GELU, false, 0, true>(a, g, tmA, tmB, tmO, tmR, stream);
+      default: return launch_pair<P2V_EPI_RESIDUAL, false, 0, true>(a, g, tmA, tmB, tmO, tmR, stream);
+    }
+  }
   switch (a.epilogue) {
     case P2V_EPI_REQUANT:
       return pot ? launch_pair<P2V_EPI_REQUANT, true>(a, g, tmA, tmB, tmO, tmR, stream)

@@ -522,11 +522,6 @@ __global__ void __launch_bounds__(128, (WPLN <= 3 && !GATHER) ? 4 : 3) layernorm
 // row): the register-resident form of the power-of-two kernel would need 6 x 24 registers at C = 768.
 // ViT-B percentile: 6.8 ms of LayerNorm per 256 images with the generic kernel (r2).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float div_rb(float a, float b, float rb) {
-  const float q0 = fmul(a, rb);
-  const float q1 = __fmaf_rn(__fmaf_rn(-b, q0, a), rb, q0);
-  return __fmaf_rn(__fmaf_rn(-b, q1, a), rb, q1);
-}
 // one lane's words of a row in the reference's operation order (the generic kernel's element code)
 __device__ __noinline__ void ln_np_row_slow(const p2v_layernorm_args& a, int row, uint32_t* __restrict__ orow, int sub, int lpr, int wpln,
                                             float t, float mos) {

@@ -304,6 +304,44 @@ def test_gemm_pair_gelu(M, N, K, pot):
     assert d.max() <= 1 and (d != 0).float().mean() < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(1300, 1152, 384), (1100, 1536, 384), (1024, 384, 1536), (700, 96, 96)])
+@pytest.mark.parametrize("epi", ["requant", "gelu", "residual"])
+def test_gemm_pair_zero_points(M, N, K, epi):
+    """asymmetric quantizers (omse) on the CTA-pair kernel: zp_corr subtracted from the accumulator, output zero point added to the
+    exactly rounded quotient (uniform.py:83-86) - equal to the one-tile kernel bit for bit and to the fp32 reference sequence"""
+    A, W, bias = _gemm_inputs(M, N, K, 180)
+    torch.manual_seed(181)
+    acc_scale = (torch.rand(N) * 3e-5 + 5e-5).to(DEV)
+    zp_in, out_zp = 11, -23.0
+    zc = (zp_in * W.long().sum(dim=1)).to(torch.int32).to(DEV)
+    Ad, Wd, bd = A.to(DEV), W.to(DEV), bias.to(DEV)
+    y = (_acc_exact(A, W) - zc.long()).float() * acc_scale + bd
+    if epi == "residual":
+        fac = torch.tensor([1.0, 2.0, 4.0, 8.0])
+        mid = (0.00931 * fac[torch.randint(0, 4, (N,))]).to(DEV)
+        rs = (0.0123 * fac[torch.randint(0, 4, (N,))]).to(DEV)
+        outs = (0.0171 * fac[torch.randint(0, 4, (N,))]).to(DEV)
+        res = _rand_codes(M, N, seed=182).to(DEV)
+        c = (y / mid).round().clamp(-128, 127)
+        ref = ((res.float() * rs + c * mid) / outs).round().clamp(-128, 127)
+        old, new = _run_variants(lambda o8: ops.gemm_args(Ad, Wd, ops.EPI_RESIDUAL, acc_scale, bias=bd, out_scale=outs, mid_scale=mid,
+                                                           res_scale=rs, res=res, out_i8=o8, zp_corr=zc), M, N)
+        assert torch.equal(new.float(), ref), "pair kernel: %d mismatches vs the exact reference" % int((new.float() != ref).sum())
+    else:
+        out_scale = (torch.rand(N) * 0.02 + 0.02).to(DEV)
+        code = ops.EPI_GELU if epi == "gelu" else ops.EPI_REQUANT
+        old, new = _run_variants(lambda o8: ops.gemm_args(Ad, Wd, code, acc_scale, bias=bd, out_scale=out_scale, out_i8=o8, zp_corr=zc,
+                                                           out_zp=out_zp), M, N)
+        v = torch.nn.functional.gelu(y) if epi == "gelu" else y
+        ref = (v / out_scale + out_zp).round().clamp(-128, 127)
+        d = (new.float() - ref).abs()
+        if epi == "gelu":       # erf implementations differ by an ulp on rare inputs: only rounding ties can flip
+            assert d.max() <= 1 and (d != 0).float().mean() < 2e-5
+        else:
+            assert torch.equal(new.float(), ref), "pair kernel: %d mismatches vs the exact reference" % int((d != 0).sum())
+    assert torch.equal(old, new), "%d codes differ between the two tcgen05 kernels" % int((old != new).sum())
+
+
 @pytest.mark.parametrize("M,N,K", [(394, 384, 384), (300, 384, 1536), (197, 192, 768)])
 def test_gemm_residual_ptf(M, N, K):
     A, W, bias = _gemm_inputs(M, N, K, 40)
