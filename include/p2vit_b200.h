@@ -124,9 +124,11 @@ typedef struct {
  * boundary on each side of GELU's minimum, laid out so that the epilogue's lookups are free of bank conflicts.  The builder
  * checks it against the direct evaluation on ~2.3 M arguments (every threshold +-256 ulps, a dense grid, 200 binades). */
 #define P2V_GELU_TABLE_BYTES (16 + 8 * P2V_GELU_TABLE_MAX_ENTRIES + 64 + 8 * 64 + 4 * 512)
-/* returns 0 and fills `table_dev` (P2V_GELU_TABLE_BYTES bytes, 16-byte aligned), or 3 if out_scale is not a power of two in
- * the tabulated range 2^-7 .. 2^-2 or a form failed its self-check (the caller then passes gelu_table = NULL and the kernels
- * evaluate erf per element).  Synchronises `stream` once (the verdict of the self-check is read back). */
+/* returns 0 and fills `table_dev` (P2V_GELU_TABLE_BYTES bytes, 16-byte aligned), or 3 if out_scale is outside the tabulated
+ * range 2^-7 .. 2^-2 or a form failed its self-check (the caller then passes gelu_table = NULL and the kernels evaluate erf per
+ * element).  An out_scale that is not a power of two (ema / percentile observers, zero point 0) gets the second form only
+ * (first form: n = 0), with thresholds found on the reference's division gelu(y) / out_scale; the kernels that read the first
+ * form ignore the table unless pot_scales is set.  Synchronises `stream` once (the verdict of the self-check is read back). */
 int p2v_build_gelu_table(float out_scale, void* table_dev, void* stream);
 
 int p2v_gemm_i8(const p2v_gemm_args* args_host, void* stream);

@@ -112,6 +112,8 @@ struct GeluTabHeader { float y0, inv_w; int n, reserved; };
 struct GeluTab { const uint2* entries; int n; float inv_w, off; };   // entries may live in shared or global memory
 // the reference arithmetic: qact1(gelu(y)) for a power-of-two output scale (ro = 1/out_scale)
 __device__ __forceinline__ int gelu_code_direct(float y, float ro) { return sat_s8(fmul(gelu_erf(y), ro)); }
+// the same for any output scale: the reference's division (equal to the product above when the scale is a power of two)
+__device__ __forceinline__ int gelu_code_div(float y, float so) { return sat_s8(fdiv(gelu_erf(y), so)); }
 // segment of y; the SAME expression builds the table and looks it up, so its own rounding is immaterial
 __device__ __forceinline__ int gelu_segment(float y, float inv_w, float off, int n) {
   return min(max(__float2int_rd(__fmaf_rn(y, inv_w, off)), 0), n - 1);

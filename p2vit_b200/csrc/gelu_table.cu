@@ -76,12 +76,12 @@ __global__ void __launch_bounds__(128) build_gelu_table_kernel(GeluTabHeader hd,
 // thread i: threshold of code boundary c = cr0 + i (right of y*: smallest y with code >= c) or, for i >= nr, c = cr0 + i - nr
 // (left of y*: smallest y with code < c, the code being non-increasing in y there); +-inf when the boundary is never / always
 // crossed on that branch.  A threshold whose neighbourhood is not a clean step outside the +-8 ulp band clears *ok.
-__global__ void __launch_bounds__(128) build_gelu_steps_kernel(GeluStepsHeader h, float ro, int cr0, float* __restrict__ thr, int* __restrict__ ok) {
+__global__ void __launch_bounds__(128) build_gelu_steps_kernel(GeluStepsHeader h, float so, int cr0, float* __restrict__ thr, int* __restrict__ ok) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h.nr + h.nl) return;
   const bool left = i >= h.nr;
   const int c = cr0 + (left ? i - h.nr : i);
-  auto F = [&](uint32_t k) { return gelu_code_direct(key2f(k), ro); };
+  auto F = [&](uint32_t k) { return gelu_code_div(key2f(k), so); };
   const uint32_t k_star = f2key(h.ystar), k_lo = left ? f2key(h.ymin) : k_star, k_hi = left ? k_star : f2key(h.ymax);
   // on [k_lo, k_hi] the predicate Q(k) = (code >= c) on the right branch, (code < c) on the left one, goes from false to true
   auto Q = [&](uint32_t k) { return left ? F(k) < c : F(k) >= c; };
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128) build_gelu_steps_kernel(GeluStepsHeader h
 // evaluation (near_min > 16) must get exactly the direct code.  A mismatch clears *ok.  A y inside the band whose step code
 // differs from the direct one clears *clean: the band around every threshold is scanned exhaustively, so a table that keeps
 // `clean` needs no distance test in the epilogue.
-__global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __restrict__ table, float ro, int* __restrict__ ok, int* __restrict__ clean) {
+__global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __restrict__ table, float so, int* __restrict__ ok, int* __restrict__ clean) {
   extern __shared__ uint8_t vsm[];
   const uint32_t base = (uint32_t(__cvta_generic_to_shared(vsm)) + 255u) & ~255u;
   gelu_steps_fill_smem(table, base, int(threadIdx.x), int(blockDim.x));
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __re
   auto check = [&](float y) {
     uint32_t nm = 0xffffffffu;
     const int c = int(int8_t(gelu_steps_code(y, t, nm) & 0xffu));
-    if (c != gelu_code_direct(y, ro)) {
+    if (c != gelu_code_div(y, so)) {
       if (nm > 16u) bad = true; else unclean = true;
     }
   };
@@ -228,7 +228,7 @@ static int build_gelu_steps(float out_scale, void* table_dev, cudaStream_t strea
   cudaMemcpyAsync(base + sizeof(h), seg.data(), seg.size() * sizeof(float2), cudaMemcpyHostToDevice, stream);
   int* ok_dev = &reinterpret_cast<GeluStepsHeader*>(base)->ok;
   float* thr_dev = reinterpret_cast<float*>(base + sizeof(h) + 8 * P2V_GELU_STEPS_MAX_SEG);
-  build_gelu_steps_kernel<<<(h.nr + h.nl + 127) / 128, 128, 0, stream>>>(h, 1.0f / out_scale, cr0, thr_dev, ok_dev);
+  build_gelu_steps_kernel<<<(h.nr + h.nl + 127) / 128, 128, 0, stream>>>(h, out_scale, cr0, thr_dev, ok_dev);
   const size_t smem = gelu_steps_smem_bytes(h) + 256;
   static bool attr = false;
   if (!attr) {
@@ -236,7 +236,7 @@ static int build_gelu_steps(float out_scale, void* table_dev, cudaStream_t strea
     attr = true;
   }
   int* clean_dev = &reinterpret_cast<GeluStepsHeader*>(base)->clean;
-  verify_gelu_steps_kernel<<<64, 256, smem, stream>>>(table_dev, 1.0f / out_scale, ok_dev, clean_dev);
+  verify_gelu_steps_kernel<<<64, 256, smem, stream>>>(table_dev, out_scale, ok_dev, clean_dev);
   count_launch(2);
   if (int r = check_launch("build_gelu_steps")) return r;
   GeluStepsHeader back;
@@ -253,15 +253,23 @@ static int build_gelu_steps(float out_scale, void* table_dev, cudaStream_t strea
 int launch_build_gelu_table(float out_scale, void* table_dev, cudaStream_t stream) {
   int ex = 0;
   const float m = frexpf(out_scale, &ex);
-  if (!(out_scale > 0.f) || m != 0.5f) return 3;                     // power of two only
+  if (!(out_scale > 0.f) || !(out_scale < 1e30f)) return 3;
+  GeluTabHeader hd;
+  hd.y0 = -8.5f;
+  hd.reserved = 0;
+  if (m != 0.5f) {
+    // not a power of two (ema / percentile observers): only the second form - its thresholds come from the reference's own
+    // division gelu(y) / out_scale, so it holds for any scale; the first form (one-tile and dp4a kernels) stays empty
+    hd.inv_w = 0.f;
+    hd.n = 0;
+    cudaMemcpyAsync(table_dev, &hd, sizeof(hd), cudaMemcpyHostToDevice, stream);
+    return build_gelu_steps(out_scale, table_dev, stream);
+  }
   const double inv_w = 2.0 / double(out_scale);                      // segment width out_scale / 2
   const double n_d = (8.5 + 128.0 * double(out_scale) + 0.5) * inv_w;
   if (n_d > double(P2V_GELU_TABLE_MAX_ENTRIES) || n_d < 4.0) return 3;
-  GeluTabHeader hd;
-  hd.y0 = -8.5f;
   hd.inv_w = float(inv_w);
   hd.n = int(n_d);
-  hd.reserved = 0;
   cudaMemcpyAsync(table_dev, &hd, sizeof(hd), cudaMemcpyHostToDevice, stream);   // pageable source: staged before the call returns
   build_gelu_table_kernel<<<(hd.n + 127) / 128, 128, 0, stream>>>(hd, 1.0f / out_scale,
                                                                    reinterpret_cast<uint2*>(reinterpret_cast<char*>(table_dev) + sizeof(hd)));

@@ -255,13 +255,16 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
     } else if (POT && EPI == P2V_EPI_REQUANT) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) t[e] = quant_pot(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]));   // S, B pre-divided by out_scale
-    } else if (POT && EPI == P2V_EPI_GELU && GST) {
+    } else if (EPI == P2V_EPI_GELU && GST && !ZP) {
       // step tables (common.cuh: gelu_steps_code): ~19 instructions per column (9 ALU-pipe, 8 FMA-pipe) instead of ~40 for erff.  No branch inside the
       // chunk, so the 16 columns' lookup chains (two dependent shared-memory loads each) overlap; the near-threshold test is
       // taken once per chunk, after the loop.
       uint32_t q[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) q[e] = gelu_steps_code<GST == 1>(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]), gst, gst_near);
+      for (int e = 0; e < 4; ++e) {
+        const float af = __int2float_rn(acc[j4 + e]);
+        q[e] = gelu_steps_code<GST == 1>(POT ? __fmaf_rn(af, Sv[e], Bv[e]) : fadd(fmul(af, Sv[e]), Bv[e]), gst, gst_near);
+      }
       ow[j4 >> 2] = pack4_low_bytes(q[0], q[1], q[2], q[3]);
       continue;
     } else if (POT && EPI == P2V_EPI_GELU) {
@@ -305,21 +308,21 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
     }
     ow[j4 >> 2] = pack4_sat(t[0], t[1], t[2], t[3]);
   }
-  if (POT && EPI == P2V_EPI_GELU && GST == 1) {
+  if (EPI == P2V_EPI_GELU && GST == 1 && !ZP) {
     if (gst_near <= 16u) {     // some y within 8 ulps of the threshold it consulted: the chunk takes the direct evaluation
 #pragma unroll 1
       for (int j4 = 0; j4 < 16; j4 += 4) {
         const float4 S4 = *reinterpret_cast<const float4*>(prmg + PR_S * 64 + j4);
         const float4 B4 = *reinterpret_cast<const float4*>(prmg + PR_B * 64 + j4);
-        const float4 R4 = *reinterpret_cast<const float4*>(prmg + PR_RO * 64 + j4);
+        const float4 R4 = *reinterpret_cast<const float4*>(prmg + (POT ? PR_RO : PR_O) * 64 + j4);     // POT: 1 / out_scale, else out_scale
         const int a0 = j4 == 0 ? acc[0] : j4 == 4 ? acc[4] : j4 == 8 ? acc[8] : acc[12];
         const int a1 = j4 == 0 ? acc[1] : j4 == 4 ? acc[5] : j4 == 8 ? acc[9] : acc[13];
         const int a2 = j4 == 0 ? acc[2] : j4 == 4 ? acc[6] : j4 == 8 ? acc[10] : acc[14];
         const int a3 = j4 == 0 ? acc[3] : j4 == 4 ? acc[7] : j4 == 8 ? acc[11] : acc[15];
-        const uint32_t w = pack4_sat_int(gelu_code_direct(__fmaf_rn(__int2float_rn(a0), S4.x, B4.x), R4.x),
-                                         gelu_code_direct(__fmaf_rn(__int2float_rn(a1), S4.y, B4.y), R4.y),
-                                         gelu_code_direct(__fmaf_rn(__int2float_rn(a2), S4.z, B4.z), R4.z),
-                                         gelu_code_direct(__fmaf_rn(__int2float_rn(a3), S4.w, B4.w), R4.w));
+        auto code = [&](int a, float S, float B, float R) {
+          return POT ? gelu_code_direct(__fmaf_rn(__int2float_rn(a), S, B), R) : gelu_code_div(fadd(fmul(__int2float_rn(a), S), B), R);
+        };
+        const uint32_t w = pack4_sat_int(code(a0, S4.x, B4.x, R4.x), code(a1, S4.y, B4.y, R4.y), code(a2, S4.z, B4.z, R4.z), code(a3, S4.w, B4.w, R4.w));
         if (j4 == 0) ow[0] = w; else if (j4 == 4) ow[1] = w; else if (j4 == 8) ow[2] = w; else ow[3] = w;
       }
     }
@@ -763,7 +766,7 @@ static int launch_pair(const p2v_gemm_args& a, const PairGeom& g, const CUtensor
 int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
   P2V_REQUIRE(gemm_pair_supported(a), "gemm_pair: unsupported arguments");
   const bool pot = a.pot_scales != 0;
-  const bool gst = a.epilogue == P2V_EPI_GELU && pot && a.gelu_table;
+  const bool gst = a.epilogue == P2V_EPI_GELU && a.gelu_table && (pot || (a.zp_corr == nullptr && a.out_zp == 0.f));
   const bool zpv = !pot && (a.zp_corr != nullptr || a.out_zp != 0.f);
   const int rows = a.epilogue == P2V_EPI_RESIDUAL ? (zpv ? prm_rows<P2V_EPI_RESIDUAL, false, true>() : prm_rows<P2V_EPI_RESIDUAL, true>())
                    : a.epilogue == P2V_EPI_GELU   ? (pot ? prm_rows<P2V_EPI_GELU, true>() : prm_rows<P2V_EPI_GELU, false>())
@@ -799,8 +802,10 @@ int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
       return pot ? launch_pair<P2V_EPI_REQUANT, true>(a, g, tmA, tmB, tmO, tmR, stream)
                  : launch_pair<P2V_EPI_REQUANT, false>(a, g, tmA, tmB, tmO, tmR, stream);
     case P2V_EPI_GELU:
-      if (gst) return gelu_table_is_clean(a.gelu_table) ? launch_pair<P2V_EPI_GELU, true, 2>(a, g, tmA, tmB, tmO, tmR, stream)
-                                                        : launch_pair<P2V_EPI_GELU, true, 1>(a, g, tmA, tmB, tmO, tmR, stream);
+      if (gst && pot) return gelu_table_is_clean(a.gelu_table) ? launch_pair<P2V_EPI_GELU, true, 2>(a, g, tmA, tmB, tmO, tmR, stream)
+                                                               : launch_pair<P2V_EPI_GELU, true, 1>(a, g, tmA, tmB, tmO, tmR, stream);
+      if (gst) return gelu_table_is_clean(a.gelu_table) ? launch_pair<P2V_EPI_GELU, false, 2>(a, g, tmA, tmB, tmO, tmR, stream)
+                                                        : launch_pair<P2V_EPI_GELU, false, 1>(a, g, tmA, tmB, tmO, tmR, stream);
       return pot ? launch_pair<P2V_EPI_GELU, true>(a, g, tmA, tmB, tmO, tmR, stream)
                  : launch_pair<P2V_EPI_GELU, false>(a, g, tmA, tmB, tmO, tmR, stream);
     default:

@@ -118,8 +118,8 @@ _gelu_tables = {}
 
 
 def gelu_table(out_scale, device):
-    """device-resident step table of y -> qact(gelu(y)) for a power-of-two output scale (None if the scale is not tabulable);
-    cached per (scale, device)"""
+    """device-resident step table of y -> qact(gelu(y)) for a symmetric output scale (None if the scale is not tabulable); a scale
+    that is not a power of two gets the CTA-pair kernel's form only; cached per (scale, device)"""
     key = (float(out_scale), str(device))
     if key not in _gelu_tables:
         t = torch.empty(_lib.GELU_TABLE_BYTES, dtype=torch.uint8, device=device)

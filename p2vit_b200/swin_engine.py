@@ -152,7 +152,7 @@ class SwinPlan:
                 p["fc1"] = _Gemm(mlp.fc1, mlp.fc1.weight * cs.reshape(1, -1), 8, m0, dev)
                 p["fc1_out"] = _vec(m1, p["fc1"].N, dev)
                 p["fc1_pot"] = intmath.is_pot(m1)
-                p["gelu_tab"] = ops.gelu_table(float(m1), dev) if p["fc1_pot"] else None
+                p["gelu_tab"] = ops.gelu_table(float(m1), dev)
                 p["fc2"] = _Gemm(mlp.fc2, mlp.fc2.weight, 8, m1, dev)
                 p["fc2_mid"] = _vec(_sym_scale(mlp.qact2, "mlp.qact2"), C, dev)
                 s_b4 = _vec(_sym_scale(blk.qact4, "block.qact4"), C, dev)

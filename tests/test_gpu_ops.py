@@ -207,6 +207,36 @@ def test_gemm_pair_gelu_step_tables_equal_direct_erf(log2so):
         ops.set_gemm_variant(0)
 
 
+@pytest.mark.parametrize("so", [0.0234, 0.0117, 0.0871, 0.2, 0.0331, 0.0502])
+def test_gemm_pair_gelu_step_tables_any_scale(so):
+    """output scales that are not powers of two (ema / percentile observers): the step tables are built on the reference's own
+    division gelu(y) / scale, and the CTA-pair kernel must reproduce its direct erf epilogue bit for bit with them"""
+    tab = ops.gelu_table(so, DEV)
+    if tab is None:     # the builder's self-check found a threshold that is not a clean step of erff for this scale: direct erf is used
+        pytest.skip("scale %g is not tabulated" % so)
+    M, N, K = 2048 + 77, 256, 64
+    A, W, _ = _gemm_inputs(M, N, K, 190)
+    Ad, Wd = A.to(DEV), W.to(DEV)
+    outs = torch.full((N,), so, device=DEV)
+    cases = ((1.37e-4, torch.randn(N) * 0.5), (1.7e-5, torch.linspace(-9.0, 5.0, N)), (9.1e-7, torch.linspace(-1.5, 0.5, N)),
+             (3.3e-6, torch.linspace(-0.9, -0.6, N)), (4.1e-3, torch.randn(N) * 3), (2.9e-7, torch.linspace(-4.0, 130.0 * so, N)))
+    try:
+        ops.set_gemm_variant(2)
+        for acc_scale, bias in cases:
+            s = (torch.full((N,), acc_scale) * (1.0 + 0.1 * torch.rand(N))).to(DEV)
+            res = []
+            for table in (None, tab):
+                o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
+                ops.gemm(ops.gemm_args(Ad, Wd, ops.EPI_GELU, s, bias=bias.to(DEV), out_scale=outs, out_i8=o8, pot=False, gelu_table=table))
+                res.append(o8)
+            torch.cuda.synchronize()
+            assert torch.equal(res[0], res[1]), "acc_scale %g: %d codes differ between step tables and direct erf" % (
+                acc_scale, int((res[0] != res[1]).sum()))
+            assert int(res[0].float().abs().sum()) > 0
+    finally:
+        ops.set_gemm_variant(0)
+
+
 def test_gelu_table_rejects_unsupported_scales():
     assert ops.gelu_table(0.3, DEV) is None and ops.gelu_table(2.0 ** -9, DEV) is None
 
