@@ -395,11 +395,27 @@ __device__ __forceinline__ uint32_t ln_pot_fast_word(float t, float mos, const f
 //   Bv = RNE(fl(fl(b - fl(m*g))*ros)*2^N) == RNE(fl(b' - fl(m*g'))*2^N),  b' = b*ros
 //   q  = sat(RNE(((yq*os)/pd)/next))  == sat(RNE(yq*f))
 // (scaling by a power of two commutes with rounding), so the codes equal the generic kernel's bit for bit.
+// Sums of two integers over each group of LPR lanes, every lane of the warp taking part.  A full warp is one REDUX each; for
+// groups of 8 / 16 lanes __reduce_add_sync with the group's own mask compiles to a uniformity test and, the masks differing
+// between the groups, a WARPSYNC.COLLECTIVE loop over them - C = 96 ran at 342 Gelement/s against 877 at C = 384 (r2) - so they
+// take xor butterflies, which never leave the group.
+template <int LPR>
+__device__ __forceinline__ void group_sum2(int& a, int& b) {
+  if (LPR == 32) {
+    a = __reduce_add_sync(0xffffffffu, a);
+    b = __reduce_add_sync(0xffffffffu, b);
+  } else {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+  }
+}
 template <int LPR, int WPLN, bool CLAMP_MID, bool GATHER>
 __global__ void __launch_bounds__(128, (WPLN <= 3 && !GATHER) ? 4 : 3) layernorm_pot_kernel(p2v_layernorm_args a) {
   constexpr int GPW = 32 / LPR;                       // rows per warp iteration
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
-  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int row_stride = gridDim.x * (blockDim.x >> 5) * GPW;
   float g[WPLN][4], bt[WPLN][4], f[WPLN][4];
@@ -465,8 +481,7 @@ __global__ void __launch_bounds__(128, (WPLN <= 3 && !GATHER) ? 4 : 3) layernorm
 #pragma unroll
       for (int e = 0; e < 4; ++e) { S1 += xv[i][e]; S2 += xv[i][e] * xv[i][e]; }
     }
-    S1 = __reduce_add_sync(gmask, S1);
-    S2 = __reduce_add_sync(gmask, S2);
+    group_sum2<LPR>(S1, S2);
     const float S1f = float(S1), S2f = float(S2);
     const float mean = fmul(fdiv(S1f, Cf), s1);
     const float stdv = fmul(s1c, __fsqrt_rn(fsub(fmul(Cf, S2f), fmul(S1f, S1f))));
@@ -487,14 +502,18 @@ __global__ void __launch_bounds__(128, (WPLN <= 3 && !GATHER) ? 4 : 3) layernorm
       for (int i = 0; i < WPLN; ++i) orow[sub + LPR * i] = qw[i];
     }
   };
-  const int row0 = warp_global * GPW + grp;
-  if (row0 >= a.rows) return;
+  // All 32 lanes stay in the loop (the lane groups of a warp's last iteration that have no row left redo the last row and skip
+  // the store), so the group sums are full-mask butterflies - see group_sum2.
+  const int rb0 = warp_global * GPW;
+  if (rb0 >= a.rows) return;
+  const int last = a.rows - 1;
   // (Measured and rejected, r2: two rows in flight - the statistics chain of row n + 1 in the same straight-line block as the
   // element loop of row n, 143 registers - 23.3 vs 22.5 us at C = 384 stand-alone, 0.74 vs 0.71 ms per DeiT-S step.)
   uint32_t ucur[WPLN], unext[WPLN];
-  load_row(row0, ucur);
-  for (int row = row0; row < a.rows; row += row_stride) {
-    if (row + row_stride < a.rows) load_row(row + row_stride, unext);
+  load_row(min(rb0 + grp, last), ucur);
+  for (int rb = rb0; rb < a.rows; rb += row_stride) {
+    const int row = rb + grp;
+    if (rb + row_stride < a.rows) load_row(min(rb + row_stride + grp, last), unext);
     int xv[WPLN][4];
     float t, mos;
     row_stats(ucur, xv, t, mos);
@@ -506,7 +525,7 @@ __global__ void __launch_bounds__(128, (WPLN <= 3 && !GATHER) ? 4 : 3) layernorm
 #pragma unroll
       for (int i = 0; i < WPLN; ++i) qw[i] = ln_pot_fast_word<CLAMP_MID>(t, mos, g[i], bt[i], f[i], xv[i], mant_max);
     }
-    finish_row(row, t, mos, qw, mant_max);
+    if (row <= last) finish_row(row, t, mos, qw, mant_max);
   }
 }
 
@@ -560,7 +579,6 @@ __global__ void __launch_bounds__(128, 4) layernorm_np_kernel(p2v_layernorm_args
   extern __shared__ float4 ln_np_sm[];                 // [6][C / 4]: gamma, beta, out_scale, 1 / out_scale, 1 / post_div, in_mult
   constexpr int GPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
-  const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int row_stride = gridDim.x * (blockDim.x >> 5) * GPW;
   const int nw = a.C >> 2;
@@ -609,17 +627,20 @@ __global__ void __launch_bounds__(128, 4) layernorm_np_kernel(p2v_layernorm_args
   const float Cf = float(a.C), s1 = a.in_scale_min, s1c = fdiv(s1, Cf);
   pdl_wait();
   pdl_trigger();
-  const int row0 = warp_global * GPW + grp;
-  if (row0 >= a.rows) return;
+  const int rb0 = warp_global * GPW;
+  if (rb0 >= a.rows) return;
+  const int last = a.rows - 1;
   auto load_row = [&](int row, uint32_t (&u)[WPLN]) {
     const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
 #pragma unroll
     for (int i = 0; i < WPLN; ++i) u[i] = __ldg(xr + sub + LPR * i);
   };
   uint32_t ucur[WPLN], unext[WPLN];
-  load_row(row0, ucur);
-  for (int row = row0; row < a.rows; row += row_stride) {
-    if (row + row_stride < a.rows) load_row(row + row_stride, unext);
+  load_row(min(rb0 + grp, last), ucur);
+  for (int rb = rb0; rb < a.rows; rb += row_stride) {      // every lane stays in the loop: see layernorm_pot_kernel
+    const int row = min(rb + grp, last);
+    const bool live = rb + grp <= last;
+    if (rb + row_stride < a.rows) load_row(min(rb + row_stride + grp, last), unext);
     int xv[WPLN][4];
     int S1 = 0, S2 = 0;
 #pragma unroll
@@ -632,8 +653,7 @@ __global__ void __launch_bounds__(128, 4) layernorm_np_kernel(p2v_layernorm_args
       for (int e = 0; e < 4; ++e) { S1 += xv[i][e]; S2 += xv[i][e] * xv[i][e]; }
       ucur[i] = unext[i];
     }
-    S1 = __reduce_add_sync(gmask, S1);
-    S2 = __reduce_add_sync(gmask, S2);
+    group_sum2<LPR>(S1, S2);
     const float S1f = float(S1), S2f = float(S2);
     const float mean = fmul(fdiv(S1f, Cf), s1);
     const float stdv = fmul(s1c, __fsqrt_rn(fsub(fmul(Cf, S2f), fmul(S1f, S1f))));
@@ -670,6 +690,7 @@ __global__ void __launch_bounds__(128, 4) layernorm_np_kernel(p2v_layernorm_args
         qw[i] = pack4_sat(r[0], r[1], r[2], r[3]);
       }
     }
+    if (!live) continue;
     if (!in_range || mant_max >= 0x007ffff0u) {
       ln_np_row_slow(a, row, orow, sub, LPR, WPLN, t, mos);
     } else {
