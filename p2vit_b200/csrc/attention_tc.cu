@@ -51,11 +51,16 @@ constexpr uint32_t AT_SMEM = AT_OFF_BARS + 64;
 // The kernel has no static shared memory, so its dynamic window starts at the 1 KB the system reserves per CTA and is
 // 1024-aligned already; 128 bytes of slack, checked at run time (two CTAs of 112 KB + tables have to fit one SM).
 constexpr size_t AT_SMEM_ALLOC = AT_SMEM + 128;
-// Asymmetric qact1 (zero point z, omse observers): a constant tile of the byte -z (one K / V tile large) turns the correction
-// terms into MMAs on the same accumulators,  (q - z)(k - z) = q k + (-z) k + q (-z) + dh z^2  and  P (v - z) = P v + P (-z),
-// so the softmax warps only add the scalar dh z^2.  The tile costs 14 KB: one CTA per SM for that variant.
-constexpr uint32_t AT_OFF_ZC = (AT_SMEM + 1023u) & ~1023u;
-constexpr size_t AT_SMEM_ALLOC_ZP = AT_OFF_ZC + AT_KV_ROWS * AT_DH + 128;
+// Asymmetric qact1 (zero point z, omse observers): a constant tile of the byte -z turns the correction terms into MMAs on the
+// same accumulators,  (q - z)(k - z) = q k + (-z) k + q (-z) + dh z^2  and  P (v - z) = P v + P (-z),  so the softmax warps only
+// add the scalar dh z^2.  Every byte of that tile is the same, so one 512-byte swizzle atom stands for all of it: the operand
+// descriptors carry a stride of ZERO between the 8-row groups (K-major, the q / k side) and between the k atoms (MN-major, the
+// v side), and the MMA reads the same atom for every group.  The atom fits behind the barriers with no slack left
+// (2 x (115 712 + 1 024 reserved) = the SM's 228 KB), so the variant keeps two CTAs per SM; a 14-KB tile (r2 start) meant one.
+constexpr uint32_t AT_OFF_ZC = (AT_SMEM + 511u) & ~511u;
+constexpr uint32_t AT_ZC_BYTES = 512;
+constexpr size_t AT_SMEM_ALLOC_ZP = AT_OFF_ZC + AT_ZC_BYTES;
+static_assert(2 * (AT_SMEM_ALLOC_ZP + 1024) <= 228 * 1024, "two CTAs of the zero-point variant must fit one SM");
 static_assert(AT_OFF_K % 1024 == 0 && AT_OFF_V % 1024 == 0 && AT_OFF_P % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 struct AttTcParams {
@@ -107,7 +112,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   static_assert(!(POTM && ZP), "zero points come with raw fp32 scales");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  if (base - smem_u32(smem_raw) + (ZP ? AT_OFF_ZC + AT_KV_ROWS * AT_DH : AT_SMEM) > uint32_t(ZP ? AT_SMEM_ALLOC_ZP : AT_SMEM_ALLOC)) __trap();     // dynamic window not aligned as assumed
+  if (base - smem_u32(smem_raw) + (ZP ? AT_OFF_ZC + AT_ZC_BYTES : AT_SMEM) > uint32_t(ZP ? AT_SMEM_ALLOC_ZP : AT_SMEM_ALLOC)) __trap();     // dynamic window not aligned as assumed
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + AT_OFF_BARS;
   const uint32_t bar_qk = bars, bar_v = bars + 8, bar_s = bars + 16, bar_p = bars + 24, bar_o = bars + 32, bar_free = bars + 40;
@@ -133,7 +138,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (ZP) {
     const uint32_t zb = uint32_t(p.zp_qkv == -128 ? 64 : -p.zp_qkv) & 0xffu;
     const uint32_t zw = zb * 0x01010101u;
-    for (int i = threadIdx.x; i < AT_KV_ROWS * AT_DH / 16; i += AT_THREADS)
+    for (int i = threadIdx.x; i < int(AT_ZC_BYTES) / 16; i += AT_THREADS)
       asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + AT_OFF_ZC + uint32_t(i) * 16u), "r"(zw) : "memory");
     fence_proxy_async_smem();
   }
@@ -187,10 +192,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               for (int rep = 0; rep < zreps; ++rep)
 #pragma unroll
                 for (int k = 0; k < AT_DH / 32; ++k) {
-                  umma_i8(tmem_base, make_smem_desc(base + AT_OFF_ZC + k * 32, 16, 512, UMMA_LAYOUT_SW64),
+                  umma_i8(tmem_base, make_smem_desc(base + AT_OFF_ZC + k * 32, 16, 0, UMMA_LAYOUT_SW64),
                           make_smem_desc(base + AT_OFF_K + k * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_qk, 1u);
                   umma_i8(tmem_base, make_smem_desc(base + AT_OFF_Q + mt * 128 * AT_DH + k * 32, 16, 512, UMMA_LAYOUT_SW64),
-                          make_smem_desc(base + AT_OFF_ZC + k * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_qk, 1u);
+                          make_smem_desc(base + AT_OFF_ZC + k * 32, 16, 0, UMMA_LAYOUT_SW64), idesc_qk, 1u);
                 }
             }
             tc_commit(bar_s);
@@ -216,7 +221,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                   for (int ks = 0; ks < p.ksteps; ++ks)
                     umma_i8(tmem_base + plane * AT_DH,
                             make_kmajor_sw128_desc(base + AT_OFF_P + plane * AT_P_PLANE + (ks >> 2) * AT_P_CHUNK + (ks & 3) * 32),
-                            make_smem_desc(base + AT_OFF_ZC + ks * 32 * AT_DH, AT_KV_ROWS * AT_DH, 512, UMMA_LAYOUT_SW64), idesc_pv, 1u);
+                            make_smem_desc(base + AT_OFF_ZC, 0, 0, UMMA_LAYOUT_SW64), idesc_pv, 1u);
               }
             }
             tc_commit(bar_o);
@@ -457,9 +462,14 @@ int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AT_SMEM_ALLOC_ZP));
     P2V_REQUIRE(e == cudaSuccess, "attention_tc: cannot set %zu bytes of dynamic shared memory: %s", AT_SMEM_ALLOC_ZP, cudaGetErrorString(e));
   }
-  if (zp) {      // asymmetric quantizers: constant-tile variant, one CTA per SM
+  if (zp) {      // asymmetric quantizers: constant-atom variant
+    static int zp_ctas = 0;
+    if (zp_ctas == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zp_ctas, attention_tc_kernel<false, true>, AT_THREADS, AT_SMEM_ALLOC_ZP) != cudaSuccess || zp_ctas < 1) zp_ctas = 1;
+      zp_ctas = std::min(zp_ctas, 2);
+    }
     pdl_next_kind(PDL_ATTENTION);
-    launch_pdl(attention_tc_kernel<false, true>, dim3(std::min(p.total_heads, sms)), dim3(AT_THREADS), AT_SMEM_ALLOC_ZP, stream, tmQ, tmKV, p);
+    launch_pdl(attention_tc_kernel<false, true>, dim3(std::min(p.total_heads, zp_ctas * sms)), dim3(AT_THREADS), AT_SMEM_ALLOC_ZP, stream, tmQ, tmKV, p);
     count_launch();
     return check_launch("attention_tc");
   }

@@ -1,9 +1,8 @@
 #!/bin/bash
 export PYTHONPATH=$PWD
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_ops.py -q -k "gemm or gelu" > gpurun_out/ab_zp_tests.log 2>&1; echo "gemm tests rc $?"; tail -5 gpurun_out/ab_zp_tests.log
-python -m pytest tests/test_gpu_model.py tests/test_gpu_swin.py -q -x > gpurun_out/ab_zp_model.log 2>&1; echo "model tests rc $?"; tail -3 gpurun_out/ab_zp_model.log
-for spec in "vit_base percentile" "deit_small ema" "deit_small minmax"; do
+python -m pytest tests -m gpu -x -q > gpurun_out/tests_full.log 2>&1; echo "tests rc $?"; tail -3 gpurun_out/tests_full.log
+for spec in "vit_base omse"; do
   set -- $spec
   python bench.py --model $1 --method $2 --steps 10 --warmup 3 --no-cpu-baseline --configs none --sustain 0 > gpurun_out/zp_$1_$2.json 2>gpurun_out/zp.err || tail -3 gpurun_out/zp.err
   python - <<PY
