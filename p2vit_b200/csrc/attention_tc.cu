@@ -26,6 +26,8 @@
 // instead of 6 + 2 and 10 + 4.
 #include <climits>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 #include "tc_common.cuh"
 
@@ -55,12 +57,14 @@ constexpr size_t AT_SMEM_ALLOC = AT_SMEM + 128;
 // same accumulators,  (q - z)(k - z) = q k + (-z) k + q (-z) + dh z^2  and  P (v - z) = P v + P (-z),  so the softmax warps only
 // add the scalar dh z^2.  Every byte of that tile is the same, so one 512-byte swizzle atom stands for all of it: the operand
 // descriptors carry a stride of ZERO between the 8-row groups (K-major, the q / k side) and between the k atoms (MN-major, the
-// v side), and the MMA reads the same atom for every group.  The atom fits behind the barriers with no slack left
-// (2 x (115 712 + 1 024 reserved) = the SM's 228 KB), so the variant keeps two CTAs per SM; a 14-KB tile (r2 start) meant one.
-constexpr uint32_t AT_OFF_ZC = (AT_SMEM + 511u) & ~511u;
+// v side), and the MMA reads the same atom for every group.  The K load writes only the n_pad rows S = q k^T reads, so for
+// T <= 208 the atom sits in the unused tail of the K tile (rows 208..215) and the variant keeps two CTAs per SM like the others;
+// beyond that it goes behind the barriers and one CTA fits (a 14-KB tile, r2 start, always meant one).
 constexpr uint32_t AT_ZC_BYTES = 512;
-constexpr size_t AT_SMEM_ALLOC_ZP = AT_OFF_ZC + AT_ZC_BYTES;
-static_assert(2 * (AT_SMEM_ALLOC_ZP + 1024) <= 228 * 1024, "two CTAs of the zero-point variant must fit one SM");
+constexpr uint32_t AT_OFF_ZC_K = AT_OFF_K + 208 * AT_DH;          // rows 208..215 of the K tile
+constexpr uint32_t AT_OFF_ZC = (AT_SMEM + 511u) & ~511u;
+constexpr size_t AT_SMEM_ALLOC_ZP = AT_OFF_ZC + AT_ZC_BYTES + 128;
+static_assert(AT_OFF_ZC_K % 512 == 0 && AT_OFF_ZC % 512 == 0, "a SWIZZLE_64B atom needs 512-byte alignment");
 static_assert(AT_OFF_K % 1024 == 0 && AT_OFF_V % 1024 == 0 && AT_OFF_P % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 struct AttTcParams {
@@ -71,6 +75,8 @@ struct AttTcParams {
   float score_mult, out_mult;
   const p2v_softmax_lut* lut;
   int8_t* out;
+  int k_rows;               // key rows the K load writes (= n_pad; the tile has room for AT_KV_ROWS)
+  uint32_t zc_off, smem_alloc;   // ZP variant: shared-memory offset of the constant atom; bytes of dynamic shared memory of this launch
   int zp_qkv, zc2;          // ZP variant: zero point z of q / k / v and dh * z^2
   float zp_score, zp_out;   // ZP variant: zero points of qact_attn1 and qact2
 };
@@ -108,11 +114,12 @@ __device__ __forceinline__ void quarter_exchange_sync(uint32_t quarter) {
 // and no single stall reason exceeds 15 % of the samples (profiles/r2_attention_stalls.txt).
 template <bool POTM, bool ZP>
 __global__ void __launch_bounds__(AT_THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, AttTcParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    AttTcParams p) {
   static_assert(!(POTM && ZP), "zero points come with raw fp32 scales");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  if (base - smem_u32(smem_raw) + (ZP ? AT_OFF_ZC + AT_ZC_BYTES : AT_SMEM) > uint32_t(ZP ? AT_SMEM_ALLOC_ZP : AT_SMEM_ALLOC)) __trap();     // dynamic window not aligned as assumed
+  if (base - smem_u32(smem_raw) + ((ZP && p.zc_off >= AT_SMEM) ? p.zc_off + AT_ZC_BYTES : AT_SMEM) > p.smem_alloc) __trap();     // dynamic window not aligned as assumed
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + AT_OFF_BARS;
   const uint32_t bar_qk = bars, bar_v = bars + 8, bar_s = bars + 16, bar_p = bars + 24, bar_o = bars + 32, bar_free = bars + 40;
@@ -139,7 +146,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t zb = uint32_t(p.zp_qkv == -128 ? 64 : -p.zp_qkv) & 0xffu;
     const uint32_t zw = zb * 0x01010101u;
     for (int i = threadIdx.x; i < int(AT_ZC_BYTES) / 16; i += AT_THREADS)
-      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + AT_OFF_ZC + uint32_t(i) * 16u), "r"(zw) : "memory");
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + p.zc_off + uint32_t(i) * 16u), "r"(zw) : "memory");
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -156,19 +163,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     {
       if (elect_one()) {
         tma_prefetch_map(&tmQ);
-        tma_prefetch_map(&tmKV);
+        tma_prefetch_map(&tmK);
+        tma_prefetch_map(&tmV);
       }
       const int row_bytes_h = AT_DH;  // column offsets inside a token row: q at h*64, k at (H+h)*64, v at (2H+h)*64
       auto load_qk = [&](int hd) {
         const int b = hd / H, h = hd % H;
-        mbar_expect_tx(bar_qk, uint32_t(p.mtiles) * 128u * AT_DH + AT_KV_ROWS * AT_DH);
+        mbar_expect_tx(bar_qk, uint32_t(p.mtiles) * 128u * AT_DH + uint32_t(p.k_rows) * AT_DH);
         for (int mt = 0; mt < p.mtiles; ++mt) tma_load_3d(base + AT_OFF_Q + mt * 128 * AT_DH, &tmQ, bar_qk, h * row_bytes_h, mt * 128, b);
-        tma_load_3d(base + AT_OFF_K, &tmKV, bar_qk, (H + h) * row_bytes_h, 0, b);
+        tma_load_3d(base + AT_OFF_K, &tmK, bar_qk, (H + h) * row_bytes_h, 0, b);
       };
       auto load_v = [&](int hd) {
         const int b = hd / H, h = hd % H;
         mbar_expect_tx(bar_v, AT_KV_ROWS * AT_DH);
-        tma_load_3d(base + AT_OFF_V, &tmKV, bar_v, (2 * H + h) * row_bytes_h, 0, b);
+        tma_load_3d(base + AT_OFF_V, &tmV, bar_v, (2 * H + h) * row_bytes_h, 0, b);
       };
       const uint32_t idesc_qk = make_i8_idesc(128, p.n_pad, true, true);
       const uint32_t idesc_pv = make_i8_idesc(128, AT_DH, false, true, false, true);   // P u8 K-major, V s8 MN-major
@@ -192,10 +200,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
               for (int rep = 0; rep < zreps; ++rep)
 #pragma unroll
                 for (int k = 0; k < AT_DH / 32; ++k) {
-                  umma_i8(tmem_base, make_smem_desc(base + AT_OFF_ZC + k * 32, 16, 0, UMMA_LAYOUT_SW64),
+                  umma_i8(tmem_base, make_smem_desc(base + p.zc_off + k * 32, 16, 0, UMMA_LAYOUT_SW64),
                           make_smem_desc(base + AT_OFF_K + k * 32, 16, 512, UMMA_LAYOUT_SW64), idesc_qk, 1u);
                   umma_i8(tmem_base, make_smem_desc(base + AT_OFF_Q + mt * 128 * AT_DH + k * 32, 16, 512, UMMA_LAYOUT_SW64),
-                          make_smem_desc(base + AT_OFF_ZC + k * 32, 16, 0, UMMA_LAYOUT_SW64), idesc_qk, 1u);
+                          make_smem_desc(base + p.zc_off + k * 32, 16, 0, UMMA_LAYOUT_SW64), idesc_qk, 1u);
                 }
             }
             tc_commit(bar_s);
@@ -221,7 +229,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                   for (int ks = 0; ks < p.ksteps; ++ks)
                     umma_i8(tmem_base + plane * AT_DH,
                             make_kmajor_sw128_desc(base + AT_OFF_P + plane * AT_P_PLANE + (ks >> 2) * AT_P_CHUNK + (ks & 3) * 32),
-                            make_smem_desc(base + AT_OFF_ZC, 0, 0, UMMA_LAYOUT_SW64), idesc_pv, 1u);
+                            make_smem_desc(base + p.zc_off, 0, 0, UMMA_LAYOUT_SW64), idesc_pv, 1u);
               }
             }
             tc_commit(bar_o);
@@ -438,13 +446,17 @@ bool attention_tc_supported(const p2v_attention_args& a) {
 
 int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
   P2V_REQUIRE(attention_tc_supported(a), "attention_tc: needs head dim 64, T <= %d, 16-byte aligned tensors, no debug dumps", AT_KV_ROWS);
-  CUtensorMap tmQ, tmKV;
+  CUtensorMap tmQ, tmK, tmV;
   const int W = 3 * a.H * AT_DH;
   if (int r = make_tmap_qkv(&tmQ, a.qkv, a.B, a.T, W, 128)) return r;
-  if (int r = make_tmap_qkv(&tmKV, a.qkv, a.B, a.T, W, AT_KV_ROWS)) return r;
+  const int n_pad = (a.T + 15) / 16 * 16;
+  if (int r = make_tmap_qkv(&tmK, a.qkv, a.B, a.T, W, n_pad)) return r;          // only the rows S = q k^T reads
+  if (int r = make_tmap_qkv(&tmV, a.qkv, a.B, a.T, W, AT_KV_ROWS)) return r;
   AttTcParams p;
   p.T = a.T; p.H = a.H; p.total_heads = a.B * a.H;
-  p.n_pad = (a.T + 15) / 16 * 16;
+  p.n_pad = n_pad;
+  p.k_rows = n_pad;
+  p.zc_off = 0; p.smem_alloc = uint32_t(AT_SMEM_ALLOC);
   p.ksteps = (a.T + 31) / 32;
   p.mtiles = (a.T + 127) / 128;
   p.score_mult = a.score_mult; p.out_mult = a.out_mult;
@@ -463,23 +475,22 @@ int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
     P2V_REQUIRE(e == cudaSuccess, "attention_tc: cannot set %zu bytes of dynamic shared memory: %s", AT_SMEM_ALLOC_ZP, cudaGetErrorString(e));
   }
   if (zp) {      // asymmetric quantizers: constant-atom variant
-    static int zp_ctas = 0;
-    if (zp_ctas == 0) {
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&zp_ctas, attention_tc_kernel<false, true>, AT_THREADS, AT_SMEM_ALLOC_ZP) != cudaSuccess || zp_ctas < 1) zp_ctas = 1;
-      zp_ctas = std::min(zp_ctas, 2);
-    }
+    const bool in_k_tail = n_pad <= 208;
+    p.zc_off = in_k_tail ? AT_OFF_ZC_K : AT_OFF_ZC;
+    p.smem_alloc = uint32_t(in_k_tail ? AT_SMEM_ALLOC : AT_SMEM_ALLOC_ZP);
     pdl_next_kind(PDL_ATTENTION);
-    launch_pdl(attention_tc_kernel<false, true>, dim3(std::min(p.total_heads, zp_ctas * sms)), dim3(AT_THREADS), AT_SMEM_ALLOC_ZP, stream, tmQ, tmKV, p);
+    launch_pdl(attention_tc_kernel<false, true>, dim3(std::min(p.total_heads, (in_k_tail ? 2 : 1) * sms)), dim3(AT_THREADS), p.smem_alloc, stream, tmQ, tmK, tmV, p);
     count_launch();
     return check_launch("attention_tc");
   }
-  const int grid = std::min(p.total_heads, 2 * sms);
+  static const int ctas_per_sm = [] { const char* v = getenv("P2V_ATT_CTAS"); return v ? std::max(1, std::min(2, atoi(v))) : 2; }();   // perf triage only
+  const int grid = std::min(p.total_heads, ctas_per_sm * sms);
   // power-of-two score multiplier in [2^-20, 2^8]: RMAGIC * (1 - mult) is then exact and so is the fused scaling
   int mexp = 0;
   const bool potm = std::frexp(a.score_mult, &mexp) == 0.5f && mexp >= -19 && mexp <= 9;
   pdl_next_kind(PDL_ATTENTION);
-  if (potm) launch_pdl(attention_tc_kernel<true, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
-  else launch_pdl(attention_tc_kernel<false, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmKV, p);
+  if (potm) launch_pdl(attention_tc_kernel<true, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmK, tmV, p);
+  else launch_pdl(attention_tc_kernel<false, false>, dim3(grid), dim3(AT_THREADS), AT_SMEM_ALLOC, stream, tmQ, tmK, tmV, p);
   count_launch();
   return check_launch("attention_tc");
 }
