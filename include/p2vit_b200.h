@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define P2V_ABI_VERSION 2
+#define P2V_ABI_VERSION 3
 
 int p2v_abi_version(void);
 const char* p2v_last_error(void);
@@ -219,6 +219,13 @@ typedef struct {
    * out_i8 = sat(RNE(fl(O*out_mult) + zp_out)).  All integer valued; 0 for symmetric observers. */
   int zp_qkv;
   float zp_score, zp_out;
+  /* how the tcgen05 kernel gets log_round(RNE(fl(sum / exp))); the codes are identical, only the speed differs with the data:
+   *   0  product with the table's reciprocal + a guard band; a 16-score unit with a score next to a decision boundary is redone
+   *      with the IEEE division (fastest when that is rare)
+   *   1  the exactly rounded quotient for every score (reciprocal + two residual corrections), no guard, no redo - for coarse score
+   *      scales whose quotients land on the ties x.5 all the time (ViT-B: up to a fifth of the units took the redo)
+   * p2vit_b200/engine.py times both on the first batch of a program and keeps the faster one per layer. */
+  int prob_mode;
 } p2v_attention_args;
 
 /* Head dim 64, T <= 224 and no debug dumps: tcgen05 kernel (csrc/attention_tc.cu: TMA-fed S = q k^T and O = P v on

@@ -64,6 +64,7 @@ class AttentionArgs(C.Structure):
         ("lut_dev", C.c_void_p),
         ("probs_or_null", C.c_void_p), ("scores_or_null", C.c_void_p),
         ("zp_qkv", C.c_int), ("zp_score", C.c_float), ("zp_out", C.c_float),
+        ("prob_mode", C.c_int),
     ]
 
 
@@ -119,7 +120,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library diverge
         fn.restype, fn.argtypes = res, args
-    if lib.p2v_abi_version() != 2:
+    if lib.p2v_abi_version() != 3:
         raise RuntimeError("p2vit_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -26,6 +26,7 @@
 // instead of 6 + 2 and 10 + 4.
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
@@ -75,6 +76,7 @@ struct AttTcParams {
   float score_mult, out_mult;
   const p2v_softmax_lut* lut;
   int8_t* out;
+  int exact_probs;          // pass 3 without the guard band (prob_bits_div)
   int k_rows;               // key rows the K load writes (= n_pad; the tile has room for AT_KV_ROWS)
   uint32_t zc_off, smem_alloc;   // ZP variant: shared-memory offset of the constant atom; bytes of dynamic shared memory of this launch
   int zp_qkv, zc2;          // ZP variant: zero point z of q / k / v and dh * z^2
@@ -138,7 +140,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   for (int i = threadIdx.x; i < 257; i += AT_THREADS) {
     const int d = max(i - 1, 0);
     s_lut[i] = make_uint2(p.lut->hi[d], p.lut->lo[d]);
-    s_rcp[i] = make_float2(fdiv(1.0f, p.lut->exp_f32[d]), 0.f);
+    s_rcp[i] = make_float2(prob_rcp(p.lut->exp_f32[d]), p.lut->exp_f32[d]);
   }
   // -z as an int8 byte; z = -128 has no int8 negative: the tile then holds 64 and the correction MMAs are issued twice
   const int zreps = ZP ? (p.zp_qkv == -128 ? 2 : 1) : 0;
@@ -246,6 +248,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else {
     // ================= softmax warps: thread = one query row (TMEM lane) x one half of the key axis =================
     const uint32_t quarter = uint32_t(warp) & 3u, half = uint32_t(warp) >> 2;
+    const bool exact_probs = p.exact_probs != 0;
     const int rloc = int(quarter) * 32 + lane;
     const uint32_t tlane = tmem_base + ((quarter * 32u) << 16);
     const float mult = p.score_mult;
@@ -341,11 +344,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int nv = T - u * 16;
             uint32_t pv[16];
             float gmax = 0.f;
+            if (exact_probs) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                float rcp, ef;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(rcp), "=f"(ef) : "r"(uint32_t(aa[e])), "n"(AT_RCP_OFF));
+                pv[e] = prob_bits_div(tot, rcp, ef);
+              }
+            } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               float rcp;
               asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(rcp) : "r"(uint32_t(aa[e])), "n"(AT_RCP_OFF));
               pv[e] = prob_bits_fast(tot2, tot43, rcp, gmax);
+            }
             }
             if (!(gmax < PROB_GUARD)) {   // some element sits next to a rounding / log2 boundary (or is not finite): redo the unit with the IEEE division
 #pragma unroll
@@ -456,6 +468,8 @@ int launch_attention_tc(const p2v_attention_args& a, cudaStream_t stream) {
   p.T = a.T; p.H = a.H; p.total_heads = a.B * a.H;
   p.n_pad = n_pad;
   p.k_rows = n_pad;
+  static const int force_mode = getenv("P2V_ATT_EXACT") ? atoi(getenv("P2V_ATT_EXACT")) : -1;      // triage: pin the mode
+  p.exact_probs = force_mode >= 0 ? force_mode : a.prob_mode;
   p.zc_off = 0; p.smem_alloc = uint32_t(AT_SMEM_ALLOC);
   p.ksteps = (a.T + 31) / 32;
   p.mtiles = (a.T + 127) / 128;

@@ -268,12 +268,28 @@ __device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t n) {   // PTX
   asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
   return r;
 }
+// Reciprocal of a table entry for prob_bits_fast.  exp_int = 0 (the far tail of the table) must not become +inf: g = inf trips the
+// guard band and sends the WHOLE WARP's unit to the IEEE-division redo - with raw observer scales (percentile / ema: codes spread
+// over the full int8 range) most units hold such an entry.  2^60 keeps g finite (row sums are >= exp_int[0] >= 2^32 and < 2^56), puts
+// its exponent far above 16, and the probability comes out 0 exactly as the reference's x = inf does.
+__device__ __forceinline__ float prob_rcp(float e) { return e > 0.f ? fdiv(1.0f, e) : 1152921504606846976.f; }
 constexpr float PROB_GUARD = 16384.f - 0.0625f;     // 16 ulps of [2^15, 2^16)
 __device__ __forceinline__ uint32_t prob_bits_fast(float tot2, float tot43, float rcp, float& gmax) {
   const float g = fminf(__fmaf_rn(tot2, rcp, -1.0f), __fmaf_rn(tot43, rcp, 0.666666686534881591796875f));
   const float pf = __uint_as_float(0x86800000u - (__float_as_uint(g) & 0x7F800000u));     // 2^(15 - E), E = floor(log2 g)
   gmax = fmaxf(gmax, fabsf(__fmaf_rn(g, pf, -49152.f)));       // g * pf is exact (pf is a power of two), and so is the difference
   return __float_as_uint(fadd(pf, 8388608.f));      // low 16 bits: 2^(15-E)
+}
+// The same probability with no guard band: q = fl(sum / exp) exactly (div_rb from the table's reciprocal), x = RNE(q), and
+// g' = (4x + 1) / 3 has floor(log2 g') = log_round(x) for every integer x >= 1 (x = 3 2^j - 1 gives 2^(j+2) - 1, x = 3 2^j gives
+// 2^(j+2) + 1/3; the fp32 error of the FFMA stays below 0.2 up to the last threshold that matters, x = 49152).  Three FMA-pipe
+// instructions more per score than prob_bits_fast, but no redo: for rows whose quotients keep landing exactly on the ties x.5.
+__device__ __forceinline__ uint32_t prob_bits_div(float tot, float rcp, float e) {
+  const float q = div_rb(tot, e, rcp);
+  const float x = fsub(fadd(q, RMAGIC), RMAGIC);                     // RNE(q) below 2^22; beyond, any value that large gives 0
+  const float g = __fmaf_rn(x, 1.33333337306976318359375f, 0.3333333432674407958984375f);
+  const float pf = __uint_as_float(0x86800000u - (__float_as_uint(g) & 0x7F800000u));
+  return __float_as_uint(fadd(pf, 8388608.f));
 }
 // exactly rounded (RNE) fp32 of the 128-bit integer hi*2^32 + lo  (hi, lo < 2^63)
 __device__ __forceinline__ float u96_to_f32(unsigned long long hi, unsigned long long lo) {

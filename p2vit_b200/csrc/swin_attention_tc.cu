@@ -78,7 +78,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, WinTcParam
     const bool tail = i == 256 && MASK;            // (without a mask entry 256 only serves the padding keys of a partial chunk: a copy of 255)
     const int k = min(i, 255);
     const float e = tail ? float(p.e_mask) : p.lut->exp_f32[k];
-    s_lut[i] = make_uint4(tail ? 0u : p.lut->hi[k], tail ? p.e_mask : p.lut->lo[k], __float_as_uint(e), __float_as_uint(fdiv(1.0f, e)));
+    s_lut[i] = make_uint4(tail ? 0u : p.lut->hi[k], tail ? p.e_mask : p.lut->lo[k], __float_as_uint(e), __float_as_uint(prob_rcp(e)));
   }
   for (uint32_t i = threadIdx.x; i < 2 * WT_P_PLANE / 16; i += WT_THREADS)       // off-diagonal blocks and key padding of P stay zero
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(base + WT_OFF_P + i * 16u), "r"(0u) : "memory");

@@ -38,11 +38,11 @@ __global__ void __launch_bounds__(WA_WARPS * 32) window_attention_kernel(p2v_win
   const int64_t row_bytes = int64_t(3) * H * DH;
   for (int i = tid; i < 256; i += blockDim.x) {
     const float e = a.lut_dev->exp_f32[i];
-    sLut[i] = make_uint4(a.lut_dev->hi[i], a.lut_dev->lo[i], __float_as_uint(e), __float_as_uint(fdiv(1.0f, e)));
+    sLut[i] = make_uint4(a.lut_dev->hi[i], a.lut_dev->lo[i], __float_as_uint(e), __float_as_uint(prob_rcp(e)));
   }
   for (int i = tid; i < DH * VSTR; i += blockDim.x) sVt[i] = 0u;       // rows >= T of V and keys >= T of P stay zero for every unit
   for (int i = tid; i < WA_WARPS * 2 * TW; i += blockDim.x) sP[i] = 0u;
-  const float e_mask_f = float(e_mask), r_mask = fdiv(1.0f, e_mask_f);
+  const float e_mask_f = float(e_mask), r_mask = prob_rcp(e_mask_f);
   const float r2 = fdiv(1.0f, a.s_attn2);
   constexpr float LO = RMAGIC - 128.f, HI = RMAGIC + 127.f;
   uint32_t* pHi = sP + warp * 2 * TW;

@@ -12,6 +12,8 @@ QAct, ~35 per LayerNorm, ~40 per softmax) is split here into
         LN(cls rows) -> GEMM[head, dequant]
 Only int8 tensors cross HBM between kernels: r/r2 [B*197, D], qkv [B*197, 3D], attention out, MLP hidden.
 """
+import os
+
 import torch
 
 from . import intmath, ops
@@ -193,6 +195,40 @@ class _Lru(dict):
         return v
 
 
+_ATT_AUTOTUNE = os.environ.get("P2VIT_ATT_AUTOTUNE", "1") != "0"
+
+
+class _AttentionStep:
+    """One attention launch of a program.  The tcgen05 kernel has two ways to the log2 probabilities (p2v_attention_args.prob_mode:
+    reciprocal + guard band + redo, or the exactly rounded quotient for every score) with identical codes and data-dependent
+    speed: coarse score scales put a fifth of ViT-B's 16-score units on exact ties, where the redo path costs more than the
+    exact quotient everywhere would.  tune() runs both on the batch in the workspace and keeps the faster one."""
+
+    def __init__(self, args, simt):
+        self.args, self.simt, self.tuned = args, simt, bool(simt)
+
+    def __call__(self):
+        ops.attention(self.args, simt=self.simt)
+
+    def tune(self):
+        best = None
+        for mode in (0, 1):
+            self.args.prob_mode = mode
+            self()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self()
+            self()
+            e1.record()
+            e1.synchronize()
+            t = e0.elapsed_time(e1)
+            if best is None or t < best[0]:
+                best = (t, mode)
+        self.args.prob_mode = best[1]
+        self.tuned = True
+        self()
+
+
 class VitEngine:
     MAX_PLANS = 8         # packed weight sets kept (one per bit_config, least recently used out first)
     MAX_PROGRAMS = 16     # (bit_config, batch) programs / graphs kept
@@ -260,7 +296,7 @@ class VitEngine:
                                                                        zp_corr=g.zp_corr, out_zp=p["qkv_zp"]))))
             at = ops.attention_args(ws["qkv"], ws["ao"], B, T + 1, H, p["dh"], p["score_mult"], p["out_mult"], p["lut"],
                                     zp_qkv=p["att_zp"][0], zp_score=p["att_zp"][1], zp_out=p["att_zp"][2])
-            steps.append((pre + "attn.qact2", (lambda at=at, simt=self.simt_gemm: ops.attention(at, simt=simt))))
+            steps.append((pre + "attn.qact2", _AttentionStep(at, self.simt_gemm)))
             g = p["proj"]
             steps.append((pre + "qact2", self._gemm(ops.gemm_args(ws["ao"], g.W, ops.EPI_RESIDUAL, g.acc_scale, bias=g.bias,
                                                                   out_scale=p["proj_out"], mid_scale=p["proj_mid"],
@@ -326,13 +362,13 @@ class VitEngine:
     def _graph(self, prog, key, first):
         """CUDA graph of prog's steps[first:] (first = 1: everything after patchify, see __call__)"""
         def capture():
-            for _, fn in prog["steps"]:   # eager warm-up: sets kernel attributes, loads modules
-                fn()
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for _, fn in prog["steps"][first:]:
+            for _, fn in prog["steps"][first:]:   # eager warm-up: sets kernel attributes, loads modules
+                if isinstance(fn, _AttentionStep) and not fn.tuned and _ATT_AUTOTUNE:
+                    fn.tune()             # (on the batch in the workspace: the callers below patchify theirs before the first capture)
+                else:
                     fn()
+            torch.cuda.synchronize()
+            g = ops.capture_graph(lambda: [fn() for _, fn in prog["steps"][first:]])
             return g, prog          # the graph replays raw pointers into the program's plan and workspace: it keeps them alive
         return self.graphs.get_or(key, capture)[0]
 
@@ -349,9 +385,8 @@ class VitEngine:
                 and x.shape == img.shape and x.data_ptr() != img.data_ptr()):
             # the only kernel that reads the images is patchify (qact_input + patch gather): launch it on the caller's tensor and
             # replay the graph of the rest - no 4-byte-per-pixel device-to-device copy into the program's own input buffer
-            g = self._graph(prog, (bits, B, "after patchify"), 1)      # (its first use warms up with the program's own buffer)
             ops.quantize_patchify(x, pl.P, pl.s_in, pl.z_in, out=prog["ws"]["cols"])
-            g.replay()
+            self._graph(prog, (bits, B, "after patchify"), 1).replay()      # (a first use warms up - and picks the attention modes - on this batch)
             return prog["ws"]["logits"].clone()
         if x.data_ptr() != img.data_ptr():
             img.copy_(x)
@@ -372,9 +407,8 @@ class VitEngine:
         if key not in self._pixel_luts:
             self._pixel_luts[key] = ops.pixel_code_table(norm[0], norm[1], pl.s_in, x.device, pl.z_in)
         if self.use_graph:
-            g = self._graph(prog, (bits, B, "after patchify"), 1)
             ops.patchify_u8(x, self._pixel_luts[key], pl.P, out=ws["cols"])
-            g.replay()
+            self._graph(prog, (bits, B, "after patchify"), 1).replay()
         else:
             ops.patchify_u8(x, self._pixel_luts[key], pl.P, out=ws["cols"])
             for _, fn in prog["steps"][1:]:

@@ -176,7 +176,8 @@ def int_softmax_log2(scores_i8, lut_dev):
     return out
 
 
-def attention_args(qkv, out, B, T, H, dh, score_mult, out_mult, lut_dev, probs=None, scores=None, zp_qkv=0, zp_score=0.0, zp_out=0.0):
+def attention_args(qkv, out, B, T, H, dh, score_mult, out_mult, lut_dev, probs=None, scores=None, zp_qkv=0, zp_score=0.0, zp_out=0.0,
+                   prob_mode=0):
     a = AttentionArgs()
     a.B, a.T, a.H, a.dh = B, T, H, dh
     a.qkv, a.out = ptr(qkv), ptr(out)
@@ -184,6 +185,7 @@ def attention_args(qkv, out, B, T, H, dh, score_mult, out_mult, lut_dev, probs=N
     a.lut_dev = ptr(lut_dev)
     a.probs_or_null, a.scores_or_null = ptr(probs), ptr(scores)
     a.zp_qkv, a.zp_score, a.zp_out = int(zp_qkv), float(zp_score), float(zp_out)
+    a.prob_mode = int(prob_mode)
     return a
 
 
@@ -326,3 +328,21 @@ def launch_count(reset=False):
     if reset:
         lib.p2v_reset_launch_count()
     return n
+
+
+def capture_graph(launch):
+    """CUDA graph of the launches `launch()` makes.  The cyclic garbage collector stays off while the stream is capturing: a model
+    of an earlier (bit_config, batch) - engine, programs and their CUDAGraph objects form reference cycles - may be collected at any
+    allocation, and destroying a CUDAGraph is not permitted while another capture is open (it invalidates the capture)."""
+    import gc
+    g = torch.cuda.CUDAGraph()
+    was_enabled = gc.isenabled()
+    gc.collect()
+    gc.disable()
+    try:
+        with torch.cuda.graph(g):
+            launch()
+    finally:
+        if was_enabled:
+            gc.enable()
+    return g

@@ -308,11 +308,7 @@ class SwinEngine:
             for _, fn in prog["steps"]:
                 fn()
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for _, fn in prog["steps"]:
-                    fn()
-            self.graphs[B] = g
+            self.graphs[B] = ops.capture_graph(lambda: [fn() for _, fn in prog["steps"]])
         self.graphs[B].replay()
         return prog["ws"]["logits"]
 
@@ -345,11 +341,7 @@ class SwinEngine:
             for _, fn in prog["steps"]:
                 fn()
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for _, fn in prog["steps"][1:]:
-                    fn()
-            self.graphs[gkey] = g
+            self.graphs[gkey] = ops.capture_graph(lambda: [fn() for _, fn in prog["steps"][1:]])
         ops.patchify_u8(x, self._pixel_luts[key], pl.P, out=ws["cols"])
         if self.use_graph:
             self.graphs[gkey].replay()

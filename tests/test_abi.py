@@ -31,7 +31,7 @@ def test_library_exports_every_header_symbol():
     for s in header_symbols():
         assert hasattr(lib, s), "library does not export %s" % s
     assert sorted(_lib.SYMBOLS) == header_symbols(), "ctypes table and header diverge"
-    assert lib.p2v_abi_version() == 2
+    assert lib.p2v_abi_version() == 3
     assert lib.p2v_launch_count() >= 0
 
 

@@ -505,6 +505,32 @@ def test_int_softmax_vs_oracle(log2s, n):
     assert torch.equal(out, ref), "mismatches %d" % int((out != ref).sum())
 
 
+@pytest.mark.parametrize("s_as", [0.5, 0.7, 2.0 ** -2, 0.31, 2.0 ** -4, 0.043])
+def test_attention_probability_modes_agree(s_as):
+    """p2v_attention_args.prob_mode: the guarded reciprocal path (0) and the exactly rounded quotient (1) must give the same codes;
+    coarse score scales (exp_int = c 2^(32-d)) make the quotients short dyadic numbers that land exactly on the ties x.5 all the time,
+    few distinct key codes per row make it worse - both are in here, next to fine scales where the guard hardly ever trips"""
+    B, T, H = 3, 197, 3
+    D = H * 64
+    g = torch.Generator().manual_seed(int(s_as * 1000))
+    qkv = torch.randint(-24, 25, (B, T, 3, H, 64), generator=g, dtype=torch.int32)
+    qkv[1, :, 1] = qkv[1, :7, 1].repeat(29, 1, 1)[:T]          # image 1: only 7 distinct keys -> rows of few distinct scores
+    qkv = qkv.to(torch.int8).to(DEV)
+    s1, s2 = 2.0 ** -4, 2.0 ** -5
+    lut = intmath.lut_to_device(intmath.build_softmax_lut(torch.tensor([s_as])), DEV)
+    outs = []
+    for mode in (0, 1):
+        out = torch.full((B * T, D), 77, dtype=torch.int8, device=DEV)
+        ops.attention(ops.attention_args(qkv, out, B, T, H, 64, s1 * s1 * 0.125 / s_as, s1 / s2 / 32768.0, lut, prob_mode=mode))
+        torch.cuda.synchronize()
+        outs.append(out)
+    ref = torch.full((B * T, D), 77, dtype=torch.int8, device=DEV)
+    ops.attention(ops.attention_args(qkv, ref, B, T, H, 64, s1 * s1 * 0.125 / s_as, s1 / s2 / 32768.0, lut), simt=True)
+    assert torch.equal(outs[0], outs[1]), "%d codes differ between the two probability paths" % int((outs[0] != outs[1]).sum())
+    assert torch.equal(outs[0], ref), "%d codes differ from the dp4a kernel" % int((outs[0] != ref).sum())
+    assert int(outs[0].float().abs().sum()) > 0
+
+
 @pytest.mark.parametrize("B,T,H,dh", [(2, 197, 3, 64), (3, 49, 2, 32), (1, 197, 6, 64)])
 def test_attention_vs_oracle(B, T, H, dh):
     D = H * dh
