@@ -130,6 +130,9 @@ typedef struct {
  * (first form: n = 0), with thresholds found on the reference's division gelu(y) / out_scale; the kernels that read the first
  * form ignore the table unless pot_scales is set.  Synchronises `stream` once (the verdict of the self-check is read back). */
 int p2v_build_gelu_table(float out_scale, void* table_dev, void* stream);
+/* the same for an asymmetric output quantizer (omse): code = sat(RNE(fl(fl(gelu(y) / out_scale) + out_zp))), out_zp an integer in
+ * [-128, 127]; second form only.  The caller passes the table with the matching out_scale / out_zp of p2v_gemm_args. */
+int p2v_build_gelu_table_zp(float out_scale, float out_zp, void* table_dev, void* stream);
 
 int p2v_gemm_i8(const p2v_gemm_args* args_host, void* stream);
 /* Two tcgen05 kernels implement p2v_gemm_i8 with identical results: csrc/gemm_pair.cu (CTA pairs, cta_group::2, TMA-staged

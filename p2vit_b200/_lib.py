@@ -81,6 +81,7 @@ SYMBOLS = {
     "p2v_quantize_patchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _F, _I, _I, _P]),
     "p2v_patchify_u8_lut": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "p2v_build_gelu_table": (_I, [_F, _P, _P]),
+    "p2v_build_gelu_table_zp": (_I, [_F, _F, _P, _P]),
     "p2v_gemm_i8": (_I, [C.POINTER(GemmArgs), _P]),
     "p2v_gemm_i8_simt": (_I, [C.POINTER(GemmArgs), _P]),
     "p2v_set_gemm_variant": (None, [_I]),

@@ -58,7 +58,7 @@ int check_launch(const char* what) {
 }
 
 int launch_gemm_simt(const p2v_gemm_args& a, cudaStream_t stream);
-int launch_build_gelu_table(float out_scale, void* table_dev, cudaStream_t stream);
+int launch_build_gelu_table(float out_scale, float out_zp, void* table_dev, cudaStream_t stream);
 int launch_gemm_tc(const p2v_gemm_args& a, cudaStream_t stream);
 void set_gemm_variant(int v);
 int launch_quantize(const float* x, int8_t* q, float* y, int64_t n, int C, int64_t inner, const float* scale, int n_scale,
@@ -161,7 +161,11 @@ int p2v_patchify_u8_lut(const uint8_t* img, const int8_t* lut, int8_t* out, int 
 }
 int p2v_build_gelu_table(float out_scale, void* table_dev, void* stream) {
   P2V_REQUIRE(table_dev != nullptr && (reinterpret_cast<uintptr_t>(table_dev) & 15) == 0, "build_gelu_table: table must be 16-byte aligned");
-  return launch_build_gelu_table(out_scale, table_dev, (cudaStream_t)stream);
+  return launch_build_gelu_table(out_scale, 0.f, table_dev, (cudaStream_t)stream);
+}
+int p2v_build_gelu_table_zp(float out_scale, float out_zp, void* table_dev, void* stream) {
+  P2V_REQUIRE(table_dev != nullptr && (reinterpret_cast<uintptr_t>(table_dev) & 15) == 0, "build_gelu_table: table must be 16-byte aligned");
+  return launch_build_gelu_table(out_scale, out_zp, table_dev, (cudaStream_t)stream);
 }
 int p2v_gemm_i8(const p2v_gemm_args* a, void* stream) {
   if (int r = validate_gemm(a)) return r;

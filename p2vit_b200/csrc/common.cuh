@@ -113,7 +113,7 @@ struct GeluTab { const uint2* entries; int n; float inv_w, off; };   // entries 
 // the reference arithmetic: qact1(gelu(y)) for a power-of-two output scale (ro = 1/out_scale)
 __device__ __forceinline__ int gelu_code_direct(float y, float ro) { return sat_s8(fmul(gelu_erf(y), ro)); }
 // the same for any output scale: the reference's division (equal to the product above when the scale is a power of two)
-__device__ __forceinline__ int gelu_code_div(float y, float so) { return sat_s8(fdiv(gelu_erf(y), so)); }
+__device__ __forceinline__ int gelu_code_div(float y, float so, float zp = 0.f) { return sat_s8(fadd(fdiv(gelu_erf(y), so), zp)); }
 // segment of y; the SAME expression builds the table and looks it up, so its own rounding is immaterial
 __device__ __forceinline__ int gelu_segment(float y, float inv_w, float off, int n) {
   return min(max(__float2int_rd(__fmaf_rn(y, inv_w, off)), 0), n - 1);
@@ -140,7 +140,8 @@ struct GeluStepsHeader {   // 64 bytes, then float2 seg[P2V_GELU_STEPS_MAX_SEG],
   float seg_scale;         // nseg - 1 + 0.49: segment = RNE(sat((y * inv_w + soff) / seg_scale) * seg_scale)
   float f_scale;           // 126 - f0 + 0.49 (f0 = -k1): f = f0 + RNE(sat(A' y + B') * f_scale), seg = (A', B') = (A, B - f0) / f_scale
   int clean;               // 1: the step code equals the direct evaluation also within 8 ulps of every threshold (no distance test needed)
-  int pad[2];
+  float zp;                // zero point of the output quantizer the table was built for (0 for symmetric observers)
+  int pad[1];
 };
 bool gelu_table_is_clean(const void* table_dev);     // host (gelu_table.cu): verdict of the table's self-check, by device address
 constexpr int P2V_GELU_STEPS_MAX_SEG = 64, P2V_GELU_STEPS_MAX_THR = 512;

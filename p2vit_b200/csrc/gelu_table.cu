@@ -76,12 +76,12 @@ __global__ void __launch_bounds__(128) build_gelu_table_kernel(GeluTabHeader hd,
 // thread i: threshold of code boundary c = cr0 + i (right of y*: smallest y with code >= c) or, for i >= nr, c = cr0 + i - nr
 // (left of y*: smallest y with code < c, the code being non-increasing in y there); +-inf when the boundary is never / always
 // crossed on that branch.  A threshold whose neighbourhood is not a clean step outside the +-8 ulp band clears *ok.
-__global__ void __launch_bounds__(128) build_gelu_steps_kernel(GeluStepsHeader h, float so, int cr0, float* __restrict__ thr, int* __restrict__ ok) {
+__global__ void __launch_bounds__(128) build_gelu_steps_kernel(GeluStepsHeader h, float so, float zp, int cr0, float* __restrict__ thr, int* __restrict__ ok) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h.nr + h.nl) return;
   const bool left = i >= h.nr;
   const int c = cr0 + (left ? i - h.nr : i);
-  auto F = [&](uint32_t k) { return gelu_code_div(key2f(k), so); };
+  auto F = [&](uint32_t k) { return gelu_code_div(key2f(k), so, zp); };
   const uint32_t k_star = f2key(h.ystar), k_lo = left ? f2key(h.ymin) : k_star, k_hi = left ? k_star : f2key(h.ymax);
   // on [k_lo, k_hi] the predicate Q(k) = (code >= c) on the right branch, (code < c) on the left one, goes from false to true
   auto Q = [&](uint32_t k) { return left ? F(k) < c : F(k) >= c; };
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128) build_gelu_steps_kernel(GeluStepsHeader h
 // evaluation (near_min > 16) must get exactly the direct code.  A mismatch clears *ok.  A y inside the band whose step code
 // differs from the direct one clears *clean: the band around every threshold is scanned exhaustively, so a table that keeps
 // `clean` needs no distance test in the epilogue.
-__global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __restrict__ table, float so, int* __restrict__ ok, int* __restrict__ clean) {
+__global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __restrict__ table, float so, float zp, int* __restrict__ ok, int* __restrict__ clean) {
   extern __shared__ uint8_t vsm[];
   const uint32_t base = (uint32_t(__cvta_generic_to_shared(vsm)) + 255u) & ~255u;
   gelu_steps_fill_smem(table, base, int(threadIdx.x), int(blockDim.x));
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) verify_gelu_steps_kernel(const void* __re
   auto check = [&](float y) {
     uint32_t nm = 0xffffffffu;
     const int c = int(int8_t(gelu_steps_code(y, t, nm) & 0xffu));
-    if (c != gelu_code_div(y, so)) {
+    if (c != gelu_code_div(y, so, zp)) {
       if (nm > 16u) bad = true; else unclean = true;
     }
   };
@@ -168,21 +168,24 @@ bool gelu_table_is_clean(const void* table_dev) {
 static double gelu_f64(double y) { return 0.5 * y * (1.0 + erf(y * 0.70710678118654752440)); }
 
 // host side of the second form: active range, segment map, table dimensions.  false = this scale is not tabulated.
-static bool plan_gelu_steps(float out_scale, GeluStepsHeader& h, std::vector<float2>& seg, int& cr0) {
-  const double so = out_scale, ro = 1.0 / so;
+static bool plan_gelu_steps(float out_scale, float out_zp, GeluStepsHeader& h, std::vector<float2>& seg, int& cr0) {
+  const double so = out_scale, ro = 1.0 / so, zp = out_zp;
+  if (!(zp >= -128.0 && zp <= 127.0) || zp != floor(zp)) return false;
   const float ystar = -0.7517916f;
   const double gmin = gelu_f64(ystar);
   if (-gmin * ro <= 0.45 || so > 0.25) return false;          // (almost) no negative codes: not worth a table
   double lo = 0.0, hi = 300.0 * so + 10.0;                     // ymax: gelu = 128.2 * so (every y above saturates to 127)
-  for (int it = 0; it < 200; ++it) { const double mid = 0.5 * (lo + hi); if (gelu_f64(mid) < 128.2 * so) lo = mid; else hi = mid; }
+  for (int it = 0; it < 200; ++it) { const double mid = 0.5 * (lo + hi); if (gelu_f64(mid) < (128.2 - zp) * so) lo = mid; else hi = mid; }
   const double ymax = hi;
   lo = -40.0; hi = ystar;                                      // ymin: gelu = -0.4 * so left of the minimum (every y below has code 0)
   for (int it = 0; it < 200; ++it) { const double mid = 0.5 * (lo + hi); if (gelu_f64(mid) > -0.4 * so) lo = mid; else hi = mid; }
   const double ymin = lo;
-  cr0 = int(floor(gmin * ro + 0.5)) - 2;
+  // lowest code - 2, but not below -128: with a zero point near -128 (post-GELU activations under an asymmetric observer) the low
+  // codes saturate; f is then clamped at f0 = -129 and the thresholds of codes <= -128 are -inf, so the lookup returns -128 there
+  cr0 = std::max(int(floor(gmin * ro + zp + 0.5)) - 2, -128);
   h.ymin = float(ymin); h.ymax = float(ymax); h.ystar = ystar;
-  h.nr = 131 - cr0; h.nl = 3 - cr0; h.k1 = 1 - cr0; h.ok = 1; h.clean = 1;
-  for (int k = 0; k < 2; ++k) h.pad[k] = 0;
+  h.nr = 131 - cr0; h.nl = std::max(int(zp) + 3 - cr0, 1); h.k1 = 1 - cr0; h.ok = 1; h.clean = 1; h.zp = out_zp;
+  h.pad[0] = 0;
   const double f0 = double(cr0 - 1);
   h.f_scale = float(126.0 - f0 + 0.49);
   const int entries = h.nr + h.nl;
@@ -200,13 +203,13 @@ static bool plan_gelu_steps(float out_scale, GeluStepsHeader& h, std::vector<flo
       double a = (double(s) - 0.52 - double(h.soff)) / double(h.inv_w), b = (double(s) + 0.52 - double(h.soff)) / double(h.inv_w);
       a = std::max(a, double(h.ymin)); b = std::min(b, double(h.ymax));
       if (!(b > a)) {
-        seg[s] = make_float2(0.f, float((gelu_f64(std::min(std::max(a, double(h.ymin)), double(h.ymax))) * ro - 0.5 - f0) / double(h.f_scale)));
+        seg[s] = make_float2(0.f, float((gelu_f64(std::min(std::max(a, double(h.ymin)), double(h.ymax))) * ro + zp - 0.5 - f0) / double(h.f_scale)));
         continue;
       }
       const double A = (gelu_f64(b) - gelu_f64(a)) * ro / (b - a);
       double dmin = 1e300, dmax = -1e300;
       for (int j = 0; j <= 128; ++j) {
-        const double y = a + (b - a) * j / 128.0, d = gelu_f64(y) * ro - A * y;
+        const double y = a + (b - a) * j / 128.0, d = gelu_f64(y) * ro + zp - A * y;
         dmin = std::min(dmin, d); dmax = std::max(dmax, d);
       }
       worst = std::max(worst, 0.5 * (dmax - dmin));
@@ -218,17 +221,17 @@ static bool plan_gelu_steps(float out_scale, GeluStepsHeader& h, std::vector<flo
 }
 
 // builds the second form behind the first in `table_dev`; synchronises `stream` to read the verdict back
-static int build_gelu_steps(float out_scale, void* table_dev, cudaStream_t stream) {
+static int build_gelu_steps(float out_scale, float out_zp, void* table_dev, cudaStream_t stream) {
   GeluStepsHeader h;
   std::vector<float2> seg;
   int cr0 = 0;
   char* base = reinterpret_cast<char*>(table_dev) + P2V_GELU_STEPS_OFFSET;
-  if (!plan_gelu_steps(out_scale, h, seg, cr0)) return 3;
+  if (!plan_gelu_steps(out_scale, out_zp, h, seg, cr0)) return 3;
   cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, stream);
   cudaMemcpyAsync(base + sizeof(h), seg.data(), seg.size() * sizeof(float2), cudaMemcpyHostToDevice, stream);
   int* ok_dev = &reinterpret_cast<GeluStepsHeader*>(base)->ok;
   float* thr_dev = reinterpret_cast<float*>(base + sizeof(h) + 8 * P2V_GELU_STEPS_MAX_SEG);
-  build_gelu_steps_kernel<<<(h.nr + h.nl + 127) / 128, 128, 0, stream>>>(h, out_scale, cr0, thr_dev, ok_dev);
+  build_gelu_steps_kernel<<<(h.nr + h.nl + 127) / 128, 128, 0, stream>>>(h, out_scale, out_zp, cr0, thr_dev, ok_dev);
   const size_t smem = gelu_steps_smem_bytes(h) + 256;
   static bool attr = false;
   if (!attr) {
@@ -236,7 +239,7 @@ static int build_gelu_steps(float out_scale, void* table_dev, cudaStream_t strea
     attr = true;
   }
   int* clean_dev = &reinterpret_cast<GeluStepsHeader*>(base)->clean;
-  verify_gelu_steps_kernel<<<64, 256, smem, stream>>>(table_dev, out_scale, ok_dev, clean_dev);
+  verify_gelu_steps_kernel<<<64, 256, smem, stream>>>(table_dev, out_scale, out_zp, ok_dev, clean_dev);
   count_launch(2);
   if (int r = check_launch("build_gelu_steps")) return r;
   GeluStepsHeader back;
@@ -250,20 +253,21 @@ static int build_gelu_steps(float out_scale, void* table_dev, cudaStream_t strea
   return back.ok ? 0 : 3;
 }
 
-int launch_build_gelu_table(float out_scale, void* table_dev, cudaStream_t stream) {
+int launch_build_gelu_table(float out_scale, float out_zp, void* table_dev, cudaStream_t stream) {
   int ex = 0;
   const float m = frexpf(out_scale, &ex);
   if (!(out_scale > 0.f) || !(out_scale < 1e30f)) return 3;
   GeluTabHeader hd;
   hd.y0 = -8.5f;
   hd.reserved = 0;
-  if (m != 0.5f) {
-    // not a power of two (ema / percentile observers): only the second form - its thresholds come from the reference's own
-    // division gelu(y) / out_scale, so it holds for any scale; the first form (one-tile and dp4a kernels) stays empty
+  if (m != 0.5f || out_zp != 0.f) {
+    // not a power of two (ema / percentile observers) or a zero point (omse): only the second form - its thresholds come from
+    // the reference's own sequence fl(gelu(y) / out_scale) + zp, so it holds for any quantizer; the first form (one-tile and dp4a
+    // kernels) stays empty
     hd.inv_w = 0.f;
     hd.n = 0;
     cudaMemcpyAsync(table_dev, &hd, sizeof(hd), cudaMemcpyHostToDevice, stream);
-    return build_gelu_steps(out_scale, table_dev, stream);
+    return build_gelu_steps(out_scale, out_zp, table_dev, stream);
   }
   const double inv_w = 2.0 / double(out_scale);                      // segment width out_scale / 2
   const double n_d = (8.5 + 128.0 * double(out_scale) + 0.5) * inv_w;
@@ -275,7 +279,7 @@ int launch_build_gelu_table(float out_scale, void* table_dev, cudaStream_t strea
                                                                    reinterpret_cast<uint2*>(reinterpret_cast<char*>(table_dev) + sizeof(hd)));
   count_launch();
   if (int r = check_launch("build_gelu_table")) return r;
-  return build_gelu_steps(out_scale, table_dev, stream);             // both forms or none: the caller passes one pointer to every kernel
+  return build_gelu_steps(out_scale, 0.f, table_dev, stream);             // both forms or none: the caller passes one pointer to every kernel
 }
 
 }  // namespace p2v

@@ -255,14 +255,19 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
     } else if (POT && EPI == P2V_EPI_REQUANT) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) t[e] = quant_pot(__fmaf_rn(__int2float_rn(acc[j4 + e]), Sv[e], Bv[e]));   // S, B pre-divided by out_scale
-    } else if (EPI == P2V_EPI_GELU && GST && !ZP) {
+    } else if (EPI == P2V_EPI_GELU && GST) {
       // step tables (common.cuh: gelu_steps_code): ~19 instructions per column (9 ALU-pipe, 8 FMA-pipe) instead of ~40 for erff.  No branch inside the
       // chunk, so the 16 columns' lookup chains (two dependent shared-memory loads each) overlap; the near-threshold test is
       // taken once per chunk, after the loop.
       uint32_t q[4];
+      int zc[4] = {0, 0, 0, 0};
+      if (ZP) {
+        const float4 z4 = *reinterpret_cast<const float4*>(prmg + PR_ZC * 64 + j4);
+        zc[0] = __float_as_int(z4.x); zc[1] = __float_as_int(z4.y); zc[2] = __float_as_int(z4.z); zc[3] = __float_as_int(z4.w);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float af = __int2float_rn(acc[j4 + e]);
+        const float af = __int2float_rn(acc[j4 + e] - zc[e]);
         q[e] = gelu_steps_code<GST == 1>(POT ? __fmaf_rn(af, Sv[e], Bv[e]) : fadd(fmul(af, Sv[e]), Bv[e]), gst, gst_near);
       }
       ow[j4 >> 2] = pack4_low_bytes(q[0], q[1], q[2], q[3]);
@@ -308,7 +313,7 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
     }
     ow[j4 >> 2] = pack4_sat(t[0], t[1], t[2], t[3]);
   }
-  if (EPI == P2V_EPI_GELU && GST == 1 && !ZP) {
+  if (EPI == P2V_EPI_GELU && GST == 1) {
     if (gst_near <= 16u) {     // some y within 8 ulps of the threshold it consulted: the chunk takes the direct evaluation
 #pragma unroll 1
       for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -319,10 +324,16 @@ __device__ __forceinline__ void pair_chunk(const float* __restrict__ prmg, const
         const int a1 = j4 == 0 ? acc[1] : j4 == 4 ? acc[5] : j4 == 8 ? acc[9] : acc[13];
         const int a2 = j4 == 0 ? acc[2] : j4 == 4 ? acc[6] : j4 == 8 ? acc[10] : acc[14];
         const int a3 = j4 == 0 ? acc[3] : j4 == 4 ? acc[7] : j4 == 8 ? acc[11] : acc[15];
+        int z0 = 0, z1 = 0, z2 = 0, z3 = 0;
+        if (ZP) {
+          const float4 z4 = *reinterpret_cast<const float4*>(prmg + PR_ZC * 64 + j4);
+          z0 = __float_as_int(z4.x); z1 = __float_as_int(z4.y); z2 = __float_as_int(z4.z); z3 = __float_as_int(z4.w);
+        }
         auto code = [&](int a, float S, float B, float R) {
-          return POT ? gelu_code_direct(__fmaf_rn(__int2float_rn(a), S, B), R) : gelu_code_div(fadd(fmul(__int2float_rn(a), S), B), R);
+          return POT ? gelu_code_direct(__fmaf_rn(__int2float_rn(a), S, B), R) : gelu_code_div(fadd(fmul(__int2float_rn(a), S), B), R, out_zp);
         };
-        const uint32_t w = pack4_sat_int(code(a0, S4.x, B4.x, R4.x), code(a1, S4.y, B4.y, R4.y), code(a2, S4.z, B4.z, R4.z), code(a3, S4.w, B4.w, R4.w));
+        const uint32_t w = pack4_sat_int(code(a0 - z0, S4.x, B4.x, R4.x), code(a1 - z1, S4.y, B4.y, R4.y), code(a2 - z2, S4.z, B4.z, R4.z),
+                                         code(a3 - z3, S4.w, B4.w, R4.w));
         if (j4 == 0) ow[0] = w; else if (j4 == 4) ow[1] = w; else if (j4 == 8) ow[2] = w; else ow[3] = w;
       }
     }
@@ -766,7 +777,7 @@ static int launch_pair(const p2v_gemm_args& a, const PairGeom& g, const CUtensor
 int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
   P2V_REQUIRE(gemm_pair_supported(a), "gemm_pair: unsupported arguments");
   const bool pot = a.pot_scales != 0;
-  const bool gst = a.epilogue == P2V_EPI_GELU && a.gelu_table && (pot || (a.zp_corr == nullptr && a.out_zp == 0.f));
+  const bool gst = a.epilogue == P2V_EPI_GELU && a.gelu_table;        // the table was built for this out_scale / out_zp (caller's contract)
   const bool zpv = !pot && (a.zp_corr != nullptr || a.out_zp != 0.f);
   const int rows = a.epilogue == P2V_EPI_RESIDUAL ? (zpv ? prm_rows<P2V_EPI_RESIDUAL, false, true>() : prm_rows<P2V_EPI_RESIDUAL, true>())
                    : a.epilogue == P2V_EPI_GELU   ? (pot ? prm_rows<P2V_EPI_GELU, true>() : prm_rows<P2V_EPI_GELU, false>())
@@ -793,7 +804,10 @@ int launch_gemm_pair(const p2v_gemm_args& a, cudaStream_t stream) {
   if (zpv) {
     switch (a.epilogue) {
       case P2V_EPI_REQUANT: return launch_pair<P2V_EPI_REQUANT, false, 0, true>(a, g, tmA, tmB, tmO, tmR, stream);
-      case P2V_EPI_GELU: return launch_pair<P2V_EPI_GELU, false, 0, true>(a, g, tmA, tmB, tmO, tmR, stream);
+      case P2V_EPI_GELU:
+        if (gst) return gelu_table_is_clean(a.gelu_table) ? launch_pair<P2V_EPI_GELU, false, 2, true>(a, g, tmA, tmB, tmO, tmR, stream)
+                                                          : launch_pair<P2V_EPI_GELU, false, 1, true>(a, g, tmA, tmB, tmO, tmR, stream);
+        return launch_pair<P2V_EPI_GELU, false, 0, true>(a, g, tmA, tmB, tmO, tmR, stream);
       default: return launch_pair<P2V_EPI_RESIDUAL, false, 0, true>(a, g, tmA, tmB, tmO, tmR, stream);
     }
   }

@@ -146,8 +146,8 @@ class VitPlan:
             p["fc1_out"] = _vec(m1, p["fc1"].N, dev)
             p["fc1_zp"] = z_m1
             p["fc1_pot"] = intmath.is_pot(m1) and not (z_m0 or z_m1)
-            # step tables for any symmetric output scale (thresholds from the reference's own division); zero points: direct erf
-            p["gelu_tab"] = ops.gelu_table(float(m1), dev) if not (z_m0 or z_m1) else None
+            # step tables for any output quantizer (thresholds bisected on the reference's own fl(gelu / scale) + zp)
+            p["gelu_tab"] = ops.gelu_table(float(m1), dev, zp=float(z_m1))
             p["fc2"] = _Gemm(mlp.fc2, mlp.fc2.weight, b4[3], m1, dev, z_m1)
             p["fc2_mid"] = _vec(_sym_scale(mlp.qact2, "mlp.qact2"), D, dev)
             s_b4 = _vec(_sym_scale(blk.qact4, "block.qact4"), D, dev)

@@ -117,13 +117,16 @@ def gemm_args(A, W, epilogue, acc_scale, bias=None, out_scale=None, mid_scale=No
 _gelu_tables = {}
 
 
-def gelu_table(out_scale, device):
-    """device-resident step table of y -> qact(gelu(y)) for a symmetric output scale (None if the scale is not tabulable); a scale
-    that is not a power of two gets the CTA-pair kernel's form only; cached per (scale, device)"""
-    key = (float(out_scale), str(device))
+def gelu_table(out_scale, device, zp=0.0):
+    """device-resident step table of y -> qact(gelu(y)) for an output quantizer (scale, zero point); None if it is not tabulable.
+    A scale that is not a power of two or a zero point gets the CTA-pair kernel's form only; cached per (scale, zp, device)"""
+    key = (float(out_scale), float(zp), str(device))
     if key not in _gelu_tables:
         t = torch.empty(_lib.GELU_TABLE_BYTES, dtype=torch.uint8, device=device)
-        rc = _lib.load().p2v_build_gelu_table(float(out_scale), ptr(t), stream())
+        if zp:
+            rc = _lib.load().p2v_build_gelu_table_zp(float(out_scale), float(zp), ptr(t), stream())
+        else:
+            rc = _lib.load().p2v_build_gelu_table(float(out_scale), ptr(t), stream())
         if rc not in (0, 3):
             check(rc, "build_gelu_table")
         _gelu_tables[key] = t if rc == 0 else None

@@ -237,6 +237,40 @@ def test_gemm_pair_gelu_step_tables_any_scale(so):
         ops.set_gemm_variant(0)
 
 
+@pytest.mark.parametrize("so,zp", [(0.0263, -122.0), (0.031, -120.0), (0.05, 5.0), (2.0 ** -5, -128.0), (0.0871, -126.0)])
+def test_gemm_pair_gelu_step_tables_zero_point(so, zp):
+    """asymmetric output quantizer after GELU (omse: zero point near -128, the lowest codes saturate): step tables built on
+    fl(gelu(y) / scale) + zp must reproduce the CTA-pair kernel's direct erf epilogue bit for bit, input zero point included"""
+    tab = ops.gelu_table(so, DEV, zp=zp)
+    if tab is None:
+        pytest.skip("(%g, %g) is not tabulated" % (so, zp))
+    M, N, K = 2048 + 77, 256, 64
+    A, W, _ = _gemm_inputs(M, N, K, 195)
+    Ad, Wd = A.to(DEV), W.to(DEV)
+    zc = (7 * W.long().sum(dim=1)).to(torch.int32).to(DEV)
+    outs = torch.full((N,), so, device=DEV)
+    cases = ((1.37e-4, torch.randn(N) * 0.5), (1.7e-5, torch.linspace(-9.0, 5.0, N)), (9.1e-7, torch.linspace(-1.5, 0.5, N)),
+             (3.3e-6, torch.linspace(-0.9, -0.6, N)), (4.1e-3, torch.randn(N) * 3), (2.9e-7, torch.linspace(-4.0, (130.0 - zp) * so, N)))
+    seen = set()
+    try:
+        ops.set_gemm_variant(2)
+        for acc_scale, bias in cases:
+            s = (torch.full((N,), acc_scale) * (1.0 + 0.1 * torch.rand(N))).to(DEV)
+            res = []
+            for table in (None, tab):
+                o8 = torch.empty(M, N, dtype=torch.int8, device=DEV)
+                ops.gemm(ops.gemm_args(Ad, Wd, ops.EPI_GELU, s, bias=bias.to(DEV), out_scale=outs, out_i8=o8, pot=False, gelu_table=table,
+                                       zp_corr=zc, out_zp=zp))
+                res.append(o8)
+            torch.cuda.synchronize()
+            assert torch.equal(res[0], res[1]), "acc_scale %g: %d codes differ between step tables and direct erf" % (
+                acc_scale, int((res[0] != res[1]).sum()))
+            seen.update(torch.unique(res[0]).tolist())
+        assert len(seen) > 40, "the cases must exercise many output codes (%d seen)" % len(seen)
+    finally:
+        ops.set_gemm_variant(0)
+
+
 def test_gelu_table_rejects_unsupported_scales():
     assert ops.gelu_table(0.3, DEV) is None and ops.gelu_table(2.0 ** -9, DEV) is None
 
