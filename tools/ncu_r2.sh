@@ -1,6 +1,7 @@
 #!/bin/bash
 # round-2 evidence for the headline workload: launch list of one bench run + one full capture of the step's kernels (one forward)
 export PYTHONPATH=$PWD
+export P2VIT_ATT_AUTOTUNE=0     # the engine would otherwise time both attention probability paths per layer inside the listed run (extra launches); DeiT-S keeps mode 0 anyway
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --configs none --sustain 0 --golden-state"
 $CMD > gpurun_out/plain_r2.log 2>&1 &&
