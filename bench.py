@@ -579,6 +579,18 @@ def main():
     if not is_swin:      # achieved int8 TOP/s of each block GEMM kind (2 * MACs / device time)
         kind_macs = {"gemm_qkv": 3 * D * D, "gemm_proj": D * D, "gemm_fc1": 4 * D * D, "gemm_fc2": 4 * D * D}
         roof["gemm_tops_by_kind"] = {k: round(2.0 * L * B * T1 * m / (fine_ms[k] * 1e-3) / 1e12, 1) for k, m in kind_macs.items() if fine_ms.get(k)}
+    if not is_swin:      # the row kernels against the HBM roofline: algorithmic int8 bytes in + out / device time / measured copy bandwidth
+        hv = {}
+        if fam_ms.get("attention"):
+            by = L * B * T1 * 4 * D                       # qkv codes in (3D), attention codes out (D), per token and layer
+            hv["attention"] = {"GB/s": round(by / (fam_ms["attention"] * 1e-3) / 1e9, 1), "frac": round(by / (fam_ms["attention"] * 1e-3) / 1e9 / hbm_gbs, 4)}
+        if fam_ms.get("layernorm"):
+            by = 2 * L * B * T1 * D * 2                   # two LayerNorms per block, codes in + codes out
+            hv["layernorm"] = {"GB/s": round(by / (fam_ms["layernorm"] * 1e-3) / 1e9, 1), "frac": round(by / (fam_ms["layernorm"] * 1e-3) / 1e9 / hbm_gbs, 4)}
+        if fam_ms.get("patchify"):
+            by = B * 3 * 224 * 224 * 5                    # fp32 pixels in, int8 codes out
+            hv["patchify"] = {"GB/s": round(by / (fam_ms["patchify"] * 1e-3) / 1e9, 1), "frac": round(by / (fam_ms["patchify"] * 1e-3) / 1e9 / hbm_gbs, 4)}
+        roof["hbm_view"] = {"peak_GB/s": hbm_gbs, "note": "neither attention nor LayerNorm is HBM-bound: both are bound by the bit-exact integer arithmetic per element (DESIGN.md 3.2, 3.5)", **hv}
     roof["tensor_fraction_of_whole_forward"] = 2.0 * macs * value / world / (i8_sus * 1e12)      # whole step vs the SUSTAINED int8 peak
     roof["int8_peak"] = {"burst_tops": i8_burst, "sustained_tops": i8_sus, "source": i8_src}
 
