@@ -565,6 +565,29 @@ def test_attention_probability_modes_agree(s_as):
     assert int(outs[0].float().abs().sum()) > 0
 
 
+@pytest.mark.parametrize("T", [197, 220, 64])
+@pytest.mark.parametrize("zps", [(-3, 5.0, -7.0), (-128, -4.0, 9.0), (0, 0.0, 6.0)])
+def test_attention_zero_points_tcgen05_vs_dp4a(T, zps):
+    """asymmetric qact1 / qact_attn1 / qact2 (omse) on the tcgen05 kernel against the dp4a kernel: T = 197 keeps the constant atom in
+    the K tile's unused tail (two CTAs per SM), T = 220 fills the K tile and takes the atom behind the barriers (one CTA per SM);
+    z = -128 has no int8 negative (the correction MMAs are issued twice with the byte 64); both probability paths"""
+    B, H = 3, 3
+    D = H * 64
+    g = torch.Generator().manual_seed(T + 1000)
+    qkv = torch.randint(-60, 61, (B, T, 3, H, 64), generator=g, dtype=torch.int32).to(torch.int8).to(DEV)
+    s_as = 0.61
+    lut = intmath.lut_to_device(intmath.build_softmax_lut(torch.tensor([s_as])), DEV)
+    m1, m2 = 0.0137 * 0.0137 * 0.125 / s_as, 0.0137 / 0.0131 / 32768.0
+    ref = torch.full((B * T, D), 77, dtype=torch.int8, device=DEV)
+    ops.attention(ops.attention_args(qkv, ref, B, T, H, 64, m1, m2, lut, zp_qkv=zps[0], zp_score=zps[1], zp_out=zps[2]), simt=True)
+    for mode in (0, 1):
+        out = torch.full((B * T, D), 55, dtype=torch.int8, device=DEV)
+        ops.attention(ops.attention_args(qkv, out, B, T, H, 64, m1, m2, lut, zp_qkv=zps[0], zp_score=zps[1], zp_out=zps[2], prob_mode=mode))
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref), "mode %d: %d codes differ from the dp4a kernel" % (mode, int((out != ref).sum()))
+    assert len(torch.unique(ref)) > 8
+
+
 @pytest.mark.parametrize("B,T,H,dh", [(2, 197, 3, 64), (3, 49, 2, 32), (1, 197, 6, 64)])
 def test_attention_vs_oracle(B, T, H, dh):
     D = H * dh
