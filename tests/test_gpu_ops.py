@@ -506,6 +506,49 @@ def test_layernorm_int_vs_oracle(C, pot):
     assert torch.equal(o8.cpu().float(), ref_q)
 
 
+@pytest.mark.parametrize("C", [96, 192, 384, 768, 1024])
+@pytest.mark.parametrize("pot,clamp_mid,zp", [(True, False, 0.0), (True, True, 0.0), (False, False, 0.0), (False, True, 0.0), (False, False, -11.0)])
+def test_layernorm_row_persistent_kernels_vs_generic_kernel(C, pot, clamp_mid, zp):
+    """The row-persistent kernels (layernorm_pot_kernel for power-of-two scales, layernorm_np_kernel for raw fp32 scales, with or
+    without a zero point of the next QAct) run when only int8 codes are asked for; with an fp32 output as well the generic kernel
+    runs.  Same codes bit for bit - on random rows, rows of equal values (std = 0), single spikes, and a row count that leaves
+    the last warp's lane groups without a row (C = 96 / 192: 4 / 2 rows per warp)."""
+    torch.manual_seed(C + 7)
+    rows = 197 * 2 + 3
+    fac = torch.tensor([1.0, 2.0, 4.0, 8.0])
+    in_scale = 0.0137 * fac[torch.randint(0, 4, (C,))]
+    in_scale[0] = 0.0137
+    codes = _rand_codes(rows, C, seed=C + 1)
+    codes[5] = 17                       # std = 0 (an all-zero row is 0 / 0 in the reference: NaN, not a defined case)
+    codes[7] = 0
+    codes[7, C // 2] = 127              # one spike
+    codes[rows - 1] = -128
+    cs = 2.0 ** torch.randint(-3, 3, (C,)).float()
+    nxt = 2.0 ** -6 if pot else 0.0173
+    gamma, beta = 1 + 0.2 * torch.randn(C), 0.2 * torch.randn(C)
+    gamma[3] = -gamma[3]
+    out_scale = (torch.tensor([nxt]) * cs)
+    if not pot:
+        out_scale = out_scale * (1.0 + 0.3 * torch.rand(C))
+    dev = lambda t: t.to(DEV)
+    common = (dev(codes), rows, C, C, dev((in_scale / in_scale.min()).round()), float(in_scale.min()), dev(gamma), dev(beta), dev(out_scale), dev(cs), nxt, pot)
+    fast = torch.full((rows, C), 77, dtype=torch.int8, device=DEV)
+    ops.layernorm(ops.layernorm_args(*common, out_i8=fast, clamp_mid=clamp_mid, next_zp=zp))
+    gen = torch.full((rows, C), 55, dtype=torch.int8, device=DEV)
+    of = torch.empty(rows, C, device=DEV)
+    ops.layernorm(ops.layernorm_args(*common, out_i8=gen, out_f32=of, clamp_mid=clamp_mid, next_zp=zp))
+    torch.cuda.synchronize()
+    assert torch.equal(fast, gen), "%d codes differ between the row-persistent and the generic kernel (rows %s)" % (
+        int((fast != gen).sum()), sorted(set((fast != gen).nonzero()[:, 0].tolist()))[:8])
+    if not clamp_mid:
+        x = (codes.float() * in_scale).reshape(1, rows, C)
+        ref_f = port.int_layernorm(x, in_scale, out_scale, gamma, beta, exact_sums=True).reshape(rows, C)
+        ref_q = (((ref_f / cs) / nxt) + zp).round().clamp(-128, 127)
+        ok = torch.isfinite(ref_f).all(dim=1)          # std = 0 rows divide by zero in the reference; kernels agree with each other above
+        assert torch.equal(fast.cpu().float()[ok], ref_q[ok])
+    assert len(torch.unique(fast)) > 16
+
+
 def test_layernorm_cls_rows_only():
     torch.manual_seed(7)
     B, T1, C = 5, 197, 192
