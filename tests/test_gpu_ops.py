@@ -549,6 +549,28 @@ def test_layernorm_row_persistent_kernels_vs_generic_kernel(C, pot, clamp_mid, z
     assert len(torch.unique(fast)) > 16
 
 
+def test_layernorm_fp32_scales_constants_outside_the_fast_path():
+    """layernorm_np_kernel takes the reference-order code for every row when a constant rules out its exact shortcuts: a
+    post-divisor that is not a power of two (the quotient by it is then an IEEE division, not a multiplication)"""
+    torch.manual_seed(5)
+    rows, C = 200, 384
+    codes = _rand_codes(rows, C, seed=55)
+    in_mult = torch.ones(C)
+    gamma, beta = 1 + 0.2 * torch.randn(C), 0.2 * torch.randn(C)
+    cs = 2.0 ** torch.randint(-2, 3, (C,)).float()
+    cs[10] = 3.0
+    out_scale = 0.0173 * cs * (1.0 + 0.2 * torch.rand(C))
+    dev = lambda t: t.to(DEV)
+    common = (dev(codes), rows, C, C, dev(in_mult), 0.0137, dev(gamma), dev(beta), dev(out_scale), dev(cs), 0.0173, False)
+    fast = torch.full((rows, C), 77, dtype=torch.int8, device=DEV)
+    ops.layernorm(ops.layernorm_args(*common, out_i8=fast, next_zp=3.0))
+    gen = torch.full((rows, C), 55, dtype=torch.int8, device=DEV)
+    of = torch.empty(rows, C, device=DEV)
+    ops.layernorm(ops.layernorm_args(*common, out_i8=gen, out_f32=of, next_zp=3.0))
+    torch.cuda.synchronize()
+    assert torch.equal(fast, gen), "%d codes differ" % int((fast != gen).sum())
+
+
 def test_layernorm_cls_rows_only():
     torch.manual_seed(7)
     B, T1, C = 5, 197, 192
