@@ -710,6 +710,116 @@ static void launch_ln_np(const p2v_layernorm_args& a, cudaStream_t stream) {
   else launch_pdl(layernorm_np_kernel<LPR, WPLN, false>, dim3(blocks), dim3(128), smem, stream, a);
 }
 
+// The power-of-two kernel for rows of 6 to 8 words per lane (C = 768 .. 1024: ViT-B, ViT-L).  Its register-resident channel
+// constants (4 x 4 x WPL floats per lane) fill the 170 registers of three blocks per SM at C = 768 and spill at C = 1024 (144 bytes),
+// so this form keeps them in shared memory ([4][C / 4] float4: g', b', f, in_mult; three conflict-free LDS.128 per word and row) and
+// runs four blocks per SM: C = 1024 262 -> 191 us per 200 k rows, C = 768 40.3 -> 38.0 us per 50 k rows; below that the registers win
+// (C = 512 30.2 vs 34.9 us, C = 384 22.3 vs 27.0 us).  Same arithmetic, same helper functions, same slow path as layernorm_pot_kernel.
+template <int WPLN, bool CLAMP_MID>
+__global__ void __launch_bounds__(128, 4) layernorm_pot_smem_kernel(p2v_layernorm_args a) {
+  extern __shared__ float4 ln_ps_sm[];
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row_stride = gridDim.x * (blockDim.x >> 5);
+  const int nw = a.C >> 2;
+  const float rnext = fdiv(1.f, a.next_scale);
+  for (int w = threadIdx.x; w < nw; w += blockDim.x) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma) + w), b4 = __ldg(reinterpret_cast<const float4*>(a.beta) + w);
+    const float4 o4 = __ldg(reinterpret_cast<const float4*>(a.out_scale) + w), p4 = __ldg(reinterpret_cast<const float4*>(a.post_div) + w);
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, oo[4] = {o4.x, o4.y, o4.z, o4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+    float g[4], bt[4], f[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ros = fdiv(1.f, oo[e]);
+      g[e] = fmul(gg[e], ros);
+      bt[e] = fmul(bb[e], ros);
+      f[e] = fmul(fmul(oo[e], fdiv(1.f, pp[e])), rnext);
+    }
+    ln_ps_sm[w] = make_float4(g[0], g[1], g[2], g[3]);
+    ln_ps_sm[nw + w] = make_float4(bt[0], bt[1], bt[2], bt[3]);
+    ln_ps_sm[2 * nw + w] = make_float4(f[0], f[1], f[2], f[3]);
+    ln_ps_sm[3 * nw + w] = __ldg(reinterpret_cast<const float4*>(a.in_mult) + w);
+  }
+  __syncthreads();
+  int sh[WPLN][4];
+  float gmin = __int_as_float(0x7f800000), gmax = 0.f;
+#pragma unroll
+  for (int i = 0; i < WPLN; ++i) {
+    const float4 g4 = ln_ps_sm[lane + 32 * i], m4 = ln_ps_sm[3 * nw + lane + 32 * i];
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      gmin = fminf(gmin, fabsf(gg[e])); gmax = fmaxf(gmax, fabsf(gg[e]));
+      sh[i][e] = int(mm[e]);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gmin = fminf(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+    gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+  }
+  const float Cf = float(a.C), s1 = a.in_scale_min, s1c = fdiv(s1, Cf);
+  const float clamp_hi = a.clamp_mid ? 127.f : __int_as_float(0x7f800000);
+  pdl_wait();
+  pdl_trigger();
+  if (warp_global >= a.rows) return;
+  auto load_row = [&](int row, uint32_t (&u)[WPLN]) {
+    const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) u[i] = __ldg(xr + lane + 32 * i);
+  };
+  uint32_t ucur[WPLN], unext[WPLN];
+  load_row(warp_global, ucur);
+  for (int row = warp_global; row < a.rows; row += row_stride) {
+    if (row + row_stride < a.rows) load_row(row + row_stride, unext);
+    int xv[WPLN][4];
+    int S1 = 0, S2 = 0;
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) {
+      xv[i][0] = int(int8_t(ucur[i] & 0xff)) * sh[i][0];
+      xv[i][1] = int(int8_t((ucur[i] >> 8) & 0xff)) * sh[i][1];
+      xv[i][2] = int(int8_t((ucur[i] >> 16) & 0xff)) * sh[i][2];
+      xv[i][3] = int(int8_t(ucur[i] >> 24)) * sh[i][3];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { S1 += xv[i][e]; S2 += xv[i][e] * xv[i][e]; }
+      ucur[i] = unext[i];
+    }
+    group_sum2<32>(S1, S2);
+    const float S1f = float(S1), S2f = float(S2);
+    const float mean = fmul(fdiv(S1f, Cf), s1);
+    const float stdv = fmul(s1c, __fsqrt_rn(fsub(fmul(Cf, S2f), fmul(S1f, S1f))));
+    const float t = fdiv(s1, stdv);
+    const float mos = fdiv(mean, stdv);
+    uint32_t* orow = reinterpret_cast<uint32_t*>(a.out_i8 + int64_t(a.out_row_map ? __ldg(a.out_row_map + row) : row) * a.C);
+    const bool in_range = fmul(t, gmax) < 256.f && fmul(t, gmin) >= 0x1p-24f;
+    uint32_t qw[WPLN];
+    uint32_t mant_max = 0;
+    if (in_range) {
+#pragma unroll
+      for (int i = 0; i < WPLN; ++i) {
+        const int w = lane + 32 * i;
+        const float4 g4 = ln_ps_sm[w], b4 = ln_ps_sm[nw + w], f4 = ln_ps_sm[2 * nw + w];
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w}, f[4] = {f4.x, f4.y, f4.z, f4.w};
+        qw[i] = ln_pot_fast_word<CLAMP_MID>(t, mos, g, bt, f, xv[i], mant_max);
+      }
+    }
+    if (!in_range || mant_max >= 0x007ffff0u) {
+      ln_pot_row_slow(a, row, orow, lane, 32, WPLN, t, mos, clamp_hi);
+    } else {
+#pragma unroll
+      for (int i = 0; i < WPLN; ++i) orow[lane + 32 * i] = qw[i];
+    }
+  }
+}
+template <int WPLN>
+static void launch_ln_pot_smem(const p2v_layernorm_args& a, cudaStream_t stream) {
+  const size_t smem = size_t(a.C) * 16;
+  const int blocks = std::max(1, std::min((a.rows + 3) / 4, num_sms() * 4));
+  pdl_next_kind(PDL_LAYERNORM);
+  if (a.clamp_mid) launch_pdl(layernorm_pot_smem_kernel<WPLN, true>, dim3(blocks), dim3(128), smem, stream, a);
+  else launch_pdl(layernorm_pot_smem_kernel<WPLN, false>, dim3(blocks), dim3(128), smem, stream, a);
+}
+
 template <int LPR, int WPLN, bool CLAMP_MID, bool GATHER = false>
 static void launch_ln_pot_c(const p2v_layernorm_args& a, cudaStream_t stream) {
   constexpr int GPW = 32 / LPR;
@@ -752,7 +862,18 @@ int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
     // lanes per row: as many as leave a lane >= 12 channels (3 words) - more rows in flight per SM beat the amortisation of
     // the per-row scalar work (C = 384: 32 lanes x 3 words 26.8 us vs 16 x 6 32.9 us for 50 k rows, tools/ln_bench.py)
 #define P2V_LN_POT(LPR_, N_) case N_: launch_ln_pot<LPR_, N_>(a, stream); break;
-    if (nwords % 32 == 0 && nwords / 32 >= 3 && nwords / 32 <= 8) {
+    static const bool big_regs = getenv("P2V_LN_BIG_REGS") && atoi(getenv("P2V_LN_BIG_REGS")) != 0;     // triage: register-resident constants at C = 896 / 1024 too
+    static const int smem_min = getenv("P2V_LN_SMEM_MIN") ? atoi(getenv("P2V_LN_SMEM_MIN")) : 6;       // triage; measured: 768 38.0 vs 40.3 us, 640 equal, 512 / 384 slower
+    if (nwords % 32 == 0 && nwords / 32 >= smem_min && nwords / 32 >= 3 && nwords / 32 <= 8 && !big_regs) {
+      switch (nwords / 32) {
+        case 3: launch_ln_pot_smem<3>(a, stream); break;
+        case 4: launch_ln_pot_smem<4>(a, stream); break;
+        case 5: launch_ln_pot_smem<5>(a, stream); break;
+        case 6: launch_ln_pot_smem<6>(a, stream); break;
+        case 7: launch_ln_pot_smem<7>(a, stream); break;
+        default: launch_ln_pot_smem<8>(a, stream); break;
+      }
+    } else if (nwords % 32 == 0 && nwords / 32 >= 3 && nwords / 32 <= 8) {
       switch (nwords / 32) { P2V_LN_POT(32, 3) P2V_LN_POT(32, 4) P2V_LN_POT(32, 5) P2V_LN_POT(32, 6) P2V_LN_POT(32, 7) P2V_LN_POT(32, 8) }
     } else if (nwords % 16 == 0 && nwords / 16 >= 3 && nwords / 16 <= 6 && a.rows >= 2) {
       switch (nwords / 16) { P2V_LN_POT(16, 3) P2V_LN_POT(16, 4) P2V_LN_POT(16, 5) P2V_LN_POT(16, 6) }
