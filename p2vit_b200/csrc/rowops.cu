@@ -862,9 +862,8 @@ int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
     // lanes per row: as many as leave a lane >= 12 channels (3 words) - more rows in flight per SM beat the amortisation of
     // the per-row scalar work (C = 384: 32 lanes x 3 words 26.8 us vs 16 x 6 32.9 us for 50 k rows, tools/ln_bench.py)
 #define P2V_LN_POT(LPR_, N_) case N_: launch_ln_pot<LPR_, N_>(a, stream); break;
-    static const bool big_regs = getenv("P2V_LN_BIG_REGS") && atoi(getenv("P2V_LN_BIG_REGS")) != 0;     // triage: register-resident constants at C = 896 / 1024 too
     static const int smem_min = getenv("P2V_LN_SMEM_MIN") ? atoi(getenv("P2V_LN_SMEM_MIN")) : 6;       // triage; measured: 768 38.0 vs 40.3 us, 640 equal, 512 / 384 slower
-    if (nwords % 32 == 0 && nwords / 32 >= smem_min && nwords / 32 >= 3 && nwords / 32 <= 8 && !big_regs) {
+    if (nwords % 32 == 0 && nwords / 32 >= smem_min && nwords / 32 >= 3 && nwords / 32 <= 8) {
       switch (nwords / 32) {
         case 3: launch_ln_pot_smem<3>(a, stream); break;
         case 4: launch_ln_pot_smem<4>(a, stream); break;
