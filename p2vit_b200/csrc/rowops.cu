@@ -715,8 +715,8 @@ static void launch_ln_np(const p2v_layernorm_args& a, cudaStream_t stream) {
 // so this form keeps them in shared memory ([4][C / 4] float4: g', b', f, in_mult; three conflict-free LDS.128 per word and row) and
 // runs four blocks per SM: C = 1024 262 -> 191 us per 200 k rows, C = 768 40.3 -> 38.0 us per 50 k rows; below that the registers win
 // (C = 512 30.2 vs 34.9 us, C = 384 22.3 vs 27.0 us).  Same arithmetic, same helper functions, same slow path as layernorm_pot_kernel.
-template <int WPLN, bool CLAMP_MID>
-__global__ void __launch_bounds__(128, 4) layernorm_pot_smem_kernel(p2v_layernorm_args a) {
+template <int WPLN, bool CLAMP_MID, bool GATHER = false>
+__global__ void __launch_bounds__(128, WPLN <= 8 ? 4 : 3) layernorm_pot_smem_kernel(p2v_layernorm_args a) {
   extern __shared__ float4 ln_ps_sm[];
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -763,10 +763,19 @@ __global__ void __launch_bounds__(128, 4) layernorm_pot_smem_kernel(p2v_layernor
   pdl_wait();
   pdl_trigger();
   if (warp_global >= a.rows) return;
+  // gathered input (patch merging): segment and offset of each of the lane's words are row independent
+  int gseg[GATHER ? WPLN : 1], goff[GATHER ? WPLN : 1];
+  if (GATHER) {
+    const int seg_words = a.C / (4 * a.gather_segs);
+#pragma unroll
+    for (int i = 0; i < WPLN; ++i) { gseg[i] = (lane + 32 * i) / seg_words; goff[i] = (lane + 32 * i) - gseg[i] * seg_words; }
+  }
   auto load_row = [&](int row, uint32_t (&u)[WPLN]) {
     const uint32_t* xr = reinterpret_cast<const uint32_t*>(a.x + int64_t(row) * a.x_row_stride);
 #pragma unroll
-    for (int i = 0; i < WPLN; ++i) u[i] = __ldg(xr + lane + 32 * i);
+    for (int i = 0; i < WPLN; ++i)
+      u[i] = GATHER ? __ldg(reinterpret_cast<const uint32_t*>(a.x + int64_t(__ldg(a.in_gather + int64_t(row) * a.gather_segs + gseg[GATHER ? i : 0])) * a.x_row_stride) + goff[GATHER ? i : 0])
+                    : __ldg(xr + lane + 32 * i);
   };
   uint32_t ucur[WPLN], unext[WPLN];
   load_row(warp_global, ucur);
@@ -819,6 +828,14 @@ static void launch_ln_pot_smem(const p2v_layernorm_args& a, cudaStream_t stream)
   if (a.clamp_mid) launch_pdl(layernorm_pot_smem_kernel<WPLN, true>, dim3(blocks), dim3(128), smem, stream, a);
   else launch_pdl(layernorm_pot_smem_kernel<WPLN, false>, dim3(blocks), dim3(128), smem, stream, a);
 }
+// patch-merging form (gathered rows, no clamp): the wide merges (4C = 768 .. 1536)
+template <int WPLN>
+static void launch_ln_pot_smem_gather(const p2v_layernorm_args& a, cudaStream_t stream) {
+  const size_t smem = size_t(a.C) * 16;
+  const int blocks = std::max(1, std::min((a.rows + 3) / 4, num_sms() * (WPLN <= 8 ? 4 : 3)));
+  pdl_next_kind(PDL_LAYERNORM);
+  launch_pdl(layernorm_pot_smem_kernel<WPLN, false, true>, dim3(blocks), dim3(128), smem, stream, a);
+}
 
 template <int LPR, int WPLN, bool CLAMP_MID, bool GATHER = false>
 static void launch_ln_pot_c(const p2v_layernorm_args& a, cudaStream_t stream) {
@@ -844,12 +861,13 @@ int launch_layernorm(const p2v_layernorm_args& a, cudaStream_t stream) {
   if (a.in_gather && a.pot_scales && a.out_i8 && !a.clamp_mid && nwords % 32 == 0 && nwords / 32 >= 3 && nwords / 32 <= 12) {
     // patch-merging LayerNorm (4C = 384 / 768 / 1536 for Swin-T/S, 512 / 1024 / 2048 for Swin-B): gathered instantiations
     bool done = true;
+    static const bool gather_smem = !(getenv("P2V_LN_SMEM_MIN") && atoi(getenv("P2V_LN_SMEM_MIN")) > 8);      // triage: 9 = register form everywhere
     switch (nwords / 32) {
       case 3: launch_ln_pot_c<32, 3, false, true>(a, stream); break;
       case 4: launch_ln_pot_c<32, 4, false, true>(a, stream); break;
-      case 6: launch_ln_pot_c<32, 6, false, true>(a, stream); break;
-      case 8: launch_ln_pot_c<32, 8, false, true>(a, stream); break;
-      case 12: launch_ln_pot_c<32, 12, false, true>(a, stream); break;
+      case 6: if (gather_smem) launch_ln_pot_smem_gather<6>(a, stream); else launch_ln_pot_c<32, 6, false, true>(a, stream); break;
+      case 8: if (gather_smem) launch_ln_pot_smem_gather<8>(a, stream); else launch_ln_pot_c<32, 8, false, true>(a, stream); break;
+      case 12: if (gather_smem) launch_ln_pot_smem_gather<12>(a, stream); else launch_ln_pot_c<32, 12, false, true>(a, stream); break;
       default: done = false;
     }
     if (done) {
