@@ -113,7 +113,7 @@ __device__ __forceinline__ void quarter_exchange_sync(uint32_t quarter) {
 // wavefronts (the table lookups run at 2.3-3.1 wavefronts per ideal one, random indices in 32 lanes), three FADDs more per score.
 // Neither the instruction count of pass 2 (146 -> 95 per 16-score unit with the subnormal-address FFMA below: 101 -> 97 us) nor
 // the wavefront count is what bounds the kernel: with 4.5 warps per scheduler it issues one instruction per warp every 7 cycles,
-// and no single stall reason exceeds 15 % of the samples (profiles/r2_attention_stalls.txt).
+// and no single stall reason exceeds 15 % of the samples (profiles/r2a_stalls.txt, profiles/r2_stalls.txt).
 template <bool POTM, bool ZP>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
